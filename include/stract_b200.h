@@ -1,0 +1,161 @@
+/* stract_b200.h -- C ABI of libstract_b200.so: B200-native (sm_100a) replacements for Stract's
+ * two data-parallel ranking hot paths.  This is the drop-in boundary a Rust `extern "C"` block
+ *  binds; every entry point cites the reference interface it replaces
+ * (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - plain pointers + sizes; the caller owns every buffer; nothing is retained after return
+ *     except by the *_create calls, which COPY their inputs into device memory (HBM);
+ *   - input pointers may be host OR device pointers (detected with cudaPointerGetAttributes);
+ *     output pointers are host pointers unless a function says otherwise;
+ *   - every function returns 0 on success or a negative SB200_E* code; the message of the last
+ *     error on the calling thread is available from sb200_last_error(); nothing unwinds or
+ *     aborts across the boundary (reference: crate::Result / anyhow::Result);
+ *   - handles are not thread-safe: one caller at a time per handle (each owns a CUDA stream);
+ *     distinct handles may be used concurrently (reference: Collector: Sync+Send used from one
+ *     thread per segment, crates/tantivy/src/collector/mod.rs:133-152).
+ */
+#ifndef STRACT_B200_H
+#define STRACT_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SB200_API __attribute__((visibility("default")))
+#else
+#define SB200_API
+#endif
+
+#define SB200_OK 0
+#define SB200_EINVAL (-1)   /* bad argument */
+#define SB200_ECUDA (-2)    /* CUDA runtime error (message has the cudaError string) */
+#define SB200_ENOMEM (-3)   /* device or host allocation failed */
+#define SB200_ERANGE (-4)   /* input exceeds a documented limit (e.g. > 2^32-2 nodes) */
+#define SB200_ESTATE (-5)   /* call sequence error (e.g. result before run) */
+#define SB200_EFORMAT (-6)  /* malformed posting bytes */
+
+SB200_API const char* sb200_last_error(void);
+/* library version, number of kernels launched by this process so far (bench evidence) */
+SB200_API const char* sb200_version(void);
+SB200_API uint64_t sb200_kernel_launch_count(void);
+
+/* ===========================================================================================
+ * Path 1 -- webgraph harmonic centrality (HyperBall)
+ *   replaces  HarmonicCentrality::calculate(&Webgraph)  crates/core/src/webgraph/centrality/harmonic.rs:289-311
+ *   fed by    Webgraph::host_edges()/host_nodes()        crates/core/src/webgraph/mod.rs:157-194
+ *   and, with world_size > 1, the whole AMPC round loop   crates/core/src/entrypoint/ampc/harmonic_centrality/
+ * =========================================================================================== */
+typedef struct sb200_graph sb200_graph;
+
+/* Drain of `graph.host_edges()` as SoA: edge i is (from = from_hi[i]<<64|from_lo[i]) ->
+ * (to = ...), rel_flags[i] = RelFlags bits (crates/core/src/webpage/html/links.rs:114-141).
+ * Semantics reproduced from the reference iterator (crates/core/src/webgraph/store.rs:297-357):
+ *   - nodes  = every endpoint of every edge, including skipped ones;
+ *   - edges are de-duplicated on (from,to), the FIRST occurrence's rel_flags decide;
+ *   - an edge is ignored by the iteration iff rel_flags & skipped_rel_mask != 0
+ *     (SKIPPED_REL, harmonic.rs:36-49; pass SB200_SKIPPED_REL_DEFAULT for the reference's mask).
+ * The library relabels u128 ids to dense u32 indices, builds a destination-major CSR (and a
+ * source-major one for small frontiers) in HBM and keeps 2 x N x 64 B of HyperLogLog registers.
+ *
+ * Sharding (reference: one CentralityJob{shard} per worker, mapper.rs:356-369): rank `rank`
+ * of `world_size` owns the destination rows [rank*N/world, (rank+1)*N/world) balanced by edge
+ * count and keeps only their in-edges; every rank must be given the SAME full edge stream
+ * (or use sb200_graph_create with world_size=1 for a single GPU). */
+#define SB200_SKIPPED_REL_DEFAULT 0x6FED00ull /* bits 8,10,11,13-19,21,22 */
+
+SB200_API int sb200_graph_create(const uint64_t* from_lo, const uint64_t* from_hi, const uint64_t* to_lo,
+                       const uint64_t* to_hi, const uint64_t* rel_flags, uint64_t n_edges,
+                       uint64_t skipped_rel_mask, int device, int rank, int world_size,
+                       sb200_graph** out);
+SB200_API void sb200_graph_destroy(sb200_graph* g);
+
+typedef struct {
+  uint64_t n_nodes;        /* |host_nodes()| */
+  uint64_t n_edges_input;  /* edges handed to create */
+  uint64_t n_edges_kept;   /* unique, non-skipped, non-self-loop edges in the CSR (all ranks) */
+  uint64_t n_edges_local;  /* ... of which this rank owns (== kept when world_size == 1) */
+  uint64_t row_begin, row_end; /* owned destination rows, in INTERNAL (degree-sorted) order */
+  uint64_t hbm_bytes;      /* device memory held by the handle */
+  double stage_ms;         /* device time spent in create (relabel + CSR build) */
+} sb200_graph_info;
+SB200_API int sb200_graph_get_info(const sb200_graph* g, sb200_graph_info* info);
+
+/* Tuning/debug hook: which kernel family an iteration uses.  An iteration whose frontier covers
+ * >= dense_frac of the edges gathers every in-neighbour (dense pull); one whose frontier out-edges
+ * are <= E/push_div pushes from the frontier (the reference's small-frontier branch,
+ * harmonic.rs:244-252); otherwise frontier-filtered pull.  force_mode 0/1/2 pins a family (-1 = auto).
+ * All three compute the same result; negative dense_frac / non-positive push_div keep the current value. */
+SB200_API int sb200_hyperball_set_policy(sb200_graph* g, double dense_frac, double push_div, int force_mode);
+
+/* (Re)initialise the iteration state: counters seeded with each node's own id (harmonic.rs:53-73),
+ * centralities zero, frontier = all nodes (harmonic.rs:221-225). create() leaves the handle reset. */
+SB200_API int sb200_hyperball_reset(sb200_graph* g);
+
+typedef struct {
+  uint32_t t;              /* iteration index just executed (0-based) */
+  uint32_t mode;           /* 0 dense pull, 1 frontier-filtered pull, 2 push from frontier */
+  uint64_t n_changed;      /* nodes whose registers changed (this rank's rows when sharded) */
+  uint64_t edges_active;   /* edges whose source was in the frontier (0 if not tracked) */
+  float ms;                /* device time of the iteration */
+} sb200_iter_stats;
+
+/* One synchronous iteration new[v] = max(old[v], max_{u->v} old[u]) + centrality update
+ * (update_all_counters / update_changed_counters + update_centralities + Counters::step,
+ * harmonic.rs:75-176,210-212).  With world_size > 1 the caller must exchange the owned
+ * register rows between ranks after each step (see sb200_hyperball_exchange_*). */
+SB200_API int sb200_hyperball_step(sb200_graph* g, sb200_iter_stats* stats);
+
+/* calculate_centrality (harmonic.rs:215-287): iterate until an iteration changes nothing
+ * (max_iters == 0) or at most max_iters iterations.  Single-rank handles only. */
+SB200_API int sb200_hyperball_run(sb200_graph* g, uint32_t max_iters, uint32_t* iters_done,
+                        sb200_iter_stats* per_iter /* nullable, capacity cap */, uint32_t cap);
+
+/* Device time (CUDA events on the handle's stream) of the last sb200_hyperball_run call. */
+SB200_API int sb200_hyperball_last_run_ms(sb200_graph* g, float* ms);
+
+/* Per-kernel-family device timing, measured with CUDA events on the stream the kernels are launched
+ * on; `alg_bytes` is the algorithmic (not measured) HBM traffic of the family's launches: the
+ * numerator of the roofline bench.py reports (DESIGN.md states the per-unit figures). */
+typedef struct { char name[32]; uint64_t launches; double ms; double alg_bytes; } sb200_kernel_prof;
+SB200_API int sb200_hyperball_set_profiling(sb200_graph* g, int on); /* also clears the accumulators */
+SB200_API int sb200_hyperball_get_profile(sb200_graph* g, sb200_kernel_prof* out, uint32_t cap, uint32_t* n);
+
+/* HarmonicCentrality::iter() (harmonic.rs:300-302): ascending u128 id, only centrality > 0,
+ * already divided by (N-1) (normalize_centralities, harmonic.rs:178-195).  Call with
+ * centrality == NULL to get the length.  Sharded handles return only their owned nodes. */
+SB200_API int sb200_hyperball_result(sb200_graph* g, uint64_t* id_lo, uint64_t* id_hi, double* centrality,
+                           uint64_t cap, uint64_t* len);
+
+/* Parity/debug hooks: state of nodes [first, first+count) in ascending-u128-id (rank) order. */
+SB200_API int sb200_hyperball_registers(sb200_graph* g, uint64_t first, uint64_t count, uint8_t* out /* count*64 */);
+SB200_API int sb200_hyperball_kahan(sb200_graph* g, uint64_t first, uint64_t count, double* sum, double* err);
+SB200_API int sb200_graph_node_ids(sb200_graph* g, uint64_t first, uint64_t count, uint64_t* id_lo, uint64_t* id_hi);
+
+/* Multi-GPU exchange hooks (the DHT upsert `HyperLogLog64Upsert` = elementwise max,
+ * crates/core/src/ampc/dht/upsert.rs:66-83, degenerates to an all-gather because every
+ * destination row has exactly one owner).  Device pointers, valid until the next step:
+ *   regs      : the full N x 64 B "current" register array in INTERNAL row order; rows
+ *               [row_begin,row_end) were just produced by this rank; the caller all-gathers
+ *               them in place (e.g. ncclAllGather / torch.distributed.all_gather_into_tensor
+ *               over the per-rank row ranges given by sb200_graph_row_ranges).
+ *   frontier  : N-bit changed bitmap (32-bit words), this rank's rows only set by this rank;
+ *               the caller OR-reduces / all-gathers it word-aligned the same way.
+ * row ranges are aligned to 32 rows so bitmap words never straddle ranks. */
+SB200_API int sb200_hyperball_exchange_ptrs(sb200_graph* g, void** regs, uint64_t* regs_bytes,
+                                  void** frontier_words, uint64_t* frontier_bytes);
+SB200_API int sb200_graph_row_ranges(sb200_graph* g, uint64_t* begins /* world_size+1 */);
+/* after the exchange: tell the library the global changed count so every rank picks the same mode */
+SB200_API int sb200_hyperball_exchange_done(sb200_graph* g, uint64_t global_n_changed);
+
+/* ===========================================================================================
+ * Path 2 -- BM25 posting-list scoring + top-k   (declared in stract_b200_bm25.h)
+ * =========================================================================================== */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

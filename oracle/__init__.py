@@ -1,0 +1,6 @@
+"""CPU oracle (test infrastructure only -- see oracle/oracle_common.h).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this package.  It is a ctypes binding over oracle/liboracle.so (built by oracle/Makefile).
+"""
+from .pyoracle import *  # noqa: F401,F403

@@ -1,0 +1,196 @@
+// api_graph.cu -- C ABI of path 1 (see include/stract_b200.h) + process-wide error/launch accounting.
+#include "graph.cuh"
+
+#include <vector>
+
+namespace sb200 {
+static thread_local char t_err[1024] = "";
+std::atomic<uint64_t> g_launches{0};
+void set_error(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt);
+  vsnprintf(t_err, sizeof(t_err), fmt, ap);
+  va_end(ap);
+}
+int hb_alloc_state(sb200_graph* g);
+int hb_reset(sb200_graph* g);
+int hb_step(sb200_graph* g, sb200_iter_stats* st);
+int hb_result(sb200_graph* g, uint64_t* id_lo, uint64_t* id_hi, double* cent, uint64_t cap, uint64_t* len);
+int hb_registers(sb200_graph* g, uint64_t first, uint64_t count, uint8_t* out);
+int hb_kahan(sb200_graph* g, uint64_t first, uint64_t count, double* sum, double* err);
+}  // namespace sb200
+using namespace sb200;
+
+uint64_t sb200_graph::hbm_bytes() const {
+  return id_lo.bytes() + id_hi.bytes() + perm.bytes() + inv.bytes() + row_ptr.bytes() + col.bytes() + fwd_ptr.bytes() +
+         fwd_dst.bytes() + item_row.bytes() + item_start.bytes() + partial.bytes() + regs[0].bytes() + regs[1].bytes() +
+         bm[0].bytes() + bm[1].bytes() + size_cache.bytes() + kahan_sum.bytes() + kahan_err.bytes() +
+         frontier_list.bytes() + frontier_off.bytes() + cub_tmp.bytes() + counters.bytes();
+}
+
+extern "C" {
+
+const char* sb200_last_error(void) { return t_err; }
+const char* sb200_version(void) { return "stract_b200 0.1 (sm_100a)"; }
+uint64_t sb200_kernel_launch_count(void) { return g_launches.load(); }
+
+#define SB_ENTER(g)                                            \
+  if (!(g)) SB_FAIL(SB200_EINVAL, "NULL graph handle");        \
+  SB_CUDA(cudaSetDevice((g)->device))
+
+int sb200_graph_create(const uint64_t* from_lo, const uint64_t* from_hi, const uint64_t* to_lo, const uint64_t* to_hi,
+                       const uint64_t* rel_flags, uint64_t n_edges, uint64_t skipped_rel_mask, int device, int rank,
+                       int world_size, sb200_graph** out) {
+  if (!out) SB_FAIL(SB200_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (world_size < 1 || world_size > 64 || rank < 0 || rank >= world_size)
+    SB_FAIL(SB200_EINVAL, "bad rank/world_size %d/%d", rank, world_size);
+  int ndev = 0;
+  SB_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) SB_FAIL(SB200_EINVAL, "device %d not in [0,%d)", device, ndev);
+  SB_CUDA(cudaSetDevice(device));
+  sb200_graph* g = new (std::nothrow) sb200_graph();
+  if (!g) SB_FAIL(SB200_ENOMEM, "host allocation failed");
+  g->device = device; g->rank = rank; g->world = world_size;
+  int rc = SB200_OK;
+  auto body = [&]() -> int {
+    SB_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+    SB_CUDA(cudaEventCreate(&g->ev0)); SB_CUDA(cudaEventCreate(&g->ev1));
+    SB_CUDA(cudaEventCreate(&g->ev_run0)); SB_CUDA(cudaEventCreate(&g->ev_run1));
+    for (int f = 0; f < sb200_graph::F_COUNT; f++) { SB_CUDA(cudaEventCreate(&g->prof_ev[f][0])); SB_CUDA(cudaEventCreate(&g->prof_ev[f][1])); }
+    SB_TRY(stage_graph(g, from_lo, from_hi, to_lo, to_hi, rel_flags, n_edges, skipped_rel_mask));
+    g->cub_tmp.release();
+    SB_TRY(hb_alloc_state(g));
+    SB_TRY(hb_reset(g));
+    return SB200_OK;
+  };
+  rc = body();
+  if (rc != SB200_OK) { sb200_graph_destroy(g); return rc; }
+  *out = g;
+  return SB200_OK;
+}
+
+void sb200_graph_destroy(sb200_graph* g) {
+  if (!g) return;
+  cudaSetDevice(g->device);
+  if (g->stream) cudaStreamSynchronize(g->stream);
+  if (g->h_counters) cudaFreeHost(g->h_counters);
+  if (g->ev0) cudaEventDestroy(g->ev0);
+  if (g->ev1) cudaEventDestroy(g->ev1);
+  if (g->ev_run0) cudaEventDestroy(g->ev_run0);
+  if (g->ev_run1) cudaEventDestroy(g->ev_run1);
+  for (int f = 0; f < sb200_graph::F_COUNT; f++) for (int k = 0; k < 2; k++) if (g->prof_ev[f][k]) cudaEventDestroy(g->prof_ev[f][k]);
+  cudaStream_t s = g->stream;
+  delete g;  // DevBuf destructors free HBM
+  if (s) cudaStreamDestroy(s);
+}
+
+int sb200_graph_get_info(const sb200_graph* g, sb200_graph_info* info) {
+  if (!g || !info) SB_FAIL(SB200_EINVAL, "NULL argument");
+  info->n_nodes = g->N; info->n_edges_input = g->E_in; info->n_edges_kept = g->E_kept; info->n_edges_local = g->E_local;
+  info->row_begin = g->row_begin; info->row_end = g->row_end; info->hbm_bytes = g->hbm_bytes(); info->stage_ms = g->stage_ms;
+  return SB200_OK;
+}
+
+int sb200_hyperball_set_policy(sb200_graph* g, double dense_frac, double push_div, int force_mode) {
+  if (!g) SB_FAIL(SB200_EINVAL, "NULL graph handle");
+  if (dense_frac >= 0) g->dense_frac = dense_frac;
+  if (push_div > 0) g->push_div = push_div;
+  g->force_mode = force_mode;
+  return SB200_OK;
+}
+
+int sb200_hyperball_reset(sb200_graph* g) { SB_ENTER(g); return hb_reset(g); }
+
+int sb200_hyperball_step(sb200_graph* g, sb200_iter_stats* stats) { SB_ENTER(g); return hb_step(g, stats); }
+
+int sb200_hyperball_run(sb200_graph* g, uint32_t max_iters, uint32_t* iters_done, sb200_iter_stats* per_iter, uint32_t cap) {
+  SB_ENTER(g);
+  if (g->world != 1) SB_FAIL(SB200_ESTATE, "sb200_hyperball_run drives single-rank handles; sharded handles step + exchange");
+  uint32_t n = 0;
+  SB_CUDA(cudaEventRecord(g->ev_run0, g->stream));
+  // calculate_centrality loop, harmonic.rs:237-280: stop after the first iteration without changes
+  while (g->has_changes && (max_iters == 0 || g->t < max_iters)) {
+    sb200_iter_stats st;
+    SB_TRY(hb_step(g, &st));
+    if (per_iter && n < cap) per_iter[n] = st;
+    n++;
+  }
+  SB_CUDA(cudaEventRecord(g->ev_run1, g->stream));
+  SB_CUDA(cudaStreamSynchronize(g->stream));
+  cudaEventElapsedTime(&g->last_run_ms, g->ev_run0, g->ev_run1);
+  if (iters_done) *iters_done = g->t;
+  return SB200_OK;
+}
+
+int sb200_hyperball_last_run_ms(sb200_graph* g, float* ms) {
+  if (!g || !ms) SB_FAIL(SB200_EINVAL, "NULL argument");
+  *ms = g->last_run_ms;
+  return SB200_OK;
+}
+
+int sb200_hyperball_set_profiling(sb200_graph* g, int on) {
+  if (!g) SB_FAIL(SB200_EINVAL, "NULL graph handle");
+  g->profiling = on != 0;
+  for (int f = 0; f < sb200_graph::F_COUNT; f++) { g->prof_launches[f] = 0; g->prof_ms[f] = 0; g->prof_bytes[f] = 0; g->prof_used[f] = false; }
+  return SB200_OK;
+}
+
+int sb200_hyperball_get_profile(sb200_graph* g, sb200_kernel_prof* out, uint32_t cap, uint32_t* n) {
+  if (!g || !n) SB_FAIL(SB200_EINVAL, "NULL argument");
+  static const char* names[sb200_graph::F_COUNT] = {"k_pull_warp<dense>", "k_pull_quad<dense>", "k_pull_warp<frontier>",
+                                                     "k_pull_quad<frontier>", "k_pull_merge", "k_push", "k_finalize"};
+  uint32_t k = 0;
+  for (int f = 0; f < sb200_graph::F_COUNT; f++) {
+    if (out && k < cap) {
+      memset(&out[k], 0, sizeof(out[k]));
+      strncpy(out[k].name, names[f], sizeof(out[k].name) - 1);
+      out[k].launches = g->prof_launches[f]; out[k].ms = g->prof_ms[f]; out[k].alg_bytes = g->prof_bytes[f];
+    }
+    k++;
+  }
+  *n = k;
+  return SB200_OK;
+}
+
+int sb200_hyperball_result(sb200_graph* g, uint64_t* id_lo, uint64_t* id_hi, double* centrality, uint64_t cap, uint64_t* len) {
+  SB_ENTER(g);
+  if (!len) SB_FAIL(SB200_EINVAL, "len is NULL");
+  if (centrality && (!id_lo || !id_hi)) SB_FAIL(SB200_EINVAL, "id outputs are NULL");
+  return hb_result(g, id_lo, id_hi, centrality, cap, len);
+}
+
+int sb200_hyperball_registers(sb200_graph* g, uint64_t first, uint64_t count, uint8_t* out) { SB_ENTER(g); return hb_registers(g, first, count, out); }
+int sb200_hyperball_kahan(sb200_graph* g, uint64_t first, uint64_t count, double* sum, double* err) { SB_ENTER(g); return hb_kahan(g, first, count, sum, err); }
+
+int sb200_graph_node_ids(sb200_graph* g, uint64_t first, uint64_t count, uint64_t* id_lo, uint64_t* id_hi) {
+  SB_ENTER(g);
+  if (first + count > g->N) SB_FAIL(SB200_EINVAL, "range outside the node set");
+  if (!count) return SB200_OK;
+  SB_CUDA(cudaMemcpyAsync(id_lo, g->id_lo.p + first, count * 8, cudaMemcpyDefault, g->stream));
+  SB_CUDA(cudaMemcpyAsync(id_hi, g->id_hi.p + first, count * 8, cudaMemcpyDefault, g->stream));
+  SB_CUDA(cudaStreamSynchronize(g->stream));
+  return SB200_OK;
+}
+
+int sb200_hyperball_exchange_ptrs(sb200_graph* g, void** regs, uint64_t* regs_bytes, void** frontier_words, uint64_t* frontier_bytes) {
+  SB_ENTER(g);
+  if (regs) *regs = g->regs[g->cur].p;
+  if (regs_bytes) *regs_bytes = g->N * 64;
+  if (frontier_words) *frontier_words = g->bm[g->bcur].p;
+  if (frontier_bytes) *frontier_bytes = ((g->N + 31) / 32) * 4;
+  return SB200_OK;
+}
+int sb200_graph_row_ranges(sb200_graph* g, uint64_t* begins) {
+  if (!g || !begins) SB_FAIL(SB200_EINVAL, "NULL argument");
+  for (int r = 0; r <= g->world; r++) begins[r] = g->range_begins[r];
+  return SB200_OK;
+}
+int sb200_hyperball_exchange_done(sb200_graph* g, uint64_t global_n_changed) {
+  SB_ENTER(g);
+  g->n_changed_prev = global_n_changed;
+  g->has_changes = global_n_changed != 0;
+  g->exchange_pending = false;
+  return SB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,115 @@
+// common.cuh -- shared helpers of libstract_b200 (error plumbing, launch accounting, small device utils)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <atomic>
+#include <new>
+
+#include "../../include/stract_b200.h"
+
+namespace sb200 {
+
+// ---- error plumbing: nothing throws across the C ABI ---------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+struct Err {
+  int code;
+};
+
+#define SB_CUDA(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      ::sb200::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,           \
+                         cudaGetErrorString(_e));                                       \
+      return (_e == cudaErrorMemoryAllocation) ? SB200_ENOMEM : SB200_ECUDA;            \
+    }                                                                                   \
+  } while (0)
+
+#define SB_TRY(expr)           \
+  do {                         \
+    int _r = (expr);           \
+    if (_r != SB200_OK) return _r; \
+  } while (0)
+
+#define SB_FAIL(code, ...)            \
+  do {                                \
+    ::sb200::set_error(__VA_ARGS__);  \
+    return (code);                    \
+  } while (0)
+
+// every kernel launch goes through this so gpu_launches in bench.py is a counted number
+#define SB_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
+  do {                                                                    \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);           \
+    ::sb200::g_launches.fetch_add(1, std::memory_order_relaxed);          \
+  } while (0)
+
+#define SB_CHECK_LAUNCH() SB_CUDA(cudaGetLastError())
+
+// RAII device buffer (cudaMalloc); move-only
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+  }
+  int alloc(size_t count) {
+    release();
+    if (count == 0) { n = 0; return SB200_OK; }
+    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    if (e != cudaSuccess) {
+      p = nullptr;
+      set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+      cudaGetLastError();
+      return SB200_ENOMEM;
+    }
+    n = count;
+    return SB200_OK;
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+// copies `bytes` from a host-or-device pointer into device memory on `stream`
+int copy_in(void* dst_dev, const void* src_any, size_t bytes, cudaStream_t stream);
+bool is_device_ptr(const void* p);
+
+static inline unsigned div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+
+// ---- device helpers --------------------------------------------------------------------------
+__device__ __forceinline__ uint4 vmax_u8x16(uint4 a, uint4 b) {
+  return make_uint4(__vmaxu4(a.x, b.x), __vmaxu4(a.y, b.y), __vmaxu4(a.z, b.z), __vmaxu4(a.w, b.w));
+}
+__device__ __forceinline__ bool ne_u4(uint4 a, uint4 b) {
+  return ((a.x ^ b.x) | (a.y ^ b.y) | (a.z ^ b.z) | (a.w ^ b.w)) != 0u;
+}
+
+// streaming (read-once) 16-byte load: do not allocate in L1, evict-first in L2
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+}  // namespace sb200

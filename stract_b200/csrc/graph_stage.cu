@@ -1,0 +1,491 @@
+// graph_stage.cu -- staging of the webgraph edge stream into HBM.
+//
+// Replaces, on the device, what the reference does on one CPU thread every time it scans the
+// graph: `Webgraph::host_nodes()` (FxHashSet of all endpoints, crates/core/src/webgraph/mod.rs:157,
+// store.rs:338-357), `host_edges()` + `unique_by((from,to))` (store.rs:297-315) and the
+// `BTreeMap<NodeID,_>` keyed lookups of harmonic.rs:134-135.  Here it happens once:
+//   1. u128 node ids -> open-addressing hash set in HBM (128-bit CAS), compacted and sorted
+//      ascending => dense rank (the BTreeMap order of the reference's output);
+//   2. every edge mapped to (to_rank<<32 | from_rank), stable radix sort, first-of-run keeps the
+//      FIRST occurrence's rel_flags (unique_by semantics), skipped / self-loop edges dropped;
+//   3. nodes relabelled by in-degree (descending) so that rows of equal length are adjacent:
+//      the degree classes of the pull kernels become contiguous row ranges, CSR rebuilt by a
+//      second sort; a source-major CSR is built for the small-frontier (push) branch.
+// Radix sorts / scans / selects are CUB device primitives (staging, not the hot loop).
+#include "graph.cuh"
+
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <vector>
+
+namespace sb200 {
+
+typedef unsigned __int128 u128;
+
+__device__ __forceinline__ u128 cas128(u128* addr, u128 cmp, u128 val) {
+  u128 old;
+  asm volatile("atom.global.cas.b128 %0, [%1], %2, %3;" : "=q"(old) : "l"(addr), "q"(cmp), "q"(val) : "memory");
+  return old;
+}
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint64_t hash128(uint64_t lo, uint64_t hi) {
+  return mix64(lo ^ (hi * 0x9E3779B97F4A7C15ull) ^ (hi >> 29));
+}
+#define EMPTY64 0xFFFFFFFFFFFFFFFFull
+
+// flags: [0] overflow, [1] the all-ones id is present (it doubles as the empty sentinel)
+__global__ void k_insert_nodes(const uint64_t* __restrict__ flo, const uint64_t* __restrict__ fhi,
+                               const uint64_t* __restrict__ tlo, const uint64_t* __restrict__ thi,
+                               uint64_t n_edges, ulonglong2* table, uint64_t mask,
+                               unsigned long long* count, unsigned long long max_count, int* flags) {
+  const uint64_t total = 2 * n_edges;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t lo, hi;
+    if (i < n_edges) { lo = flo[i]; hi = fhi[i]; } else { lo = tlo[i - n_edges]; hi = thi[i - n_edges]; }
+    if (lo == EMPTY64 && hi == EMPTY64) { flags[1] = 1; continue; }
+    if (*(volatile int*)flags) return;
+    const u128 key = ((u128)hi << 64) | lo;
+    uint64_t slot = hash128(lo, hi) & mask;
+    for (uint64_t probe = 0;; probe++) {
+      ulonglong2 cur = table[slot];
+      if (cur.x == lo && cur.y == hi) break;
+      if (cur.x == EMPTY64 || cur.y == EMPTY64) {
+        // empty, being written, or a key with an all-ones half: the CAS result is the truth
+        u128 old = cas128((u128*)&table[slot], ~(u128)0, key);
+        if (old == ~(u128)0) {
+          unsigned long long c = atomicAdd(count, 1ull);
+          if (c + 1 > max_count) flags[0] = 1;
+          break;
+        }
+        if (old == key) break;
+      }
+      slot = (slot + 1) & mask;
+      if (probe > mask) { flags[0] = 1; break; }
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t lookup_rank(const ulonglong2* __restrict__ table,
+                                                const uint32_t* __restrict__ slot_val, uint64_t mask,
+                                                uint64_t lo, uint64_t hi, uint32_t max_rank) {
+  if (lo == EMPTY64 && hi == EMPTY64) return max_rank;
+  uint64_t slot = hash128(lo, hi) & mask;
+  for (;;) {
+    ulonglong2 cur = table[slot];
+    if (cur.x == lo && cur.y == hi) return slot_val[slot];
+    slot = (slot + 1) & mask;
+  }
+}
+
+__global__ void k_compact_keys(const ulonglong2* __restrict__ table, uint64_t cap, uint64_t* out_lo,
+                               uint64_t* out_hi, unsigned long long* counter) {
+  for (uint64_t base = blockIdx.x * (uint64_t)blockDim.x; base < cap; base += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t i = base + threadIdx.x;
+    ulonglong2 cur = make_ulonglong2(EMPTY64, EMPTY64);
+    if (i < cap) cur = table[i];
+    bool occ = !(cur.x == EMPTY64 && cur.y == EMPTY64);
+    unsigned m = __ballot_sync(0xffffffffu, occ);
+    int lane = threadIdx.x & 31;
+    unsigned long long wbase = 0;
+    if (lane == 0 && m) wbase = atomicAdd(counter, (unsigned long long)__popc(m));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (occ) {
+      uint64_t pos = wbase + __popc(m & ((1u << lane) - 1));
+      out_lo[pos] = cur.x; out_hi[pos] = cur.y;
+    }
+  }
+}
+
+__global__ void k_assign_ranks(const uint64_t* __restrict__ lo, const uint64_t* __restrict__ hi, uint64_t n,
+                               const ulonglong2* __restrict__ table, uint32_t* slot_val, uint64_t mask) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t l = lo[i], h = hi[i];
+  uint64_t slot = hash128(l, h) & mask;
+  for (;;) {
+    ulonglong2 cur = table[slot];
+    if (cur.x == l && cur.y == h) { slot_val[slot] = (uint32_t)i; return; }
+    slot = (slot + 1) & mask;
+  }
+}
+
+__global__ void k_map_edges(const uint64_t* __restrict__ flo, const uint64_t* __restrict__ fhi,
+                            const uint64_t* __restrict__ tlo, const uint64_t* __restrict__ thi,
+                            const uint64_t* __restrict__ rel, uint64_t n_edges, uint64_t skip_mask,
+                            const ulonglong2* __restrict__ table, const uint32_t* __restrict__ slot_val,
+                            uint64_t mask, uint32_t max_rank, uint64_t* keys, uint8_t* skip) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n_edges) return;
+  uint32_t rf = lookup_rank(table, slot_val, mask, flo[i], fhi[i], max_rank);
+  uint32_t rt = lookup_rank(table, slot_val, mask, tlo[i], thi[i], max_rank);
+  keys[i] = ((uint64_t)rt << 32) | rf;
+  skip[i] = (rel[i] & skip_mask) != 0;
+}
+
+__global__ void k_mark_keep(const uint64_t* __restrict__ keys, const uint8_t* __restrict__ skip, uint64_t n,
+                            uint8_t* keep) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t k = keys[i];
+  bool first = (i == 0) || (keys[i - 1] != k);
+  keep[i] = first && !skip[i] && ((uint32_t)k != (uint32_t)(k >> 32));
+}
+
+__global__ void k_degree_hi(const uint64_t* __restrict__ keys, uint64_t n, uint32_t* deg) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(&deg[keys[i] >> 32], 1u);
+}
+__global__ void k_iota(uint32_t* a, uint64_t n) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) a[i] = (uint32_t)i;
+}
+__global__ void k_invert(const uint32_t* __restrict__ perm, uint64_t n, uint32_t* inv) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) inv[perm[i]] = (uint32_t)i;
+}
+// keys in rank space (to<<32|from) -> internal space; swap=true builds the source-major key
+__global__ void k_remap(const uint64_t* __restrict__ in, uint64_t n, const uint32_t* __restrict__ inv,
+                        uint64_t* out, bool swap) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t k = in[i];
+  uint32_t to = inv[k >> 32], from = inv[(uint32_t)k];
+  out[i] = swap ? (((uint64_t)from << 32) | to) : (((uint64_t)to << 32) | from);
+}
+__global__ void k_lo32(const uint64_t* __restrict__ in, uint64_t n, uint32_t* out) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint32_t)in[i];
+}
+// deg is sorted descending: count rows with deg > thresholds[j] by boundary detection
+__global__ void k_class_bounds(const uint32_t* __restrict__ deg, uint64_t n, uint32_t t0, uint32_t t1,
+                               uint32_t t2, unsigned long long* out) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t d = deg[i];
+  uint32_t nx = (i + 1 < n) ? deg[i + 1] : 0u;
+  if (d > t0 && !(nx > t0)) out[0] = i + 1;
+  if (d > t1 && !(nx > t1)) out[1] = i + 1;
+  if (d > t2 && !(nx > t2)) out[2] = i + 1;
+}
+// first row whose row_ptr >= target (rows are edge-balanced between ranks), 32-row aligned
+__global__ void k_find_splits(const uint32_t* __restrict__ row_ptr, uint64_t n, uint64_t E, int world,
+                              unsigned long long* out) {
+  int r = threadIdx.x;
+  if (r > world) return;
+  if (r == 0) { out[0] = 0; return; }
+  if (r == world) { out[r] = n; return; }
+  uint64_t target = (E * (uint64_t)r) / (uint64_t)world;
+  uint64_t lo = 0, hi = n;
+  while (lo < hi) { uint64_t mid = (lo + hi) / 2; if (row_ptr[mid] < target) lo = mid + 1; else hi = mid; }
+  out[r] = (lo / 32) * 32;
+}
+__global__ void k_row_chunks(const uint32_t* __restrict__ row_ptr, uint64_t row0, uint64_t nrows, int chunk,
+                             uint32_t* nchunks) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  uint32_t d = row_ptr[row0 + i + 1] - row_ptr[row0 + i];
+  nchunks[i] = (d + chunk - 1) / chunk;
+}
+__global__ void k_fill_items(const uint32_t* __restrict__ item_start, uint64_t nrows, uint64_t n_items,
+                             uint32_t row0, uint32_t* item_row) {
+  uint64_t it = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (it >= n_items) return;
+  uint64_t lo = 0, hi = nrows;  // last row r with item_start[r] <= it
+  while (lo + 1 < hi) { uint64_t mid = (lo + hi) / 2; if (item_start[mid] <= it) lo = mid; else hi = mid; }
+  item_row[it] = row0 + (uint32_t)lo;
+}
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+int copy_in(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  if (bytes == 0) return SB200_OK;
+  SB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s));
+  return SB200_OK;
+}
+
+template <class K, class V>
+static int sort_pairs(DevBuf<uint8_t>& tmp, K*& k, K*& k_alt, V*& v, V*& v_alt, uint64_t n, int b0, int b1,
+                      bool descending, cudaStream_t s) {
+  cub::DoubleBuffer<K> dk(k, k_alt);
+  cub::DoubleBuffer<V> dv(v, v_alt);
+  size_t need = 0;
+  if (descending) SB_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, dk, dv, (int64_t)n, b0, b1, s));
+  else SB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, (int64_t)n, b0, b1, s));
+  if (tmp.n < need) SB_TRY(tmp.alloc(need + (need >> 3) + 256));
+  if (descending) SB_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp.p, need, dk, dv, (int64_t)n, b0, b1, s));
+  else SB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, need, dk, dv, (int64_t)n, b0, b1, s));
+  g_launches.fetch_add(8, std::memory_order_relaxed);
+  if (dk.Current() != k) std::swap(k, k_alt);
+  if (dv.Current() != v) std::swap(v, v_alt);
+  return SB200_OK;
+}
+template <class K>
+static int sort_keys(DevBuf<uint8_t>& tmp, K*& k, K*& k_alt, uint64_t n, int b0, int b1, cudaStream_t s) {
+  cub::DoubleBuffer<K> dk(k, k_alt);
+  size_t need = 0;
+  SB_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, need, dk, (int64_t)n, b0, b1, s));
+  if (tmp.n < need) SB_TRY(tmp.alloc(need + (need >> 3) + 256));
+  SB_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, need, dk, (int64_t)n, b0, b1, s));
+  g_launches.fetch_add(8, std::memory_order_relaxed);
+  if (dk.Current() != k) std::swap(k, k_alt);
+  return SB200_OK;
+}
+template <class T>
+static int exclusive_scan_u32(DevBuf<uint8_t>& tmp, const T* in, uint32_t* out, uint64_t n, cudaStream_t s) {
+  size_t need = 0;
+  SB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, (int64_t)n, s));
+  if (tmp.n < need) SB_TRY(tmp.alloc(need + 256));
+  SB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, need, in, out, (int64_t)n, s));
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  return SB200_OK;
+}
+
+static int bits_for(uint64_t n) { int b = 1; while (b < 32 && (1ull << b) < n) b++; return b; }
+
+int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi, const uint64_t* to_lo,
+                const uint64_t* to_hi, const uint64_t* rel, uint64_t n_edges, uint64_t skip_mask) {
+  cudaStream_t s = g->stream;
+  const int TPB = 256;
+  g->E_in = n_edges;
+  if (n_edges >= 0xFFFFFFF0ull) SB_FAIL(SB200_ERANGE, "n_edges %llu exceeds the 2^32-16 limit of u32 CSR offsets", (unsigned long long)n_edges);
+  SB_CUDA(cudaEventRecord(g->ev0, s));
+
+  // ---- 0. bring the SoA edge stream into HBM (no copy if the caller already has it there) ----
+  DevBuf<uint64_t> in_copy[5];
+  const uint64_t* src[5] = {from_lo, from_hi, to_lo, to_hi, rel};
+  const uint64_t* d[5];
+  for (int a = 0; a < 5; a++) {
+    if (n_edges == 0) { d[a] = nullptr; continue; }
+    if (!src[a]) SB_FAIL(SB200_EINVAL, "edge array %d is NULL", a);
+    if (is_device_ptr(src[a])) d[a] = src[a];
+    else { SB_TRY(in_copy[a].alloc(n_edges)); SB_TRY(copy_in(in_copy[a].p, src[a], n_edges * 8, s)); d[a] = in_copy[a].p; }
+  }
+
+  DevBuf<unsigned long long> ctr; SB_TRY(ctr.alloc(8));
+  DevBuf<int> flags; SB_TRY(flags.alloc(2));
+  unsigned long long h_ctr[8]; int h_flags[2];
+  DevBuf<uint8_t>& tmp = g->cub_tmp;
+
+  // ---- 1. node dictionary ---------------------------------------------------------------------
+  DevBuf<ulonglong2> table;
+  uint64_t cap = 1ull << 12;
+  while (cap < n_edges / 2) cap <<= 1;  // first guess: N <= E/4 keeps the load factor <= 1/2
+  uint64_t n_keys = 0; bool has_max = false;
+  for (;;) {
+    SB_TRY(table.alloc(cap));
+    SB_CUDA(cudaMemsetAsync(table.p, 0xFF, cap * sizeof(ulonglong2), s));
+    SB_CUDA(cudaMemsetAsync(ctr.p, 0, 8 * sizeof(unsigned long long), s));
+    SB_CUDA(cudaMemsetAsync(flags.p, 0, 2 * sizeof(int), s));
+    if (n_edges) {
+      unsigned grid = (unsigned)std::min<uint64_t>(div_up(2 * n_edges, TPB), 148u * 32u);
+      SB_LAUNCH(k_insert_nodes, grid, TPB, 0, s, d[0], d[1], d[2], d[3], n_edges, table.p, cap - 1, ctr.p,
+                (unsigned long long)(cap / 2), flags.p);
+      SB_CHECK_LAUNCH();
+    }
+    SB_CUDA(cudaMemcpyAsync(h_ctr, ctr.p, sizeof(h_ctr), cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaMemcpyAsync(h_flags, flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    if (!h_flags[0]) { n_keys = h_ctr[0]; has_max = h_flags[1] != 0; break; }
+    cap <<= 2;  // load factor exceeded 1/2: grow and redo (still linear overall)
+    if (cap > (1ull << 34)) SB_FAIL(SB200_ENOMEM, "node hash set would exceed 2^34 slots");
+  }
+  const uint64_t N = n_keys + (has_max ? 1 : 0);
+  g->N = N;
+  if (N >= 0xFFFFFFFEull) SB_FAIL(SB200_ERANGE, "%llu nodes exceed the u32 index space", (unsigned long long)N);
+  SB_TRY(g->id_lo.alloc(N)); SB_TRY(g->id_hi.alloc(N));
+  SB_TRY(g->perm.alloc(N)); SB_TRY(g->inv.alloc(N));
+  SB_TRY(g->row_ptr.alloc(N + 1));
+  if (N == 0) {
+    SB_CUDA(cudaMemsetAsync(g->row_ptr.p, 0, sizeof(uint32_t), s));
+    g->E_kept = g->E_local = 0; g->row_begin = g->row_end = 0; g->n_pos = 0;
+    for (int r = 0; r <= g->world; r++) g->range_begins[r] = 0;
+    SB_CUDA(cudaEventRecord(g->ev1, s)); SB_CUDA(cudaStreamSynchronize(s));
+    return SB200_OK;
+  }
+  {
+    // compact the occupied slots and sort ascending by (hi, lo): LSD = two stable 64-bit passes
+    DevBuf<uint64_t> alt_lo, alt_hi; SB_TRY(alt_lo.alloc(N)); SB_TRY(alt_hi.alloc(N));
+    SB_CUDA(cudaMemsetAsync(ctr.p, 0, sizeof(unsigned long long), s));
+    unsigned grid = (unsigned)std::min<uint64_t>(div_up(cap, TPB), 148u * 32u);
+    SB_LAUNCH(k_compact_keys, grid, TPB, 0, s, table.p, cap, g->id_lo.p, g->id_hi.p, ctr.p);
+    SB_CHECK_LAUNCH();
+    uint64_t *klo = g->id_lo.p, *klo_alt = alt_lo.p, *khi = g->id_hi.p, *khi_alt = alt_hi.p;
+    if (n_keys > 1) {
+      SB_TRY((sort_pairs<uint64_t, uint64_t>(tmp, klo, klo_alt, khi, khi_alt, n_keys, 0, 64, false, s)));
+      SB_TRY((sort_pairs<uint64_t, uint64_t>(tmp, khi, khi_alt, klo, klo_alt, n_keys, 0, 64, false, s)));
+    }
+    if (klo != g->id_lo.p) SB_CUDA(cudaMemcpyAsync(g->id_lo.p, klo, n_keys * 8, cudaMemcpyDeviceToDevice, s));
+    if (khi != g->id_hi.p) SB_CUDA(cudaMemcpyAsync(g->id_hi.p, khi, n_keys * 8, cudaMemcpyDeviceToDevice, s));
+    if (has_max) {  // the all-ones id is the largest possible u128: it takes the last rank
+      SB_CUDA(cudaMemsetAsync(g->id_lo.p + n_keys, 0xFF, 8, s));
+      SB_CUDA(cudaMemsetAsync(g->id_hi.p + n_keys, 0xFF, 8, s));
+    }
+    SB_CUDA(cudaStreamSynchronize(s));
+  }
+  DevBuf<uint32_t> slot_val; SB_TRY(slot_val.alloc(cap));
+  if (n_keys) {
+    SB_LAUNCH(k_assign_ranks, div_up(n_keys, TPB), TPB, 0, s, g->id_lo.p, g->id_hi.p, n_keys, table.p, slot_val.p, cap - 1);
+    SB_CHECK_LAUNCH();
+  }
+
+  // ---- 2. edges -> (to_rank<<32|from_rank), stable sort, unique_by first-wins, drop skipped ----
+  DevBuf<uint64_t> keys_a, keys_b; SB_TRY(keys_a.alloc(n_edges)); SB_TRY(keys_b.alloc(n_edges));
+  DevBuf<uint8_t> skip_a, skip_b; SB_TRY(skip_a.alloc(n_edges)); SB_TRY(skip_b.alloc(n_edges));
+  SB_LAUNCH(k_map_edges, div_up(n_edges, TPB), TPB, 0, s, d[0], d[1], d[2], d[3], d[4], n_edges, skip_mask, table.p,
+            slot_val.p, cap - 1, (uint32_t)(N - 1), keys_a.p, skip_a.p);
+  SB_CHECK_LAUNCH();
+  SB_CUDA(cudaStreamSynchronize(s));
+  for (int a = 0; a < 5; a++) in_copy[a].release();
+  table.release(); slot_val.release();
+
+  const int nb = bits_for(N);
+  uint64_t *k = keys_a.p, *k_alt = keys_b.p; uint8_t *sk = skip_a.p, *sk_alt = skip_b.p;
+  SB_TRY((sort_pairs<uint64_t, uint8_t>(tmp, k, k_alt, sk, sk_alt, n_edges, 0, 32 + nb, false, s)));
+  SB_LAUNCH(k_mark_keep, div_up(n_edges, TPB), TPB, 0, s, k, sk, n_edges, sk_alt);
+  SB_CHECK_LAUNCH();
+  {
+    size_t need = 0;
+    SB_CUDA(cub::DeviceSelect::Flagged(nullptr, need, k, sk_alt, k_alt, ctr.p, (int64_t)n_edges, s));
+    if (tmp.n < need) SB_TRY(tmp.alloc(need + 256));
+    SB_CUDA(cub::DeviceSelect::Flagged(tmp.p, need, k, sk_alt, k_alt, ctr.p, (int64_t)n_edges, s));
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    SB_CUDA(cudaMemcpyAsync(h_ctr, ctr.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+  }
+  const uint64_t E = h_ctr[0];
+  g->E_kept = E;
+  std::swap(k, k_alt);  // k = kept keys in rank space, sorted by (to, from)
+  skip_a.release(); skip_b.release();
+
+  // ---- 3. degree-sorted relabel + CSR (both directions) ------------------------------------------
+  DevBuf<uint32_t> deg_a, deg_b, val_b; SB_TRY(deg_a.alloc(N)); SB_TRY(deg_b.alloc(N)); SB_TRY(val_b.alloc(N));
+  SB_CUDA(cudaMemsetAsync(deg_a.p, 0, N * 4, s));
+  if (E) { SB_LAUNCH(k_degree_hi, div_up(E, TPB), TPB, 0, s, k, E, deg_a.p); SB_CHECK_LAUNCH(); }
+  SB_LAUNCH(k_iota, div_up(N, TPB), TPB, 0, s, g->perm.p, N); SB_CHECK_LAUNCH();
+  uint32_t *dk = deg_a.p, *dk_alt = deg_b.p, *pv = g->perm.p, *pv_alt = val_b.p;
+  SB_TRY((sort_pairs<uint32_t, uint32_t>(tmp, dk, dk_alt, pv, pv_alt, N, 0, 32, true, s)));
+  if (pv != g->perm.p) SB_CUDA(cudaMemcpyAsync(g->perm.p, pv, N * 4, cudaMemcpyDeviceToDevice, s));
+  SB_LAUNCH(k_invert, div_up(N, TPB), TPB, 0, s, g->perm.p, N, g->inv.p); SB_CHECK_LAUNCH();
+  // dk = in-degree by internal row, descending
+  SB_TRY(exclusive_scan_u32(tmp, dk, g->row_ptr.p, N, s));
+  {
+    uint32_t e32 = (uint32_t)E;
+    SB_CUDA(cudaMemcpyAsync(g->row_ptr.p + N, &e32, 4, cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemsetAsync(ctr.p, 0, 8 * sizeof(unsigned long long), s));
+    SB_LAUNCH(k_class_bounds, div_up(N, TPB), TPB, 0, s, dk, N, 0u, (uint32_t)QUAD_MAX_DEG, (uint32_t)CHUNK_EDGES, ctr.p);
+    SB_CHECK_LAUNCH();
+    SB_CUDA(cudaStreamSynchronize(s));
+  }
+  DevBuf<unsigned long long> splits; SB_TRY(splits.alloc(g->world + 1));
+  SB_LAUNCH(k_find_splits, 1, 128, 0, s, g->row_ptr.p, N, E, g->world, splits.p); SB_CHECK_LAUNCH();
+  std::vector<unsigned long long> h_splits(g->world + 1);
+  SB_CUDA(cudaMemcpyAsync(h_ctr, ctr.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  SB_CUDA(cudaMemcpyAsync(h_splits.data(), splits.p, (g->world + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  SB_CUDA(cudaStreamSynchronize(s));
+  const uint64_t n_pos = h_ctr[0], n_warp = h_ctr[1], n_multi = h_ctr[2];
+  g->n_pos = n_pos;
+  for (int r = 0; r <= g->world; r++) {
+    g->range_begins[r] = h_splits[r];
+    if (r > 0 && g->range_begins[r] < g->range_begins[r - 1]) g->range_begins[r] = g->range_begins[r - 1];
+  }
+  g->range_begins[g->world] = N;
+  g->row_begin = g->range_begins[g->rank];
+  g->row_end = g->range_begins[g->rank + 1];
+
+  // destination-major CSR in internal ids
+  DevBuf<uint32_t> col_full; SB_TRY(col_full.alloc(E));
+  if (E) {
+    SB_LAUNCH(k_remap, div_up(E, TPB), TPB, 0, s, k, E, g->inv.p, k_alt, false); SB_CHECK_LAUNCH();
+    uint64_t *a = k_alt, *b = k;  // sort a (clobbers b = rank-space keys, rebuilt below when needed)
+    // keep the rank-space keys: we need them again for the forward CSR, so sort into a third buffer
+    DevBuf<uint64_t> keys_c; SB_TRY(keys_c.alloc(E));
+    uint64_t* c = keys_c.p;
+    SB_TRY(sort_keys<uint64_t>(tmp, a, c, E, 0, 32 + nb, s));
+    SB_LAUNCH(k_lo32, div_up(E, TPB), TPB, 0, s, a, E, col_full.p); SB_CHECK_LAUNCH();
+    // source-major CSR (single-rank handles only: the push branch needs every out-edge)
+    if (g->world == 1) {
+      uint64_t* other = c;  // scratch half of the last sort
+      SB_LAUNCH(k_remap, div_up(E, TPB), TPB, 0, s, b, E, g->inv.p, a, true); SB_CHECK_LAUNCH();
+      SB_TRY(sort_keys<uint64_t>(tmp, a, other, E, 0, 32 + nb, s));
+      SB_TRY(g->fwd_dst.alloc(E)); SB_TRY(g->fwd_ptr.alloc(N + 1));
+      SB_LAUNCH(k_lo32, div_up(E, TPB), TPB, 0, s, a, E, g->fwd_dst.p); SB_CHECK_LAUNCH();
+      SB_CUDA(cudaMemsetAsync(deg_b.p == dk ? deg_a.p : deg_b.p, 0, N * 4, s));
+      uint32_t* od = (deg_b.p == dk) ? deg_a.p : deg_b.p;
+      SB_LAUNCH(k_degree_hi, div_up(E, TPB), TPB, 0, s, a, E, od); SB_CHECK_LAUNCH();
+      SB_TRY(exclusive_scan_u32(tmp, od, g->fwd_ptr.p, N, s));
+      uint32_t e32 = (uint32_t)E;
+      SB_CUDA(cudaMemcpyAsync(g->fwd_ptr.p + N, &e32, 4, cudaMemcpyHostToDevice, s));
+      g->has_fwd = true;
+    }
+    SB_CUDA(cudaStreamSynchronize(s));
+  } else if (g->world == 1) {
+    SB_TRY(g->fwd_ptr.alloc(N + 1));
+    SB_CUDA(cudaMemsetAsync(g->fwd_ptr.p, 0, (N + 1) * 4, s));
+    g->has_fwd = true;
+  }
+  keys_a.release(); keys_b.release();
+
+  // ---- 4. owned slice of the CSR + pull work partition --------------------------------------------
+  uint32_t h_rp[2] = {0, 0};
+  SB_CUDA(cudaMemcpyAsync(&h_rp[0], g->row_ptr.p + g->row_begin, 4, cudaMemcpyDeviceToHost, s));
+  SB_CUDA(cudaMemcpyAsync(&h_rp[1], g->row_ptr.p + g->row_end, 4, cudaMemcpyDeviceToHost, s));
+  SB_CUDA(cudaStreamSynchronize(s));
+  g->col_base = h_rp[0];
+  g->E_local = h_rp[1] - h_rp[0];
+  if (g->world == 1) g->col = std::move(col_full);
+  else {
+    SB_TRY(g->col.alloc(g->E_local));
+    if (g->E_local) SB_CUDA(cudaMemcpyAsync(g->col.p, col_full.p + g->col_base, g->E_local * 4, cudaMemcpyDeviceToDevice, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    col_full.release();
+  }
+  auto clampr = [&](uint64_t x) { return std::min(std::max(x, g->row_begin), g->row_end); };
+  g->warp_row_begin = clampr(0); g->warp_row_end = clampr(n_warp);
+  g->quad_row_begin = clampr(n_warp); g->quad_row_end = clampr(n_pos);
+  {
+    uint32_t rp[3] = {0, 0, 0};
+    SB_CUDA(cudaMemcpyAsync(&rp[0], g->row_ptr.p + g->warp_row_begin, 4, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaMemcpyAsync(&rp[1], g->row_ptr.p + g->warp_row_end, 4, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaMemcpyAsync(&rp[2], g->row_ptr.p + g->quad_row_end, 4, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    g->E_warp = rp[1] - rp[0];
+    g->E_quad = (g->quad_row_end > g->quad_row_begin) ? rp[2] - rp[1] : 0;
+  }
+  const uint64_t nwr = g->warp_row_end - g->warp_row_begin;
+  g->n_items = 0; g->n_multi_rows = 0; g->n_multi_items = 0;
+  if (nwr) {
+    DevBuf<uint32_t> nchunks; SB_TRY(nchunks.alloc(nwr + 1));
+    SB_CUDA(cudaMemsetAsync(nchunks.p, 0, (nwr + 1) * 4, s));
+    SB_LAUNCH(k_row_chunks, div_up(nwr, TPB), TPB, 0, s, g->row_ptr.p, g->warp_row_begin, nwr, CHUNK_EDGES, nchunks.p);
+    SB_CHECK_LAUNCH();
+    SB_TRY(g->item_start.alloc(nwr + 1));
+    SB_TRY(exclusive_scan_u32(tmp, nchunks.p, g->item_start.p, nwr + 1, s));
+    uint32_t total = 0, multi_items = 0;
+    const uint64_t nmr = (clampr(n_multi) > g->warp_row_begin) ? clampr(n_multi) - g->warp_row_begin : 0;
+    SB_CUDA(cudaMemcpyAsync(&total, g->item_start.p + nwr, 4, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaMemcpyAsync(&multi_items, g->item_start.p + nmr, 4, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    g->n_items = total; g->n_multi_rows = nmr; g->n_multi_items = multi_items;
+    SB_TRY(g->item_row.alloc(total));
+    SB_LAUNCH(k_fill_items, div_up(total, TPB), TPB, 0, s, g->item_start.p, nwr, (uint64_t)total,
+              (uint32_t)g->warp_row_begin, g->item_row.p);
+    SB_CHECK_LAUNCH();
+    SB_TRY(g->partial.alloc((size_t)std::max<uint64_t>(1, g->n_multi_items) * 4));
+    SB_CUDA(cudaStreamSynchronize(s));
+  }
+  SB_CUDA(cudaEventRecord(g->ev1, s));
+  SB_CUDA(cudaStreamSynchronize(s));
+  float ms = 0; cudaEventElapsedTime(&ms, g->ev0, g->ev1);
+  g->stage_ms = ms;
+  return SB200_OK;
+}
+
+}  // namespace sb200

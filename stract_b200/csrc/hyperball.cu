@@ -1,0 +1,645 @@
+// hyperball.cu -- the HyperBall iteration on the device (hot path 1).
+//
+// Reference semantics (crates/core/src/webgraph/centrality/harmonic.rs):
+//   update_all_counters  :116-157   for every kept edge u->v with u in the changed set:
+//                                   if any(old[u][i] > new[v][i]) { new[v].merge(old[u]); mark v }
+//   update_changed_counters :75-114 same, driven from the exact changed set through forward links
+//   update_centralities  :159-176   score[v] += (size(new[v]) -sat size(old[v])) as f64 / (t+1)  (Kahan)
+//   Counters::step       :210-212   old = new.clone()
+// All branches compute the synchronous update new[v] = max(old[v], max_{u->v, u changed} old[u]);
+// merging an unchanged u is a no-op (it was merged the iteration after it last changed), which is
+// why the reference may use a Bloom filter for the changed set and why the dense kernel below may
+// skip the frontier test altogether.
+//
+// Device formulation
+//   * registers live in two N x 64 B arrays (ping-pong).  Row v of the "new" array is rewritten only
+//     if v changed now or changed in the previous iteration (it is then two iterations stale);
+//     every other row is already equal in both arrays, so `old = new.clone()` costs nothing.
+//   * pull kernels (destination-major CSR, one writer per row, no atomics on registers):
+//       k_pull_quad : rows with in-degree <= 32, 4 lanes per row (16 B of the 64-B counter each)
+//       k_pull_warp : longer rows cut into 1024-edge work items, one warp per item: the 32 source
+//                     indices of a batch are loaded coalesced, each quad of lanes gathers one 64-B
+//                     counter (4 x LDG.128), byte-wise max with __vmaxu4, xor-shuffle reduce over
+//                     the 8 quads; rows spanning several items go through a partial buffer + k_pull_merge
+//     DENSE variant gathers every in-neighbour; FRONTIER variant tests the changed bitmap first.
+//   * push kernel (source-major CSR) for small frontiers: half-warp per out-edge, 32-bit CAS max.
+//   * k_finalize: per changed node, HyperLogLog<64>::size() in the reference's exact f64 operation
+//     order (sequential sum over registers 0..63, no FMA), saturating difference against the cached
+//     size(old), KahanSum update; nodes that changed in the previous iteration but not now get the
+//     reference's "+= 0.0" (it is idempotent after one application, so skipping the other N-1 zero
+//     adds is bit-exact).
+// Roofline: HBM.  Algorithmic bytes per iteration: 68 B x E_active + 132 B x N_written + 40 B x N_changed.
+#include "graph.cuh"
+#include "../../include/sb200_hll_tables.h"
+
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+namespace sb200 {
+
+struct HllTables {
+  double raw[SB200_HLL_P5_LEN];
+  double bias[SB200_HLL_P5_LEN];
+  double lc[65];  // lc[v] = 64*ln(64/v), host libm (matches the reference's f64::ln), lc[0] unused
+};
+__constant__ HllTables c_tab;
+static bool g_tab_loaded[64] = {false};
+
+int load_tables(int device) {
+  if (device >= 0 && device < 64 && g_tab_loaded[device]) return SB200_OK;
+  static HllTables h;
+  for (int i = 0; i < SB200_HLL_P5_LEN; i++) { h.raw[i] = SB200_HLL_RAW_P5[i]; h.bias[i] = SB200_HLL_BIAS_P5[i]; }
+  h.lc[0] = 0.0;
+  for (int v = 1; v <= 64; v++) h.lc[v] = 64.0 * std::log(64.0 / (double)v);  // hyperloglog.rs:4472-4476
+  SB_CUDA(cudaMemcpyToSymbol(c_tab, &h, sizeof(h)));
+  if (device >= 0 && device < 64) g_tab_loaded[device] = true;
+  return SB200_OK;
+}
+
+// ---- HyperLogLog<64>::size(), crates/core/src/hyperloglog.rs:4484-4516, bit-exact -----------------
+// `tab` points to a shared-memory copy of c_tab (divergent indexing into __constant__ serialises).
+__device__ __forceinline__ double pow2_neg(uint32_t k) {  // ONE_OVER_POWER_OF_TWO[k] == 2^-k
+  return __longlong_as_double((long long)(1023 - (int)k) << 52);
+}
+__device__ uint64_t hll64_size(const uint32_t w[16], const HllTables* tab) {
+  double sum = 0.0;
+  int zeros = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      uint32_t r = (w[i] >> (8 * b)) & 0xFFu;
+      sum = __dadd_rn(sum, pow2_neg(r));
+      zeros += (r == 0);
+    }
+  }
+  const double z = __ddiv_rn(1.0, sum);
+  const double e = __dmul_rn(0.709 * 4096.0, z);  // am() * m.powi(2) * z, left-assoc; 0.709*2^12 is exact
+  double e_star = e;
+  if (e <= 320.0) {
+    // estimate_bias(e, 6): tables [b-1-4] = "precision 5"; Rust >= 1.82 binary_search_by
+    const int LEN = SB200_HLL_P5_LEN;
+    int size = LEN, base = 0;
+    while (size > 1) {
+      int half = size >> 1, mid = base + half;
+      base = (tab->raw[mid] > e) ? base : mid;
+      size -= half;
+    }
+    int r = base;
+    if (!(tab->raw[base] == e)) r = base + (tab->raw[base] < e ? 1 : 0);
+    if (r == LEN) r = LEN - 1;
+    int il = r, ir = (r < LEN - 1) ? r + 1 : -1;
+    double bsum = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < 6; k++) {
+      bool right;
+      int idx;
+      if (il >= 0 && ir >= 0) {
+        double dl = fabs(__dsub_rn(tab->raw[il], e)), dr = fabs(__dsub_rn(tab->raw[ir], e));
+        right = dr < dl;
+        idx = right ? ir : il;
+      } else if (il >= 0) { right = false; idx = il; }
+      else { right = true; idx = ir; }
+      bsum = __dadd_rn(bsum, tab->bias[idx]);
+      if (right) ir = (idx < LEN - 1) ? idx + 1 : -1;
+      else il = (idx > 0) ? idx - 1 : -1;
+    }
+    e_star = __dsub_rn(e, __ddiv_rn(bsum, 6.0));
+  }
+  const double h = (zeros != 0) ? tab->lc[zeros] : e_star;
+  const double pick = (h <= 40.0) ? h : e_star;  // threshold(b=6) = 40
+  // Rust `as usize`: saturating, NaN -> 0
+  if (!(pick == pick) || pick <= 0.0) return 0ull;
+  if (pick >= 18446744073709551616.0) return 0xFFFFFFFFFFFFFFFFull;
+  return (uint64_t)__double2ull_rz(pick);
+}
+
+__device__ __forceinline__ void kahan_add(double& sum, double& err, double rhs) {  // kahan_sum.rs:46-53
+  const double y = __dsub_rn(rhs, err);
+  const double t = __dadd_rn(sum, y);
+  err = __dsub_rn(__dsub_rn(t, sum), y);
+  sum = t;
+}
+
+// ---- init: counters seeded with the node's own id (low 64 bits), harmonic.rs:53-73 ------------------
+__global__ void k_hb_init(const uint64_t* __restrict__ id_lo, const uint32_t* __restrict__ perm, uint64_t N,
+                          uint4* r0, uint4* r1, uint64_t* size_cache, double* ksum, double* kerr) {
+  __shared__ HllTables tab;
+  for (int i = threadIdx.x; i < (int)(sizeof(HllTables) / 8); i += blockDim.x) ((double*)&tab)[i] = ((const double*)&c_tab)[i];
+  __syncthreads();
+  uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (v >= N) return;
+  const uint64_t hash = id_lo[perm[v]] * 11400714819323198549ull;  // FastHasher hyperloglog.rs:4311-4313
+  const uint32_t j = (uint32_t)(hash >> 58);
+  const uint64_t wv = hash << 6;
+  const uint32_t p = (wv == 0 ? 64u : (uint32_t)__clzll((long long)wv)) + 1u;
+  uint32_t w[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) w[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) if ((int)(j >> 2) == i) w[i] = p << (8 * (j & 3));
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    uint4 x = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    r0[v * 4 + q] = x; r1[v * 4 + q] = x;
+  }
+  size_cache[v] = hll64_size(w, &tab);
+  ksum[v] = 0.0; kerr[v] = 0.0;
+}
+__global__ void k_bm_fill(uint32_t* bm, uint64_t N, uint64_t words) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= words) return;
+  uint64_t first = i * 32;
+  uint32_t m = 0xFFFFFFFFu;
+  if (first + 32 > N) m = (N > first) ? ((1u << (N - first)) - 1u) : 0u;
+  bm[i] = m;
+}
+
+__device__ __forceinline__ bool bm_test(const uint32_t* __restrict__ bm, uint32_t v) {
+  return (__ldg(bm + (v >> 5)) >> (v & 31)) & 1u;
+}
+
+// ---- pull, short rows: 4 lanes per destination row ----------------------------------------------------
+template <bool FRONTIER>
+__global__ void __launch_bounds__(256) k_pull_quad(uint64_t row_begin, uint64_t row_end,
+    const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col, uint32_t col_base,
+    const uint4* __restrict__ oldr, uint4* __restrict__ newr,
+    const uint32_t* __restrict__ bm_prev, uint32_t* __restrict__ bm_cur) {
+  const uint64_t gt = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint32_t sub = threadIdx.x & 3;
+  const uint32_t lane = threadIdx.x & 31;
+  uint64_t row = row_begin + (gt >> 2);
+  const bool live = row < row_end;
+  if (!live) row = row_end - 1;  // keep the warp converged; results of dead quads are discarded
+  const uint32_t e0 = row_ptr[row] - col_base, e1 = row_ptr[row + 1] - col_base;
+  const uint4 own = oldr[row * 4 + sub];
+  uint4 acc = own;
+  for (uint32_t e = e0; e < e1; e += 4) {
+    uint32_t i0 = col[e];
+    uint32_t i1 = (e + 1 < e1) ? col[e + 1] : i0;
+    uint32_t i2 = (e + 2 < e1) ? col[e + 2] : i0;
+    uint32_t i3 = (e + 3 < e1) ? col[e + 3] : i0;
+    if (FRONTIER) {  // an unchanged source is a no-op: redirect it to our own (cached) row
+      i0 = bm_test(bm_prev, i0) ? i0 : (uint32_t)row;
+      i1 = bm_test(bm_prev, i1) ? i1 : (uint32_t)row;
+      i2 = bm_test(bm_prev, i2) ? i2 : (uint32_t)row;
+      i3 = bm_test(bm_prev, i3) ? i3 : (uint32_t)row;
+    }
+    const uint4 v0 = oldr[(uint64_t)i0 * 4 + sub];
+    const uint4 v1 = oldr[(uint64_t)i1 * 4 + sub];
+    const uint4 v2 = oldr[(uint64_t)i2 * 4 + sub];
+    const uint4 v3 = oldr[(uint64_t)i3 * 4 + sub];
+    acc = vmax_u8x16(vmax_u8x16(acc, v0), vmax_u8x16(vmax_u8x16(v1, v2), v3));
+  }
+  const unsigned ball = __ballot_sync(0xffffffffu, ne_u4(acc, own));
+  const bool changed = ((ball >> (lane & ~3u)) & 0xFu) != 0u;
+  if (!live) return;
+  if (changed || bm_test(bm_prev, (uint32_t)row)) newr[row * 4 + sub] = acc;
+  if (changed && sub == 0) atomicOr(bm_cur + (row >> 5), 1u << (row & 31));
+}
+
+// ---- pull, long rows: one warp per <=CHUNK_EDGES work item ---------------------------------------------
+template <bool FRONTIER>
+__global__ void __launch_bounds__(256) k_pull_warp(uint64_t n_items, uint64_t first_multi_free_item,
+    const uint32_t* __restrict__ item_row, const uint32_t* __restrict__ item_start, uint32_t warp_row_begin,
+    const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col, uint32_t col_base,
+    const uint4* __restrict__ oldr, uint4* __restrict__ newr, uint4* __restrict__ partial,
+    const uint32_t* __restrict__ bm_prev, uint32_t* __restrict__ bm_cur) {
+  const uint64_t item = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  if (item >= n_items) return;  // whole warp exits together
+  const uint32_t lane = threadIdx.x & 31, sub = lane & 3, q = lane >> 2;
+  const uint32_t row = item_row[item];
+  const uint32_t chunk = (uint32_t)item - item_start[row - warp_row_begin];
+  const uint32_t rs = row_ptr[row] - col_base, re = row_ptr[row + 1] - col_base;
+  const uint32_t e0 = rs + chunk * (uint32_t)CHUNK_EDGES;
+  const uint32_t e1 = min(e0 + (uint32_t)CHUNK_EDGES, re);
+  uint4 acc = make_uint4(0, 0, 0, 0);
+  const uint32_t NONE = 0xFFFFFFFFu;
+  uint32_t nxt = (e0 + lane < e1) ? ld_stream_u32(col + e0 + lane) : NONE;
+  for (uint32_t base = e0; base < e1; base += 32) {
+    uint32_t mine = nxt;
+    nxt = (base + 32 + lane < e1) ? ld_stream_u32(col + base + 32 + lane) : NONE;
+    if (FRONTIER && mine != NONE && !bm_test(bm_prev, mine)) mine = NONE;
+    const uint32_t i0 = __shfl_sync(0xffffffffu, mine, q);
+    const uint32_t i1 = __shfl_sync(0xffffffffu, mine, q + 8);
+    const uint32_t i2 = __shfl_sync(0xffffffffu, mine, q + 16);
+    const uint32_t i3 = __shfl_sync(0xffffffffu, mine, q + 24);
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    uint4 v0 = zero, v1 = zero, v2 = zero, v3 = zero;
+    if (i0 != NONE) v0 = oldr[(uint64_t)i0 * 4 + sub];
+    if (i1 != NONE) v1 = oldr[(uint64_t)i1 * 4 + sub];
+    if (i2 != NONE) v2 = oldr[(uint64_t)i2 * 4 + sub];
+    if (i3 != NONE) v3 = oldr[(uint64_t)i3 * 4 + sub];
+    acc = vmax_u8x16(vmax_u8x16(acc, v0), vmax_u8x16(vmax_u8x16(v1, v2), v3));
+  }
+#pragma unroll
+  for (int off = 4; off < 32; off <<= 1) {
+    uint4 o;
+    o.x = __shfl_xor_sync(0xffffffffu, acc.x, off); o.y = __shfl_xor_sync(0xffffffffu, acc.y, off);
+    o.z = __shfl_xor_sync(0xffffffffu, acc.z, off); o.w = __shfl_xor_sync(0xffffffffu, acc.w, off);
+    acc = vmax_u8x16(acc, o);
+  }
+  if (item < first_multi_free_item) {  // this row spans several items: park the partial maximum
+    if (q == 0) partial[item * 4 + sub] = acc;
+    return;
+  }
+  const uint4 own = oldr[(uint64_t)row * 4 + sub];
+  acc = vmax_u8x16(acc, own);
+  const unsigned ball = __ballot_sync(0xffffffffu, ne_u4(acc, own));
+  const bool changed = (ball & 0xFu) != 0u;
+  if (q == 0) {
+    if (changed || bm_test(bm_prev, row)) newr[(uint64_t)row * 4 + sub] = acc;
+    if (changed && sub == 0) atomicOr(bm_cur + (row >> 5), 1u << (row & 31));
+  }
+}
+
+// rows spanning several work items: one warp reduces the parked partials
+__global__ void __launch_bounds__(256) k_pull_merge(uint64_t n_rows, const uint32_t* __restrict__ item_start,
+    uint32_t warp_row_begin, const uint4* __restrict__ partial, const uint4* __restrict__ oldr,
+    uint4* __restrict__ newr, const uint32_t* __restrict__ bm_prev, uint32_t* __restrict__ bm_cur) {
+  const uint64_t r = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_rows) return;
+  const uint32_t lane = threadIdx.x & 31, sub = lane & 3, q = lane >> 2;
+  const uint32_t row = warp_row_begin + (uint32_t)r;
+  const uint32_t i0 = item_start[r], i1 = item_start[r + 1];
+  uint4 acc = make_uint4(0, 0, 0, 0);
+  for (uint32_t it = i0 + q; it < i1; it += 8) acc = vmax_u8x16(acc, partial[(uint64_t)it * 4 + sub]);
+#pragma unroll
+  for (int off = 4; off < 32; off <<= 1) {
+    uint4 o;
+    o.x = __shfl_xor_sync(0xffffffffu, acc.x, off); o.y = __shfl_xor_sync(0xffffffffu, acc.y, off);
+    o.z = __shfl_xor_sync(0xffffffffu, acc.z, off); o.w = __shfl_xor_sync(0xffffffffu, acc.w, off);
+    acc = vmax_u8x16(acc, o);
+  }
+  const uint4 own = oldr[(uint64_t)row * 4 + sub];
+  acc = vmax_u8x16(acc, own);
+  const unsigned ball = __ballot_sync(0xffffffffu, ne_u4(acc, own));
+  const bool changed = (ball & 0xFu) != 0u;
+  if (q == 0) {
+    if (changed || bm_test(bm_prev, row)) newr[(uint64_t)row * 4 + sub] = acc;
+    if (changed && sub == 0) atomicOr(bm_cur + (row >> 5), 1u << (row & 31));
+  }
+}
+
+// ---- push from a small frontier (update_changed_counters, harmonic.rs:75-114) --------------------------
+__global__ void k_frontier_compact(const uint32_t* __restrict__ bm, uint64_t words, const uint32_t* __restrict__ fwd_ptr,
+                                   uint32_t* list, uint32_t* outdeg, unsigned long long* counter) {
+  uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (w >= words) return;
+  uint32_t m = bm[w];
+  if (!m) return;
+  unsigned long long pos = atomicAdd(counter, (unsigned long long)__popc(m));
+  while (m) {
+    int b = __ffs(m) - 1; m &= m - 1;
+    uint32_t v = (uint32_t)(w * 32 + b);
+    list[pos] = v; outdeg[pos] = fwd_ptr[v + 1] - fwd_ptr[v]; pos++;
+  }
+}
+__global__ void k_copy_stale(const uint32_t* __restrict__ list, uint64_t n, const uint4* __restrict__ oldr,
+                             uint4* __restrict__ newr) {
+  uint64_t gt = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  uint64_t i = gt >> 2;
+  if (i >= n) return;
+  uint64_t v = list[i];
+  newr[v * 4 + (gt & 3)] = oldr[v * 4 + (gt & 3)];
+}
+__global__ void __launch_bounds__(256) k_push(const uint32_t* __restrict__ list, const uint32_t* __restrict__ off,
+    uint32_t n_front, uint64_t n_slots, const uint32_t* __restrict__ fwd_ptr, const uint32_t* __restrict__ fwd_dst,
+    const uint32_t* __restrict__ old32, uint32_t* new32, uint32_t* __restrict__ bm_cur) {
+  const uint32_t lane = threadIdx.x & 31, l = lane & 15;
+  const uint64_t hw = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 4;
+  const uint64_t nhw = ((uint64_t)gridDim.x * blockDim.x) >> 4;
+  for (uint64_t s = hw; s < ((n_slots + 1) & ~1ull); s += nhw) {  // both halves of a warp iterate together
+    bool changed = false;
+    uint32_t v = 0;
+    if (s < n_slots) {
+      uint32_t lo = 0, hi = n_front;  // last j with off[j] <= s
+      while (lo + 1 < hi) { uint32_t mid = (lo + hi) >> 1; if (off[mid] <= s) lo = mid; else hi = mid; }
+      const uint32_t u = list[lo];
+      v = fwd_dst[fwd_ptr[u] + (uint32_t)(s - off[lo])];
+      const uint32_t mine = old32[(uint64_t)u * 16 + l];
+      uint32_t* addr = new32 + (uint64_t)v * 16 + l;
+      uint32_t cur = *addr;
+      uint32_t m = __vmaxu4(cur, mine);
+      while (m != cur) {
+        const uint32_t prev = atomicCAS(addr, cur, m);
+        if (prev == cur) { changed = true; break; }
+        cur = prev; m = __vmaxu4(cur, mine);
+      }
+    }
+    const unsigned ball = __ballot_sync(0xffffffffu, changed);
+    const unsigned half = (lane < 16) ? (ball & 0xFFFFu) : (ball >> 16);
+    if (half && l == 0) atomicOr(bm_cur + (v >> 5), 1u << (v & 31));
+  }
+}
+
+// ---- centrality update for the nodes touched this iteration -------------------------------------------
+__global__ void __launch_bounds__(256) k_finalize(uint64_t row_begin, uint64_t row_end,
+    const uint4* __restrict__ newr, const uint32_t* __restrict__ bm_prev, const uint32_t* __restrict__ bm_cur,
+    uint64_t* __restrict__ size_cache, double* __restrict__ ksum, double* __restrict__ kerr,
+    const uint32_t* __restrict__ fwd_ptr, double t_plus_1, unsigned long long* counters) {
+  __shared__ HllTables tab;
+  __shared__ unsigned long long s_cnt[2];
+  for (int i = threadIdx.x; i < (int)(sizeof(HllTables) / 8); i += blockDim.x) ((double*)&tab)[i] = ((const double*)&c_tab)[i];
+  if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t v = row_begin + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  unsigned long long my_changed = 0, my_out = 0;
+  if (v < row_end) {
+    const bool bc = bm_test(bm_cur, (uint32_t)v), bp = bm_test(bm_prev, (uint32_t)v);
+    if (bc || bp) {
+      double s = ksum[v], e = kerr[v];
+      if (bc) {
+        uint32_t w[16];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const uint4 x = newr[v * 4 + q];
+          w[4 * q] = x.x; w[4 * q + 1] = x.y; w[4 * q + 2] = x.z; w[4 * q + 3] = x.w;
+        }
+        const uint64_t sn = hll64_size(w, &tab);
+        const uint64_t so = size_cache[v];
+        const uint64_t d = sn >= so ? sn - so : 0ull;  // checked_sub().unwrap_or_default()
+        kahan_add(s, e, __ddiv_rn(__ull2double_rn(d), t_plus_1));
+        size_cache[v] = sn;
+        my_changed = 1;
+        if (fwd_ptr) my_out = fwd_ptr[v + 1] - fwd_ptr[v];
+      } else {
+        kahan_add(s, e, 0.0);  // the reference adds 0/(t+1) to every unchanged node; once is enough
+      }
+      ksum[v] = s; kerr[v] = e;
+    }
+  }
+  // block reduce the two counters
+  for (int off = 16; off; off >>= 1) {
+    my_changed += __shfl_down_sync(0xffffffffu, my_changed, off);
+    my_out += __shfl_down_sync(0xffffffffu, my_out, off);
+  }
+  if ((threadIdx.x & 31) == 0 && (my_changed | my_out)) { atomicAdd(&s_cnt[0], my_changed); atomicAdd(&s_cnt[1], my_out); }
+  __syncthreads();
+  if (threadIdx.x == 0 && (s_cnt[0] | s_cnt[1])) { atomicAdd(counters + 0, s_cnt[0]); atomicAdd(counters + 1, s_cnt[1]); }
+}
+
+// ---- result / debug gathers ------------------------------------------------------------------------------
+__global__ void k_result_flags(const uint32_t* __restrict__ inv, const double* __restrict__ ksum, uint64_t N,
+                               uint64_t row_begin, uint64_t row_end, double norm, uint32_t* flag, double* val) {
+  uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  const uint32_t v = inv[r];
+  double c = ksum[v];
+  const bool keep = (c > 0.0) && v >= row_begin && v < row_end;  // normalize_centralities harmonic.rs:178-195
+  c = __ddiv_rn(c, norm);
+  if (isinf(c) || isnan(c)) c = 0.0;
+  flag[r] = keep ? 1u : 0u;
+  val[r] = c;
+}
+__global__ void k_result_scatter(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos,
+                                 const double* __restrict__ val, const uint64_t* __restrict__ id_lo,
+                                 const uint64_t* __restrict__ id_hi, uint64_t N, uint64_t cap, uint64_t* out_lo,
+                                 uint64_t* out_hi, double* out_c) {
+  uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (r >= N || !flag[r]) return;
+  uint32_t p = pos[r];
+  if (p >= cap) return;
+  out_lo[p] = id_lo[r]; out_hi[p] = id_hi[r]; out_c[p] = val[r];
+}
+__global__ void k_gather_regs(const uint32_t* __restrict__ inv, const uint4* __restrict__ regs, uint64_t first,
+                              uint64_t count, uint4* out) {
+  uint64_t gt = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  uint64_t i = gt >> 2;
+  if (i >= count) return;
+  out[i * 4 + (gt & 3)] = regs[(uint64_t)inv[first + i] * 4 + (gt & 3)];
+}
+__global__ void k_gather_f64x2(const uint32_t* __restrict__ inv, const double* __restrict__ a, const double* __restrict__ b,
+                               uint64_t first, uint64_t count, double* oa, double* ob) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  uint32_t v = inv[first + i];
+  oa[i] = a[v]; ob[i] = b[v];
+}
+
+static double env_f(const char* name, double dflt) {
+  const char* s = getenv(name);
+  return s ? atof(s) : dflt;
+}
+
+int hb_alloc_state(sb200_graph* g) {
+  g->dense_frac = env_f("SB200_DENSE_FRAC", g->dense_frac);
+  g->push_div = env_f("SB200_PUSH_DIV", g->push_div);
+  g->force_mode = (int)env_f("SB200_FORCE_MODE", (double)g->force_mode);
+  const uint64_t N = g->N;
+  const uint64_t words = (N + 31) / 32;
+  SB_TRY(load_tables(g->device));
+  SB_TRY(g->regs[0].alloc(std::max<uint64_t>(N, 1) * 64));
+  SB_TRY(g->regs[1].alloc(std::max<uint64_t>(N, 1) * 64));
+  SB_TRY(g->bm[0].alloc(words + 1)); SB_TRY(g->bm[1].alloc(words + 1));
+  SB_TRY(g->size_cache.alloc(std::max<uint64_t>(N, 1)));
+  SB_TRY(g->kahan_sum.alloc(std::max<uint64_t>(N, 1))); SB_TRY(g->kahan_err.alloc(std::max<uint64_t>(N, 1)));
+  SB_TRY(g->counters.alloc(8));
+  if (!g->h_counters) SB_CUDA(cudaMallocHost((void**)&g->h_counters, 8 * sizeof(unsigned long long)));
+  return SB200_OK;
+}
+
+int hb_reset(sb200_graph* g) {
+  cudaStream_t s = g->stream;
+  const uint64_t N = g->N, words = (N + 31) / 32;
+  g->cur = 0; g->bcur = 0; g->t = 0; g->has_changes = N > 0; g->exchange_pending = false;
+  g->n_changed_prev = N; g->frontier_edges_prev = g->E_kept;
+  if (N == 0) return SB200_OK;
+  SB_LAUNCH(k_hb_init, div_up(N, 256), 256, 0, s, g->id_lo.p, g->perm.p, N, (uint4*)g->regs[0].p, (uint4*)g->regs[1].p,
+            g->size_cache.p, g->kahan_sum.p, g->kahan_err.p);
+  SB_CHECK_LAUNCH();
+  SB_LAUNCH(k_bm_fill, div_up(words, 256), 256, 0, s, g->bm[0].p, N, words);  // changed_nodes filled, harmonic.rs:223-225
+  SB_CHECK_LAUNCH();
+  SB_CUDA(cudaMemsetAsync(g->bm[1].p, 0, (words + 1) * 4, s));
+  SB_CUDA(cudaStreamSynchronize(s));
+  return SB200_OK;
+}
+
+#define PROF_BEGIN(g, fam) do { if ((g)->profiling) { SB_CUDA(cudaEventRecord((g)->prof_ev[fam][0], (g)->stream)); } } while (0)
+#define PROF_END(g, fam, bytes) do { if ((g)->profiling) { SB_CUDA(cudaEventRecord((g)->prof_ev[fam][1], (g)->stream)); \
+    (g)->prof_used[fam] = true; (g)->prof_step_bytes[fam] = (double)(bytes); } } while (0)
+
+template <bool FRONTIER>
+static int launch_pull(sb200_graph* g, const uint4* oldr, uint4* newr, const uint32_t* bmp, uint32_t* bmc) {
+  cudaStream_t s = g->stream;
+  const int FW = FRONTIER ? sb200_graph::F_PULL_WARP_FRONT : sb200_graph::F_PULL_WARP_DENSE;
+  const int FQ = FRONTIER ? sb200_graph::F_PULL_QUAD_FRONT : sb200_graph::F_PULL_QUAD_DENSE;
+  const double per_edge = FRONTIER ? 4.0 : 68.0;  // col index (+ the 64-B gather when every source is read)
+  if (g->n_items) {
+    PROF_BEGIN(g, FW);
+    SB_LAUNCH(k_pull_warp<FRONTIER>, div_up(g->n_items * 32, 256), 256, 0, s, g->n_items, g->n_multi_items,
+              g->item_row.p, g->item_start.p, (uint32_t)g->warp_row_begin, g->row_ptr.p, g->col.p, g->col_base, oldr, newr,
+              g->partial.p, bmp, bmc);
+    SB_CHECK_LAUNCH();
+    PROF_END(g, FW, per_edge * (double)g->E_warp + 68.0 * (double)(g->warp_row_end - g->warp_row_begin - g->n_multi_rows));
+  }
+  if (g->n_multi_rows) {
+    PROF_BEGIN(g, sb200_graph::F_PULL_MERGE);
+    SB_LAUNCH(k_pull_merge, div_up(g->n_multi_rows * 32, 256), 256, 0, s, g->n_multi_rows, g->item_start.p,
+              (uint32_t)g->warp_row_begin, g->partial.p, oldr, newr, bmp, bmc);
+    SB_CHECK_LAUNCH();
+    PROF_END(g, sb200_graph::F_PULL_MERGE, 64.0 * (double)g->n_multi_items + 68.0 * (double)g->n_multi_rows);
+  }
+  const uint64_t nq = g->quad_row_end - g->quad_row_begin;
+  if (nq) {
+    PROF_BEGIN(g, FQ);
+    SB_LAUNCH(k_pull_quad<FRONTIER>, div_up(nq * 4, 256), 256, 0, s, g->quad_row_begin, g->quad_row_end, g->row_ptr.p,
+              g->col.p, g->col_base, oldr, newr, bmp, bmc);
+    SB_CHECK_LAUNCH();
+    PROF_END(g, FQ, per_edge * (double)g->E_quad + 68.0 * (double)nq);
+  }
+  return SB200_OK;
+}
+
+static int run_push(sb200_graph* g, const uint4* oldr, uint4* newr, const uint32_t* bmp, uint32_t* bmc) {
+  cudaStream_t s = g->stream;
+  const uint64_t N = g->N, words = (N + 31) / 32;
+  const uint64_t nf = g->n_changed_prev, slots = g->frontier_edges_prev;
+  if (g->frontier_list.n < nf + 1) { SB_TRY(g->frontier_list.alloc(nf + 1 + (nf >> 2))); }
+  if (g->frontier_off.n < 2 * (nf + 1)) { SB_TRY(g->frontier_off.alloc(2 * (nf + 1) + (nf >> 1))); }
+  uint32_t* outdeg = g->frontier_off.p + (g->frontier_off.n / 2);
+  SB_CUDA(cudaMemsetAsync(g->counters.p + 2, 0, sizeof(unsigned long long), s));
+  SB_LAUNCH(k_frontier_compact, div_up(words, 256), 256, 0, s, bmp, words, g->fwd_ptr.p, g->frontier_list.p, outdeg,
+            g->counters.p + 2);
+  SB_CHECK_LAUNCH();
+  size_t need = 0;
+  SB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, outdeg, g->frontier_off.p, (int64_t)nf, s));
+  if (g->cub_tmp.n < need) SB_TRY(g->cub_tmp.alloc(need + 256));
+  SB_CUDA(cub::DeviceScan::ExclusiveSum(g->cub_tmp.p, need, outdeg, g->frontier_off.p, (int64_t)nf, s));
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  SB_LAUNCH(k_copy_stale, div_up(nf * 4, 256), 256, 0, s, g->frontier_list.p, nf, oldr, newr);
+  SB_CHECK_LAUNCH();
+  if (slots) {
+    unsigned grid = (unsigned)std::min<uint64_t>(div_up(slots * 16, 256), 148u * 16u);
+    PROF_BEGIN(g, sb200_graph::F_PUSH);
+    SB_LAUNCH(k_push, grid, 256, 0, s, g->frontier_list.p, g->frontier_off.p, (uint32_t)nf, slots, g->fwd_ptr.p,
+              g->fwd_dst.p, (const uint32_t*)oldr, (uint32_t*)newr, bmc);
+    SB_CHECK_LAUNCH();
+    PROF_END(g, sb200_graph::F_PUSH, 132.0 * (double)slots);
+  }
+  return SB200_OK;
+}
+
+int hb_step(sb200_graph* g, sb200_iter_stats* st) {
+  cudaStream_t s = g->stream;
+  const uint64_t N = g->N, words = (N + 31) / 32;
+  if (g->exchange_pending) SB_FAIL(SB200_ESTATE, "sb200_hyperball_exchange_done() must be called between steps of a sharded handle");
+  if (N == 0) { g->has_changes = false; if (st) memset(st, 0, sizeof(*st)); return SB200_OK; }
+  const uint4* oldr = (const uint4*)g->regs[g->cur].p;
+  uint4* newr = (uint4*)g->regs[g->cur ^ 1].p;
+  const uint32_t* bmp = g->bm[g->bcur].p;
+  uint32_t* bmc = g->bm[g->bcur ^ 1].p;
+  const double dense_frac = g->dense_frac, push_div = g->push_div;
+  const int force_mode = g->force_mode;
+  int mode;
+  const double E = (double)std::max<uint64_t>(g->E_kept, 1);
+  if (g->world == 1) {
+    const double fe = (double)g->frontier_edges_prev;
+    if (fe >= dense_frac * E) mode = 0;
+    else if (g->has_fwd && fe * push_div <= E) mode = 2;
+    else mode = 1;
+  } else {
+    mode = ((double)g->n_changed_prev >= 0.25 * (double)N) ? 0 : 1;
+  }
+  if (force_mode >= 0 && (force_mode < 2 || (g->has_fwd && g->world == 1))) mode = force_mode;
+  SB_CUDA(cudaEventRecord(g->ev0, s));
+  SB_CUDA(cudaMemsetAsync(bmc, 0, (words + 1) * 4, s));
+  SB_CUDA(cudaMemsetAsync(g->counters.p, 0, 8 * sizeof(unsigned long long), s));
+  if (mode == 0) SB_TRY(launch_pull<false>(g, oldr, newr, bmp, bmc));
+  else if (mode == 1) SB_TRY(launch_pull<true>(g, oldr, newr, bmp, bmc));
+  else SB_TRY(run_push(g, oldr, newr, bmp, bmc));
+  const uint64_t nrows = g->row_end - g->row_begin;
+  if (nrows) {
+    PROF_BEGIN(g, sb200_graph::F_FINALIZE);
+    SB_LAUNCH(k_finalize, div_up(nrows, 256), 256, 0, s, g->row_begin, g->row_end, newr, bmp, bmc, g->size_cache.p,
+              g->kahan_sum.p, g->kahan_err.p, g->has_fwd ? g->fwd_ptr.p : (const uint32_t*)nullptr, (double)(g->t + 1),
+              g->counters.p);
+    SB_CHECK_LAUNCH();
+    PROF_END(g, sb200_graph::F_FINALIZE, 0.25 * (double)nrows);  // 2 bitmap bits/row; + 112 B per changed row below
+  }
+  SB_CUDA(cudaMemcpyAsync(g->h_counters, g->counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  SB_CUDA(cudaEventRecord(g->ev1, s));
+  SB_CUDA(cudaStreamSynchronize(s));
+  float ms = 0; cudaEventElapsedTime(&ms, g->ev0, g->ev1);
+  if (g->profiling) {
+    g->prof_step_bytes[sb200_graph::F_FINALIZE] += 112.0 * (double)g->h_counters[0];
+    for (int f = 0; f < sb200_graph::F_COUNT; f++) if (g->prof_used[f]) {
+      float kms = 0; cudaEventElapsedTime(&kms, g->prof_ev[f][0], g->prof_ev[f][1]);
+      g->prof_launches[f]++; g->prof_ms[f] += kms; g->prof_bytes[f] += g->prof_step_bytes[f];
+      g->prof_used[f] = false;
+    }
+  }
+  if (st) {
+    st->t = g->t; st->mode = (uint32_t)mode; st->n_changed = g->h_counters[0];
+    st->edges_active = g->frontier_edges_prev; st->ms = ms;
+  }
+  g->cur ^= 1; g->bcur ^= 1; g->t += 1;
+  if (g->world == 1) {
+    g->n_changed_prev = g->h_counters[0];
+    g->frontier_edges_prev = g->h_counters[1];
+    g->has_changes = g->h_counters[0] != 0;
+  } else {
+    g->n_changed_prev = g->h_counters[0];
+    g->exchange_pending = true;
+  }
+  return SB200_OK;
+}
+
+int hb_result(sb200_graph* g, uint64_t* id_lo, uint64_t* id_hi, double* cent, uint64_t cap, uint64_t* len) {
+  cudaStream_t s = g->stream;
+  const uint64_t N = g->N;
+  if (N == 0) { *len = 0; return SB200_OK; }
+  DevBuf<uint32_t> flag, pos; DevBuf<double> val;
+  SB_TRY(flag.alloc(N + 1)); SB_TRY(pos.alloc(N + 1)); SB_TRY(val.alloc(N));
+  SB_CUDA(cudaMemsetAsync(flag.p + N, 0, 4, s));
+  const double norm = (double)(N - 1);
+  SB_LAUNCH(k_result_flags, div_up(N, 256), 256, 0, s, g->inv.p, g->kahan_sum.p, N, g->row_begin, g->row_end, norm, flag.p, val.p);
+  SB_CHECK_LAUNCH();
+  size_t need = 0;
+  SB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, flag.p, pos.p, (int64_t)(N + 1), s));
+  if (g->cub_tmp.n < need) SB_TRY(g->cub_tmp.alloc(need + 256));
+  SB_CUDA(cub::DeviceScan::ExclusiveSum(g->cub_tmp.p, need, flag.p, pos.p, (int64_t)(N + 1), s));
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  uint32_t total = 0;
+  SB_CUDA(cudaMemcpyAsync(&total, pos.p + N, 4, cudaMemcpyDeviceToHost, s));
+  SB_CUDA(cudaStreamSynchronize(s));
+  *len = total;
+  if (!cent) return SB200_OK;
+  const uint64_t k = std::min<uint64_t>(total, cap);
+  if (k == 0) return SB200_OK;
+  DevBuf<uint64_t> olo, ohi; DevBuf<double> oc;
+  SB_TRY(olo.alloc(k)); SB_TRY(ohi.alloc(k)); SB_TRY(oc.alloc(k));
+  SB_LAUNCH(k_result_scatter, div_up(N, 256), 256, 0, s, flag.p, pos.p, val.p, g->id_lo.p, g->id_hi.p, N, k, olo.p, ohi.p, oc.p);
+  SB_CHECK_LAUNCH();
+  SB_CUDA(cudaMemcpyAsync(id_lo, olo.p, k * 8, cudaMemcpyDefault, s));
+  SB_CUDA(cudaMemcpyAsync(id_hi, ohi.p, k * 8, cudaMemcpyDefault, s));
+  SB_CUDA(cudaMemcpyAsync(cent, oc.p, k * 8, cudaMemcpyDefault, s));
+  SB_CUDA(cudaStreamSynchronize(s));
+  return SB200_OK;
+}
+
+int hb_registers(sb200_graph* g, uint64_t first, uint64_t count, uint8_t* out) {
+  if (first + count > g->N) SB_FAIL(SB200_EINVAL, "register range [%llu,+%llu) outside %llu nodes", (unsigned long long)first, (unsigned long long)count, (unsigned long long)g->N);
+  if (!count) return SB200_OK;
+  DevBuf<uint4> tmp; SB_TRY(tmp.alloc(count * 4));
+  SB_LAUNCH(k_gather_regs, div_up(count * 4, 256), 256, 0, g->stream, g->inv.p, (const uint4*)g->regs[g->cur].p, first, count, tmp.p);
+  SB_CHECK_LAUNCH();
+  SB_CUDA(cudaMemcpyAsync(out, tmp.p, count * 64, cudaMemcpyDefault, g->stream));
+  SB_CUDA(cudaStreamSynchronize(g->stream));
+  return SB200_OK;
+}
+int hb_kahan(sb200_graph* g, uint64_t first, uint64_t count, double* sum, double* err) {
+  if (first + count > g->N) SB_FAIL(SB200_EINVAL, "range outside the node set");
+  if (!count) return SB200_OK;
+  DevBuf<double> a, b; SB_TRY(a.alloc(count)); SB_TRY(b.alloc(count));
+  SB_LAUNCH(k_gather_f64x2, div_up(count, 256), 256, 0, g->stream, g->inv.p, g->kahan_sum.p, g->kahan_err.p, first, count, a.p, b.p);
+  SB_CHECK_LAUNCH();
+  SB_CUDA(cudaMemcpyAsync(sum, a.p, count * 8, cudaMemcpyDefault, g->stream));
+  SB_CUDA(cudaMemcpyAsync(err, b.p, count * 8, cudaMemcpyDefault, g->stream));
+  SB_CUDA(cudaStreamSynchronize(g->stream));
+  return SB200_OK;
+}
+
+}  // namespace sb200

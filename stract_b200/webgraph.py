@@ -1,0 +1,330 @@
+"""Host-side mirror of the reference's webgraph-centrality interface, backed by libstract_b200.so.
+
+Mirrors (same names / argument meaning / behaviour):
+  RelFlags, SKIPPED_REL           crates/core/src/webpage/html/links.rs:114-141, harmonic.rs:36-49
+  Edge / Webgraph.insert/commit/host_edges/host_nodes
+                                  crates/core/src/webgraph/{edge.rs:30-35,mod.rs:157-194}
+  HarmonicCentrality.calculate/get/iter/len
+                                  crates/core/src/webgraph/centrality/harmonic.rs:289-311
+  ShardedHarmonicCentrality       the AMPC job (entrypoint/ampc/harmonic_centrality/*): one process
+                                  per GPU, the DHT max-upsert replaced by an all-gather of owned rows
+
+NodeID is a python int holding the u128 (crates/core/src/webgraph/node.rs:37).  All compute runs in
+the CUDA library; this module only marshals buffers.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import GraphInfo, IterStats, check, lib
+
+
+class RelFlags:
+    ALTERNATE = 1 << 0; AUTHOR = 1 << 1; CANONICAL = 1 << 2; HELP = 1 << 3; ICON = 1 << 4
+    LICENSE = 1 << 5; ME = 1 << 6; NEXT = 1 << 7; NOFOLLOW = 1 << 8; PREV = 1 << 9
+    PRIVACY_POLICY = 1 << 10; SEARCH = 1 << 11; STYLESHEET = 1 << 12; TAG = 1 << 13
+    TERMS_OF_SERVICE = 1 << 14; SPONSORED = 1 << 15; IS_IN_FOOTER = 1 << 16
+    IS_IN_NAVIGATION = 1 << 17; LINK_TAG = 1 << 18; SCRIPT_TAG = 1 << 19; META_TAG = 1 << 20
+    SAME_ICANN_DOMAIN = 1 << 21; UGC = 1 << 22
+
+
+SKIPPED_REL = (RelFlags.TAG | RelFlags.NOFOLLOW | RelFlags.SPONSORED | RelFlags.IS_IN_FOOTER
+               | RelFlags.IS_IN_NAVIGATION | RelFlags.PRIVACY_POLICY | RelFlags.TERMS_OF_SERVICE
+               | RelFlags.SEARCH | RelFlags.LINK_TAG | RelFlags.SCRIPT_TAG | RelFlags.SAME_ICANN_DOMAIN
+               | RelFlags.UGC)
+assert SKIPPED_REL == 0x6FED00
+
+_M64 = (1 << 64) - 1
+
+
+class Edge:
+    """SmallEdge{from, to, rel_flags} (crates/core/src/webgraph/edge.rs:30-35)."""
+    __slots__ = ("from_", "to", "rel_flags")
+
+    def __init__(self, from_, to, rel_flags=0):
+        self.from_, self.to, self.rel_flags = int(from_), int(to), int(rel_flags)
+
+    @classmethod
+    def new_test(cls, from_, to):  # Edge::new_test, edge.rs:198-206
+        return cls(from_, to, 0)
+
+
+def _ptr(a):
+    """(pointer, keepalive) of a numpy array or a torch tensor (host or cuda), dtype uint64/int64."""
+    if a is None:
+        return None, None
+    if hasattr(a, "data_ptr"):  # torch tensor
+        assert a.is_contiguous() and a.element_size() == 8
+        return a.data_ptr(), a
+    a = np.ascontiguousarray(a, np.uint64)
+    return a.ctypes.data, a
+
+
+class Webgraph:
+    """A host graph as the stream `Webgraph::host_edges()` yields it (SoA of from/to/rel_flags).
+
+    Built either edge by edge (`insert` + `commit`, like the reference's tests) or from arrays
+    (`from_arrays`; numpy or torch tensors, host or already resident in HBM)."""
+
+    def __init__(self):
+        self._pending = []
+        self.from_lo = self.from_hi = self.to_lo = self.to_hi = self.rel = None
+        self.n_edges = 0
+
+    @classmethod
+    def from_arrays(cls, from_lo, from_hi, to_lo, to_hi, rel_flags):
+        g = cls()
+        g.from_lo, g.from_hi, g.to_lo, g.to_hi, g.rel = from_lo, from_hi, to_lo, to_hi, rel_flags
+        g.n_edges = int(from_lo.shape[0]) if hasattr(from_lo, "shape") else len(from_lo)
+        return g
+
+    def insert(self, edge):
+        self._pending.append(edge)
+
+    def commit(self):
+        if not self._pending:
+            return
+        n = len(self._pending)
+        cols = [np.zeros(n, np.uint64) for _ in range(5)]
+        for i, e in enumerate(self._pending):
+            cols[0][i] = e.from_ & _M64; cols[1][i] = e.from_ >> 64
+            cols[2][i] = e.to & _M64; cols[3][i] = e.to >> 64
+            cols[4][i] = e.rel_flags
+        if self.n_edges:
+            old = [np.asarray(a, np.uint64) for a in (self.from_lo, self.from_hi, self.to_lo, self.to_hi, self.rel)]
+            cols = [np.concatenate([o, c]) for o, c in zip(old, cols)]
+        self.from_lo, self.from_hi, self.to_lo, self.to_hi, self.rel = cols
+        self.n_edges = len(cols[0])
+        self._pending = []
+
+    def host_edges(self):
+        """Iterate SmallEdge (host arrays only; debugging aid -- the library consumes the arrays)."""
+        for i in range(self.n_edges):
+            yield Edge((int(self.from_hi[i]) << 64) | int(self.from_lo[i]),
+                       (int(self.to_hi[i]) << 64) | int(self.to_lo[i]), int(self.rel[i]))
+
+    def host_nodes(self):
+        s = set()
+        for e in self.host_edges():
+            s.add(e.from_); s.add(e.to)
+        return s
+
+
+class DeviceGraph:
+    """Owner of an `sb200_graph*`: the staged CSR + HyperBall state in HBM."""
+
+    def __init__(self, graph, device=0, rank=0, world_size=1, skipped_rel=SKIPPED_REL):
+        self._h = C.c_void_p()
+        self._L = lib()
+        graph.commit()
+        ptrs = [_ptr(a) for a in (graph.from_lo, graph.from_hi, graph.to_lo, graph.to_hi, graph.rel)]
+        self._keep = [p[1] for p in ptrs]
+        check(self._L.sb200_graph_create(*(p[0] for p in ptrs), graph.n_edges, skipped_rel, device, rank,
+                                         world_size, C.byref(self._h)))
+        self._keep = None
+        self.world_size, self.rank = world_size, rank
+
+    def info(self):
+        gi = GraphInfo()
+        check(self._L.sb200_graph_get_info(self._h, C.byref(gi)))
+        return {k: getattr(gi, k) for k, _ in GraphInfo._fields_}
+
+    def reset(self):
+        check(self._L.sb200_hyperball_reset(self._h))
+
+    def set_policy(self, dense_frac=-1.0, push_div=-1.0, force_mode=-1):
+        check(self._L.sb200_hyperball_set_policy(self._h, dense_frac, push_div, force_mode))
+
+    def step(self):
+        st = IterStats()
+        check(self._L.sb200_hyperball_step(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in IterStats._fields_}
+
+    def run(self, max_iters=0, cap=256):
+        done = C.c_uint32(0)
+        arr = (IterStats * cap)()
+        check(self._L.sb200_hyperball_run(self._h, max_iters, C.byref(done), arr, cap))
+        n = min(done.value, cap)
+        return done.value, [{k: getattr(arr[i], k) for k, _ in IterStats._fields_} for i in range(n)]
+
+    def last_run_ms(self):
+        ms = C.c_float(0)
+        check(self._L.sb200_hyperball_last_run_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def set_profiling(self, on=True):
+        check(self._L.sb200_hyperball_set_profiling(self._h, 1 if on else 0))
+
+    def profile(self):
+        arr = (_lib.KernelProf * 16)()
+        n = C.c_uint32(0)
+        check(self._L.sb200_hyperball_get_profile(self._h, arr, 16, C.byref(n)))
+        return [dict(name=arr[i].name.decode(), launches=arr[i].launches, ms=arr[i].ms, alg_bytes=arr[i].alg_bytes)
+                for i in range(n.value)]
+
+    def result(self):
+        ln = C.c_uint64(0)
+        check(self._L.sb200_hyperball_result(self._h, None, None, None, 0, C.byref(ln)))
+        k = ln.value
+        lo = np.zeros(k, np.uint64); hi = np.zeros(k, np.uint64); c = np.zeros(k, np.float64)
+        if k:
+            check(self._L.sb200_hyperball_result(self._h, lo.ctypes.data, hi.ctypes.data, c.ctypes.data, k, C.byref(ln)))
+        return lo, hi, c
+
+    def registers(self, first=0, count=None):
+        n = self.info()["n_nodes"]
+        count = n - first if count is None else count
+        out = np.zeros((count, 64), np.uint8)
+        if count:
+            check(self._L.sb200_hyperball_registers(self._h, first, count, out.ctypes.data))
+        return out
+
+    def kahan(self, first=0, count=None):
+        n = self.info()["n_nodes"]
+        count = n - first if count is None else count
+        s = np.zeros(count, np.float64); e = np.zeros(count, np.float64)
+        if count:
+            check(self._L.sb200_hyperball_kahan(self._h, first, count, s.ctypes.data, e.ctypes.data))
+        return s, e
+
+    def node_ids(self):
+        n = self.info()["n_nodes"]
+        lo = np.zeros(n, np.uint64); hi = np.zeros(n, np.uint64)
+        if n:
+            check(self._L.sb200_graph_node_ids(self._h, 0, n, lo.ctypes.data, hi.ctypes.data))
+        return lo, hi
+
+    def row_ranges(self):
+        b = (C.c_uint64 * (self.world_size + 1))()
+        check(self._L.sb200_graph_row_ranges(self._h, b))
+        return list(b)
+
+    def exchange_ptrs(self):
+        regs, fr = C.c_void_p(), C.c_void_p()
+        rb, fb = C.c_uint64(), C.c_uint64()
+        check(self._L.sb200_hyperball_exchange_ptrs(self._h, C.byref(regs), C.byref(rb), C.byref(fr), C.byref(fb)))
+        return regs.value, rb.value, fr.value, fb.value
+
+    def exchange_done(self, global_n_changed):
+        check(self._L.sb200_hyperball_exchange_done(self._h, int(global_n_changed)))
+
+    def close(self):
+        if self._h:
+            self._L.sb200_graph_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HarmonicCentrality:
+    """`HarmonicCentrality(BTreeMap<NodeID, f64>)` (harmonic.rs:289-311): ascending node id, nodes with
+    zero centrality absent."""
+
+    def __init__(self, ids_lo, ids_hi, values, n_nodes=0, iterations=0, stats=None, info=None):
+        self.ids_lo, self.ids_hi, self.values = ids_lo, ids_hi, values
+        self.n_nodes, self.iterations, self.stats, self.info = n_nodes, iterations, stats or [], info or {}
+        self._map = None
+
+    @classmethod
+    def calculate(cls, graph, device=0, max_iters=0):
+        dg = DeviceGraph(graph, device=device)
+        try:
+            iters, stats = dg.run(max_iters)
+            lo, hi, c = dg.result()
+            info = dg.info()
+            return cls(lo, hi, c, info["n_nodes"], iters, stats, info)
+        finally:
+            dg.close()
+
+    def _m(self):
+        if self._map is None:
+            self._map = {(int(h) << 64) | int(l): float(v) for l, h, v in zip(self.ids_lo, self.ids_hi, self.values)}
+        return self._map
+
+    def get(self, node):
+        return self._m().get(int(node))
+
+    def iter(self):
+        for l, h, v in zip(self.ids_lo, self.ids_hi, self.values):
+            yield (int(h) << 64) | int(l), float(v)
+
+    def __len__(self):
+        return len(self.values)
+
+    def len(self):
+        return len(self.values)
+
+    def is_empty(self):
+        return len(self.values) == 0
+
+
+class ShardedHarmonicCentrality:
+    """The distributed job (coordinator.rs:122-135, mapper.rs:38-45) with torch.distributed as the
+    transport: every rank holds the full counter array, owns a destination-row range of the CSR and
+    after each iteration all-gathers the owned register rows (the DHT `HyperLogLog64Upsert` max-merge
+    has a single writer per row, so it degenerates to an all-gather), the changed bitmap
+    (SaveBloom/UpdateBloom) and sums the changed count (Meta.round_had_changes)."""
+
+    @staticmethod
+    def calculate(graph, device, rank, world_size, max_iters=0, group=None):
+        import torch
+        import torch.distributed as dist
+        dg = DeviceGraph(graph, device=device, rank=rank, world_size=world_size)
+        try:
+            ranges = dg.row_ranges()
+            stats = []
+            t = 0
+            dev = torch.device("cuda", device)
+            while True:
+                st = dg.step()
+                regs_ptr, regs_bytes, fr_ptr, fr_bytes = dg.exchange_ptrs()
+                regs = _as_tensor(regs_ptr, regs_bytes, torch.uint8, dev)
+                fr = _as_tensor(fr_ptr, fr_bytes, torch.int32, dev)
+                torch.cuda.current_stream(dev).synchronize()
+                cnt = torch.tensor([st["n_changed"]], dtype=torch.int64, device=dev)
+                works = []
+                for r in range(world_size):
+                    b, e = ranges[r], ranges[r + 1]
+                    if e > b:
+                        works.append(dist.broadcast(regs[b * 64:e * 64], src=_global_rank(group, r), group=group, async_op=True))
+                        wb, we = b // 32, (e + 31) // 32
+                        works.append(dist.broadcast(fr[wb:we], src=_global_rank(group, r), group=group, async_op=True))
+                works.append(dist.all_reduce(cnt, group=group, async_op=True))
+                for w in works:
+                    w.wait()
+                torch.cuda.current_stream(dev).synchronize()
+                total = int(cnt.item())
+                dg.exchange_done(total)
+                st["n_changed_global"] = total
+                stats.append(st)
+                t += 1
+                if total == 0 or (max_iters and t >= max_iters):
+                    break
+            lo, hi, c = dg.result()
+            info = dg.info()
+            return HarmonicCentrality(lo, hi, c, info["n_nodes"], t, stats, info)
+        finally:
+            dg.close()
+
+
+def _global_rank(group, r):
+    import torch.distributed as dist
+    return dist.get_global_rank(group, r) if group is not None else r
+
+
+def _as_tensor(ptr, nbytes, dtype, dev):
+    """Zero-copy torch view of a device buffer owned by the library (valid until the next step)."""
+    import torch
+
+    class _Cai:
+        pass
+    itemsize = torch.empty((), dtype=dtype).element_size()
+    holder = _Cai()
+    holder.__cuda_array_interface__ = {
+        "shape": (nbytes // itemsize,), "typestr": {1: "|u1", 4: "<i4"}[itemsize], "data": (ptr, False), "version": 2}
+    return torch.as_tensor(holder, device=dev)

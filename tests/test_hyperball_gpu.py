@@ -1,0 +1,200 @@
+"""Parity of the CUDA HyperBall path (through the C ABI) against the CPU oracle.  Needs a GPU.
+
+Bar: HyperLogLog registers bit-exact after every iteration, KahanSum (sum, err) bit-exact, result
+key set identical and values bit-exact (the contract only asks for 1e-6 relative)."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import DenseHyperBall, hyperball_faithful
+from stract_b200 import synth
+from stract_b200.webgraph import (DeviceGraph, Edge, HarmonicCentrality, RelFlags, SKIPPED_REL, Webgraph)
+
+pytestmark = pytest.mark.gpu
+M64 = (1 << 64) - 1
+
+
+def _graph(d):
+    return Webgraph.from_arrays(d["from_lo"], d["from_hi"], d["to_lo"], d["to_hi"], d["rel_flags"])
+
+
+def _args(d):
+    return (d["from_lo"], d["from_hi"], d["to_lo"], d["to_hi"], d["rel_flags"])
+
+
+def _soa(edges):
+    n = len(edges)
+    a = [np.zeros(n, np.uint64) for _ in range(5)]
+    for i, (f, t, r) in enumerate(edges):
+        a[0][i] = f & M64; a[1][i] = f >> 64; a[2][i] = t & M64; a[3][i] = t >> 64; a[4][i] = r
+    return dict(from_lo=a[0], from_hi=a[1], to_lo=a[2], to_hi=a[3], rel_flags=a[4])
+
+
+def _check_stepwise(d, force_mode=-1, max_steps=200):
+    orc = DenseHyperBall(*_args(d), threads=4)
+    dg = DeviceGraph(_graph(d))
+    try:
+        dg.set_policy(force_mode=force_mode)
+        info = dg.info()
+        assert info["n_nodes"] == orc.n_nodes
+        assert info["n_edges_kept"] <= orc.n_edges  # the library also drops self-loops (no-ops)
+        lo, hi = dg.node_ids()
+        olo, ohi = orc.ids()
+        assert np.array_equal(lo, olo) and np.array_equal(hi, ohi)
+        assert np.array_equal(dg.registers(), orc.registers())
+        for it in range(max_steps):
+            st = dg.step()
+            nch = orc.step()
+            assert st["n_changed"] == nch, (it, st, nch)
+            assert np.array_equal(dg.registers(), orc.registers()), f"registers differ after iteration {it}"
+            s, e = dg.kahan()
+            os_, oe = orc.kahan()
+            assert np.array_equal(s, os_) and np.array_equal(e, oe), f"KahanSum differs after iteration {it}"
+            if nch == 0:
+                break
+        glo, ghi, gc = dg.result()
+        r = orc.result()
+        assert np.array_equal(glo, r["ids_lo"]) and np.array_equal(ghi, r["ids_hi"])
+        assert np.array_equal(gc, r["centrality"])
+        return it + 1
+    finally:
+        dg.close()
+        orc.close()
+
+
+def test_reference_kat_graph():
+    # harmonic.rs:478-493 + hand-derived values
+    ids = {n: (0xABCDEF0000 + 7919 * (i + 1)) | ((i + 1) << 64) for i, n in enumerate("ABCD")}
+    g = Webgraph()
+    for f, t in (("A", "B"), ("B", "C"), ("A", "C"), ("C", "A"), ("D", "C")):
+        g.insert(Edge.new_test(ids[f], ids[t]))
+    g.commit()
+    c = HarmonicCentrality.calculate(g)
+    assert c.get(ids["C"]) > c.get(ids["A"]) > c.get(ids["B"])
+    assert c.get(ids["D"]) is None
+    assert c.get(ids["C"]) == 1.0
+    assert abs(c.get(ids["A"]) - 2.0 / 3) < 1e-15 and abs(c.get(ids["B"]) - (1 + 0.5 + 1 / 3) / 3) < 1e-15
+    assert c.len() == 3 and c.iterations == 4
+    # ascending id order like the BTreeMap
+    keys = [k for k, _ in c.iter()]
+    assert keys == sorted(keys)
+
+
+def test_rel_flags_and_first_wins():
+    ids = {n: (i + 11) | ((97 * i + 5) << 64) for i, n in enumerate("ABCD")}
+    base = [(ids["A"], ids["B"]), (ids["B"], ids["C"]), (ids["A"], ids["C"]), (ids["C"], ids["A"]), (ids["D"], ids["C"])]
+    for flag in (RelFlags.TAG, RelFlags.SAME_ICANN_DOMAIN):
+        c = HarmonicCentrality.calculate(_graph(_soa([(f, t, flag) for f, t in base])))
+        assert c.n_nodes == 4 and c.len() == 0
+    skipped_first = _soa([(ids["A"], ids["B"], RelFlags.NOFOLLOW), (ids["A"], ids["B"], 0)])
+    clean_first = _soa([(ids["A"], ids["B"], 0), (ids["A"], ids["B"], RelFlags.NOFOLLOW)])
+    assert HarmonicCentrality.calculate(_graph(skipped_first)).len() == 0
+    assert HarmonicCentrality.calculate(_graph(clean_first)).len() == 1
+    # additional_edges_ignored (harmonic.rs:495-553)
+    a = HarmonicCentrality.calculate(_graph(_soa([(f, t, 0) for f, t in base])))
+    b = HarmonicCentrality.calculate(_graph(_soa([(f, t, 0) for f, t in base] + [(ids["A"], ids["B"], 0)] * 8)))
+    assert dict(a.iter()) == dict(b.iter())
+
+
+def test_edge_cases():
+    # empty stream
+    c = HarmonicCentrality.calculate(_graph(_soa([])))
+    assert c.len() == 0 and c.n_nodes == 0
+    # a single self loop: one node, nothing reachable
+    c = HarmonicCentrality.calculate(_graph(_soa([(5, 5, 0)])))
+    assert c.n_nodes == 1 and c.len() == 0
+    # the all-ones id (doubles as the hash-set sentinel inside the library) and ids sharing halves
+    big = (1 << 128) - 1
+    ids = [big, (1 << 64) | 7, (2 << 64) | 7, 7, M64, M64 << 64]
+    edges = [(ids[i], ids[(i + 1) % len(ids)], 0) for i in range(len(ids))] + [(ids[0], ids[3], 0)]
+    d = _soa(edges)
+    _check_stepwise(d)
+    ref = hyperball_faithful(*_args(d))
+    got = HarmonicCentrality.calculate(_graph(d))
+    assert np.array_equal(got.ids_lo, ref["ids_lo"]) and np.array_equal(got.ids_hi, ref["ids_hi"])
+    assert np.array_equal(got.values, ref["centrality"])
+
+
+@pytest.mark.parametrize("n,e,seed", [(60, 300, 1), (2000, 6000, 2), (5000, 60000, 3)])
+@pytest.mark.parametrize("mode", [-1, 0, 1, 2])
+def test_random_graph_stepwise(n, e, seed, mode):
+    _check_stepwise(synth.uniform_graph(n, e, seed), force_mode=mode)
+
+
+def test_long_rows_and_hubs():
+    # a destination with 5000 in-edges (several 1024-edge work items + merge), a source with 3000
+    # out-edges, medium rows around the quad/warp boundary, plus a chain so it runs many iterations
+    rng = np.random.default_rng(5)
+    n = 9000
+    f = list(rng.integers(1, n, 5000)) + [0] * 3000 + list(range(100, 400))
+    t = [0] * 5000 + list(rng.integers(1, n, 3000)) + list(range(101, 401))
+    for v in range(500, 560):  # rows with 30..36 in-edges
+        k = 30 + (v % 7)
+        f += list(rng.integers(1, n, k)); t += [v] * k
+    fi = np.array(f, np.uint64); ti = np.array(t, np.uint64)
+    d = synth.edges_from_indices(fi, ti)
+    for mode in (-1, 0, 1, 2):
+        iters = _check_stepwise(d, force_mode=mode)
+    assert iters > 5
+
+
+def test_rmat_matches_faithful_reference_shape():
+    d = synth.rmat_graph(20_000, 200_000, seed=42)
+    ref = hyperball_faithful(*_args(d))
+    got = HarmonicCentrality.calculate(_graph(d))
+    assert got.n_nodes == ref["n_nodes"] and got.iterations == ref["iters"]
+    assert np.array_equal(got.ids_lo, ref["ids_lo"]) and np.array_equal(got.ids_hi, ref["ids_hi"])
+    assert np.array_equal(got.values, ref["centrality"])
+    modes = [s["mode"] for s in got.stats]
+    assert modes[0] == 0
+
+
+def test_config_c1_full_size():
+    # BASELINE.json configs[0]: 100k nodes / 1M edges, <= 20 iterations
+    d = synth.uniform_graph(100_000, 1_000_000, 42)
+    orc = DenseHyperBall(*_args(d), threads=8)
+    orc.run(20)
+    r = orc.result()
+    got = HarmonicCentrality.calculate(_graph(d), max_iters=20)
+    assert got.iterations == r["iters"]
+    assert np.array_equal(got.ids_lo, r["ids_lo"]) and np.array_equal(got.values, r["centrality"])
+
+
+def test_device_resident_input_and_reset():
+    import torch
+    d = synth.rmat_graph(3000, 40_000, seed=7)
+    dev = {k: torch.from_numpy(v.view(np.int64)).cuda() for k, v in d.items()}
+    g = Webgraph.from_arrays(dev["from_lo"], dev["from_hi"], dev["to_lo"], dev["to_hi"], dev["rel_flags"])
+    dg = DeviceGraph(g)
+    try:
+        it1, _ = dg.run()
+        r1 = dg.result()
+        dg.reset()
+        it2, _ = dg.run()
+        r2 = dg.result()
+        assert it1 == it2 and all(np.array_equal(a, b) for a, b in zip(r1, r2))
+    finally:
+        dg.close()
+    ref = hyperball_faithful(*_args(d))
+    assert np.array_equal(r1[0], ref["ids_lo"]) and np.array_equal(r1[2], ref["centrality"])
+
+
+def test_size_independent_properties_large():
+    # properties that need no oracle: idempotence of a converged state, monotone registers,
+    # centrality in (0, 1], key order
+    d = synth.rmat_graph(1_000_000, 16_000_000, seed=42)
+    dg = DeviceGraph(_graph(d))
+    try:
+        first = dg.registers(0, 4096).copy()
+        iters, stats = dg.run()
+        assert stats[-1]["n_changed"] == 0 and all(s["n_changed"] > 0 for s in stats[:-1])
+        last = dg.registers(0, 4096)
+        assert np.all(last >= first)
+        st = dg.step()  # a converged state is a fixed point
+        assert st["n_changed"] == 0 and np.array_equal(dg.registers(0, 4096), last)
+        lo, hi, c = dg.result()
+        assert np.all(c > 0) and np.all(c <= 1.0 + 1e-12)
+        key = hi.astype(object) * (1 << 64) + lo.astype(object)
+        assert all(key[i] < key[i + 1] for i in range(0, min(len(key) - 1, 20000)))
+    finally:
+        dg.close()

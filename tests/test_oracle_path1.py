@@ -1,0 +1,175 @@
+"""Pins the path-1 oracle against every known-answer test the reference holds for it
+(SURVEY.md 8c).  CPU only."""
+import math
+
+import numpy as np
+
+import oracle
+from oracle import Bloom, DenseHyperBall, Hll, KahanSum, hyperball_faithful
+from stract_b200.webgraph import RelFlags, SKIPPED_REL
+
+
+def test_kahan_kat():
+    # crates/core/src/kahan_sum.rs:86-104
+    k = KahanSum()
+    assert k.sum == 0.0
+    for x in [10000.0, math.pi, math.e, math.pi, math.e, math.pi, math.e]:
+        k.add(x)
+    assert k.sum == 10017.579623446147
+
+
+def test_bloom_kat():
+    # crates/bloom/src/lib.rs:197-216
+    bf = Bloom(100, 0.01)
+    for x in (1, 2, 3, 4, 5):
+        bf.insert(x)
+    assert all(bf.contains(x) for x in (1, 2, 3, 4, 5))
+    assert not any(bf.contains(x) for x in (6, 7, 8, 9, 10))
+
+
+def test_bloom_estimate_card_truncation():
+    # lib.rs:108-123: `.ln() as i64` binds before the multiplication -> 0 until fill >= 63.2 %
+    bf = Bloom(1000, 0.05)
+    nbits = oracle.lib().orc_bloom_num_bits(1000, 0.05)
+    assert nbits == math.ceil(1000 * math.log(0.05) / (-8.0 * math.log(2.0) ** 2))
+    assert bf.estimate_card() == 0
+    for x in range(200):
+        bf.insert(x)
+    assert bf.estimate_card() == 0
+
+
+def _size_bounds(h):
+    size = h.size()
+    delta = int((1.04 / math.sqrt(h.n)) * 2.0 * size)
+    return size - delta, size + delta
+
+
+def test_hll128_many_sizes_and_merge():
+    # crates/core/src/hyperloglog.rs:4566-4599 (N=128)
+    h = Hll(128)
+    for i in range(10_000):
+        h.add(i)
+    lo, hi = _size_bounds(h)
+    assert lo < h.size() < hi
+    wm, a, b = Hll(128), Hll(128), Hll(128)
+    for i in range(10_000):
+        wm.add(i); a.add(i)
+    for i in range(10_001, 20_000):
+        wm.add(i); b.add(i)
+    a.merge(b)
+    assert np.array_equal(a.registers, wm.registers)
+
+
+def test_hll128_ten_million():
+    # hyperloglog.rs:4553-4564: 10M inserts stay inside size_bounds
+    L = oracle.lib()
+    regs = np.zeros(128, np.uint8)
+    L.orc_hll_add_range(regs, 128, 0, 10_000_000)
+    size = int(L.orc_hll_size(regs, 128))
+    delta = int((1.04 / math.sqrt(128)) * 2.0 * size)
+    assert size > 0 and size - delta < size < size + delta
+
+
+def test_hll64_small_exact():
+    # linear counting with distinct registers truncates to the exact count for tiny sets
+    h = Hll(64)
+    seen = set()
+    n = 0
+    for i in range(1, 200):
+        hsh = (i * 11400714819323198549) & ((1 << 64) - 1)
+        j = hsh >> 58
+        if j in seen:
+            continue
+        seen.add(j); h.add(i); n += 1
+        if n <= 4:
+            assert h.size() == n
+    assert h.size() > 4
+
+
+def _ids(names):
+    # arbitrary distinct u128 ids (the reference hashes names with xxh3; orderings do not depend on it)
+    return {n: (0xABCDEF0000 + 7919 * (i + 1)) | ((i + 1) << 64) for i, n in enumerate(names)}
+
+
+def _soa(edges):
+    n = len(edges)
+    a = [np.zeros(n, np.uint64) for _ in range(5)]
+    m = (1 << 64) - 1
+    for i, (f, t, r) in enumerate(edges):
+        a[0][i] = f & m; a[1][i] = f >> 64; a[2][i] = t & m; a[3][i] = t >> 64; a[4][i] = r
+    return a
+
+
+def _as_map(res):
+    return {(int(h) << 64) | int(l): float(c) for l, h, c in zip(res["ids_lo"], res["ids_hi"], res["centrality"])}
+
+
+def _test_edges(ids, flag=0):
+    return [(ids["A"], ids["B"], flag), (ids["B"], ids["C"], flag), (ids["A"], ids["C"], flag),
+            (ids["C"], ids["A"], flag), (ids["D"], ids["C"], flag)]
+
+
+def test_harmonic_orderings_and_hand_kat():
+    # harmonic.rs:478-493: C > A > B, D absent; hand-derived values
+    ids = _ids("ABCD")
+    for impl in ("faithful", "dense"):
+        if impl == "faithful":
+            m = _as_map(hyperball_faithful(*_soa(_test_edges(ids))))
+        else:
+            d = DenseHyperBall(*_soa(_test_edges(ids)))
+            d.run()
+            m = _as_map(d.result())
+        assert m[ids["C"]] > m[ids["A"]] > m[ids["B"]]
+        assert ids["D"] not in m
+        assert m[ids["C"]] == 3.0 / 3.0
+        assert abs(m[ids["A"]] - (1 + 0.5 + 0.5) / 3) < 1e-15
+        assert abs(m[ids["B"]] - (1 + 0.5 + 1.0 / 3) / 3) < 1e-15
+
+
+def test_host_harmonic_centrality():
+    # harmonic.rs:359-476: B.com (2 in-links from distinct hosts) > A.com (only self links)
+    ids = _ids(["A.com", "B.com", "C.com", "D.com"])
+    e = [(ids["A.com"], ids["A.com"], 0)] * 12 + [(ids["C.com"], ids["B.com"], 0), (ids["D.com"], ids["B.com"], 0)]
+    m = _as_map(hyperball_faithful(*_soa(e)))
+    assert m[ids["B.com"]] > m.get(ids["A.com"], 0.0)
+
+
+def test_additional_edges_ignored():
+    # harmonic.rs:495-553: duplicates of an edge across commits give an identical map
+    ids = _ids("ABCD")
+    base = _as_map(hyperball_faithful(*_soa(_test_edges(ids))))
+    extra = _test_edges(ids) + [(ids["A"], ids["B"], 0)] * 8
+    assert _as_map(hyperball_faithful(*_soa(extra))) == base
+
+
+def test_rel_flags_ignored():
+    # harmonic.rs:555-602: all-TAG / all-SAME_ICANN_DOMAIN edges => no positive centrality
+    ids = _ids("ABCD")
+    for flag in (RelFlags.TAG, RelFlags.SAME_ICANN_DOMAIN):
+        assert flag & SKIPPED_REL
+        res = hyperball_faithful(*_soa(_test_edges(ids, flag)))
+        assert res["n_nodes"] == 4 and len(res["centrality"]) == 0
+
+
+def test_first_occurrence_decides_flags():
+    # store.rs:313 unique_by keeps the first (from,to): a skipped first copy hides a later clean one
+    ids = _ids("AB")
+    skipped_first = [(ids["A"], ids["B"], RelFlags.NOFOLLOW), (ids["A"], ids["B"], 0)]
+    clean_first = [(ids["A"], ids["B"], 0), (ids["A"], ids["B"], RelFlags.NOFOLLOW)]
+    for impl in (hyperball_faithful, lambda *a: (lambda d: (d.run(), d.result())[1])(DenseHyperBall(*a))):
+        assert len(impl(*_soa(skipped_first))["centrality"]) == 0
+        assert len(impl(*_soa(clean_first))["centrality"]) == 1
+
+
+def test_faithful_equals_dense_on_random_graphs():
+    from stract_b200 import synth
+    for n, e, seed in ((50, 200, 1), (300, 2000, 2), (2000, 6000, 3)):
+        g = synth.uniform_graph(n, e, seed)
+        a = (g["from_lo"], g["from_hi"], g["to_lo"], g["to_hi"], g["rel_flags"])
+        f = hyperball_faithful(*a)
+        d = DenseHyperBall(*a, threads=2)
+        d.run()
+        r = d.result()
+        assert f["iters"] == r["iters"] and f["n_nodes"] == r["n_nodes"]
+        assert np.array_equal(f["ids_lo"], r["ids_lo"]) and np.array_equal(f["ids_hi"], r["ids_hi"])
+        assert np.array_equal(f["centrality"], r["centrality"])  # bit-exact
