@@ -1,0 +1,405 @@
+#!/usr/bin/env python3
+"""bench.py -- the driver's measurement contract for stract_b200.
+
+Headline metric (BASELINE.json): webgraph edges/sec per centrality iteration, on configs[1]
+(50M-node / 1B-edge R-MAT host graph, harmonic centrality to convergence on 1xB200; with --gpus N the
+same graph is destination-row partitioned over N GPUs = configs[2]).  A "step" is one complete
+HarmonicCentrality computation (reset + all HyperBall iterations to convergence) on the graph
+resident in HBM; value = kept_edges x iterations / device time.  `e2e` is the same metric through the
+C-ABI call sequence a Rust shim makes (sb200_graph_create from HOST buffers -> run -> result to host),
+host<->device copies and the on-device CSR staging inside the timed region.  BM25 postings/sec is
+reported in the same line under "bm25".
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path
+  python bench.py --impl reference ...                          the reference's CPU path (oracle port)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "webgraph_edges_per_sec_per_centrality_iter"
+UNIT = "edges/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx = [], set(), None
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx = float(c[2])
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def _unique_kept_edges(d):
+    import numpy as np
+    from stract_b200.webgraph import SKIPPED_REL
+    key = np.stack([d["from_lo"], d["from_hi"], d["to_lo"], d["to_hi"]], 1)
+    _, first = np.unique(key, axis=0, return_index=True)
+    keep = (d["rel_flags"][first] & np.uint64(SKIPPED_REL)) == 0
+    return int(keep.sum())
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline_dense(nodes, edges, threads):
+    """Oracle 'dense' port (flat arrays, all host threads) on a bounded R-MAT sample of the workload."""
+    import oracle
+    from stract_b200 import synth
+    d = synth.rmat_graph(nodes, edges, seed=42)
+    a = (d["from_lo"], d["from_hi"], d["to_lo"], d["to_hi"], d["rel_flags"])
+    o = oracle.DenseHyperBall(*a, threads=threads)
+    t0 = time.perf_counter()
+    iters = o.run()
+    dt = time.perf_counter() - t0
+    kept = o.n_edges
+    o.close()
+    return {"value": kept * iters / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"R-MAT {nodes} nodes / {edges} edges (same generator, seed 42), {iters} iterations to convergence, "
+                      f"oracle dense port on {threads} threads, iteration loop only (graph already staged in RAM)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path = oracle 'faithful' port (the reference is Rust; no
+    toolchain here).  It mirrors harmonic.rs structure by structure and is single-threaded because the
+    reference's loop is (harmonic.rs:129-154).  Each step = one HarmonicCentrality::calculate on a bounded
+    sample, graph scan/dedup/maps included, exactly what the reference call does."""
+    import oracle
+    from stract_b200 import synth
+    nodes, edges = args.ref_nodes, args.ref_edges
+    d = synth.rmat_graph(nodes, edges, seed=42)
+    a = (d["from_lo"], d["from_hi"], d["to_lo"], d["to_hi"], d["rel_flags"])
+    kept = _unique_kept_edges(d)
+    for _ in range(min(args.warmup, 1)):
+        oracle.hyperball_faithful(*a)
+    t0 = time.perf_counter()
+    iters = 0
+    for _ in range(args.steps):
+        r = oracle.hyperball_faithful(*a)
+        iters = r["iters"]
+    dt = (time.perf_counter() - t0) / args.steps
+    value = kept * iters / dt
+    sample = (f"R-MAT {nodes} nodes / {edges} edges (bounded sample of the 50M/1B workload, same generator), "
+              f"{iters} iterations, one full calculate() per step")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "webgraph harmonic centrality (HyperBall), R-MAT 50M nodes / 1B edges -- bounded CPU sample",
+                       "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def gen_device_graph(torch, L, dev_index, nodes, edges, scale):
+    from stract_b200._lib import check
+    t = [torch.empty(edges, dtype=torch.int64, device=f"cuda:{dev_index}") for _ in range(5)]
+    CH = 1 << 27
+    for first in range(0, edges, CH):
+        cnt = min(CH, edges - first)
+        check(L.sb200_synth_edges(1, nodes, first, cnt, 42, scale, dev_index, *(x.data_ptr() + first * 8 for x in t)))
+    return t
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nodes", type=int, default=50_000_000)
+    ap.add_argument("--edges", type=int, default=1_000_000_000)
+    ap.add_argument("--scale", type=int, default=26)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-bm25", action="store_true")
+    ap.add_argument("--cpu-nodes", type=int, default=1_000_000)
+    ap.add_argument("--cpu-edges", type=int, default=20_000_000)
+    ap.add_argument("--ref-nodes", type=int, default=50_000)
+    ap.add_argument("--ref-edges", type=int, default=500_000)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args)
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from stract_b200 import kernel_launch_count, lib
+    from stract_b200.webgraph import DeviceGraph, ShardedHarmonicCentrality, Webgraph
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (the product path has no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = lib()
+    peaks, peak_src = _peaks()
+
+    nodes, edges = args.nodes, args.edges
+    tg = time.perf_counter()
+    cols = gen_device_graph(torch, L, local_rank, nodes, edges, args.scale)
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - tg
+    graph = Webgraph.from_arrays(*cols)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    launches0 = kernel_launch_count()
+    result = {}
+    if world == 1:
+        dg = DeviceGraph(graph, device=local_rank)
+        info = dg.info()
+        E = info["n_edges_kept"]
+
+        def one_step():
+            dg.reset()
+            iters, stats = dg.run()
+            return iters, stats
+        for _ in range(max(args.warmup, 3)):
+            one_step()
+        dg.set_profiling(True)
+        sampler = ClockSampler(local_rank); sampler.start()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches_t0 = kernel_launch_count()
+        ev0.record()
+        tot_iters = 0
+        stats_last = None
+        for _ in range(args.steps):
+            iters, stats_last = one_step()
+            tot_iters += iters
+        ev1.record()
+        barrier()
+        clocks = sampler.stop()
+        launches_timed = kernel_launch_count() - launches_t0
+        ms_total = ev0.elapsed_time(ev1)
+        prof = dg.profile()
+        dg.set_profiling(False)
+        value = E * tot_iters / (ms_total * 1e-3)
+        iters = tot_iters // args.steps
+        dom = max((p for p in prof if "dense" in p["name"] and p["launches"]), key=lambda p: p["ms"], default=None)
+        roofline = None
+        if dom:
+            ach = dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": dom["name"], "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                        "launches": dom["launches"], "avg_launch_ms": dom["ms"] / dom["launches"],
+                        "alg_bytes_per_launch": dom["alg_bytes"] / dom["launches"]}
+        result.update(value=value, ms_per_step=ms_total / args.steps, iters=iters, E=E, info=info, clocks=clocks,
+                      roofline=roofline, launches=launches_timed,
+                      kernels=[{**p, "share_of_step": p["ms"] / ms_total} for p in prof if p["launches"]],
+                      per_iter=[{"t": s["t"], "mode": s["mode"], "n_changed": s["n_changed"], "ms": round(s["ms"], 3)} for s in stats_last])
+        dg.close()
+    else:
+        # configs[2]: the same graph, destination rows partitioned over `world` GPUs
+        def one_run():
+            return ShardedHarmonicCentrality.calculate(graph, local_rank, rank, world)
+        # staging happens inside calculate(); time only the iteration loops via the per-iteration stats
+        # (device ms of the step kernels) + exchange wall time => use wall clock around the loop
+        from stract_b200.webgraph import DeviceGraph as _DG
+        dg = _DG(graph, device=local_rank, rank=rank, world_size=world)
+        info = dg.info()
+        E = info["n_edges_kept"]
+        ranges = dg.row_ranges()
+        from stract_b200.webgraph import _as_tensor, _global_rank
+
+        def one_step():
+            dg.reset()
+            t = 0
+            while True:
+                st = dg.step()
+                rp, rb, fp, fb = dg.exchange_ptrs()
+                regs = _as_tensor(rp, rb, torch.uint8, dev); fr = _as_tensor(fp, fb, torch.int32, dev)
+                cnt = torch.tensor([st["n_changed"]], dtype=torch.int64, device=dev)
+                works = []
+                for r in range(world):
+                    b, e = ranges[r], ranges[r + 1]
+                    if e > b:
+                        works.append(dist.broadcast(regs[b * 64:e * 64], src=r, async_op=True))
+                        works.append(dist.broadcast(fr[b // 32:(e + 31) // 32], src=r, async_op=True))
+                works.append(dist.all_reduce(cnt, async_op=True))
+                for w in works:
+                    w.wait()
+                torch.cuda.synchronize()
+                total = int(cnt.item())
+                dg.exchange_done(total)
+                t += 1
+                if total == 0:
+                    return t
+        for _ in range(max(args.warmup, 3)):
+            one_step()
+        sampler = ClockSampler(local_rank); sampler.start()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches_t0 = kernel_launch_count()
+        ev0.record()
+        tot_iters = 0
+        for _ in range(args.steps):
+            tot_iters += one_step()
+        ev1.record()
+        barrier()
+        clocks = sampler.stop()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_total = float(ms.item())
+        nl = torch.tensor([kernel_launch_count() - launches_t0], device=dev, dtype=torch.int64)
+        dist.all_reduce(nl)
+        value = E * tot_iters / (ms_total * 1e-3)
+        result.update(value=value, ms_per_step=ms_total / args.steps, iters=tot_iters // args.steps, E=E, info=info,
+                      clocks=clocks, roofline=None, launches=int(nl.item()), kernels=[], per_iter=[])
+        dg.close()
+
+    # ---- e2e: the C-ABI call sequence from HOST buffers (rank 0 only drives it at N=1) ----------
+    e2e = None
+    if not args.no_e2e and world == 1:
+        import psutil
+        need = edges * 40
+        avail = psutil.virtual_memory().available
+        e_nodes, e_edges, e_scale, note = nodes, edges, args.scale, "full workload"
+        if avail < need * 1.6:
+            f = 1
+            while (edges // f) * 40 * 1.6 > avail and f < 1024:
+                f *= 2
+            e_nodes, e_edges = max(nodes // f, 1000), edges // f
+            e_scale = max(1, int(np.ceil(np.log2(e_nodes))))
+            note = f"host RAM {avail / 2**30:.0f} GiB < 1.6x the {need / 2**30:.0f} GiB edge stream: scaled 1/{f}"
+            del cols, graph
+            torch.cuda.empty_cache()
+            cols = gen_device_graph(torch, L, local_rank, e_nodes, e_edges, e_scale)
+        host = []
+        for c in cols:
+            try:
+                h = torch.empty(c.shape, dtype=c.dtype, pin_memory=True)
+            except Exception:
+                h = torch.empty(c.shape, dtype=c.dtype)
+            h.copy_(c)
+            host.append(h)
+        pinned = all(h.is_pinned() for h in host)
+        del cols
+        torch.cuda.empty_cache()
+        hgraph = Webgraph.from_arrays(*host)
+        from stract_b200.webgraph import HarmonicCentrality
+
+        def e2e_step():
+            r = HarmonicCentrality.calculate(hgraph, device=local_rank)
+            return r
+        e2e_step()  # warm-up
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        tot, d2h = 0, 0
+        for _ in range(args.e2e_steps):
+            r = e2e_step()
+            tot += r.info["n_edges_kept"] * r.iterations
+            d2h = len(r.values) * 24
+        ev1.record()
+        barrier()
+        ms_e = ev0.elapsed_time(ev1)
+        e2e = {"value": tot / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e_edges * 40, "d2h_bytes_per_step": d2h,
+               "ms_per_step": ms_e / args.e2e_steps, "steps": args.e2e_steps, "pinned_host": pinned, "workload": note,
+               "nodes": e_nodes, "edges": e_edges, "stage_ms": r.info["stage_ms"], "iterations": r.iterations}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": result["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": result["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": f"webgraph harmonic centrality (HyperBall) to convergence, R-MAT(0.57,0.19,0.19,0.05) "
+                                       f"{nodes} nodes / {edges} edges (BASELINE configs[{1 if world == 1 else 2}])",
+                           "kept_edges": result["E"], "n_nodes": result["info"]["n_nodes"],
+                           "iterations_per_step": result["iters"],
+                           "l2_policy": "inputs >> L2: 2 x 3.2 GB register arrays + 4 GB CSR per iteration",
+                           "parallelism": "1 GPU" if world == 1 else f"destination-row partition x{world}, per-iteration all-gather of owned register rows (NCCL broadcast group)",
+                           "hbm_bytes": result["info"]["hbm_bytes"], "gen_s": round(gen_s, 2),
+                           "stage_ms": result["info"]["stage_ms"]},
+                "clocks": result["clocks"], "gpu_launches": result["launches"], "roofline": result["roofline"],
+                "kernels": result["kernels"], "per_iter": result["per_iter"], "e2e": e2e}
+        if not args.no_cpu and world == 1:
+            threads = os.cpu_count() or 1
+            line["cpu_baseline"] = cpu_baseline_dense(args.cpu_nodes, args.cpu_edges, threads)
+        if not args.no_bm25 and world == 1:
+            try:
+                from stract_b200 import bm25_bench
+                line["bm25"] = bm25_bench.run(local_rank, peaks, peak_src)
+            except ImportError:
+                line["bm25"] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
