@@ -1,0 +1,219 @@
+"""ctypes prototypes + helpers for the path-2 (BM25) oracle.  TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+
+import numpy as np
+
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+
+def proto(L, f):
+    vp, u32, u64, i32, f32, f64 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_float, C.c_double
+    f("orc_id_to_fieldnorm", u32, C.c_uint8)
+    f("orc_fieldnorm_to_id", C.c_uint8, u32)
+    f("orc_bp4_roundtrip", u64, _u32p, C.c_uint8, _u8p, _u32p)
+    f("orc_vint_sorted_encode", u64, _u32p, u32, u32, _u8p)
+    f("orc_encode_bitwidth", C.c_uint8, C.c_uint8, i32)
+    f("orc_tv_idf", f32, u64, u64)
+    f("orc_tv_bm25_weight", None, f32, f32, C.POINTER(f32), _f32p)
+    f("orc_tv_bm25_score", f32, f32, _f32p, C.c_uint8, u32)
+    f("orc_stract_bm25_weight", None, f32, f32, f32, f32, C.POINTER(f32), _f32p)
+    f("orc_stract_bm25_score", f32, f32, _f32p, f32, C.c_uint8, u32)
+    f("orc_seg_new", vp, _u8p, u32)
+    f("orc_seg_free", None, vp)
+    f("orc_seg_avg_fieldnorm", f32, vp)
+    f("orc_seg_set_avg_fieldnorm", None, vp, f32)
+    f("orc_seg_add_term", u32, vp, _u32p, _u32p, u32)
+    f("orc_seg_postings_len", u64, vp)
+    f("orc_seg_postings_copy", None, vp, _u8p)
+    f("orc_seg_num_terms", u32, vp)
+    f("orc_seg_term_info", None, vp, u32, C.POINTER(u64), C.POINTER(u64), C.POINTER(u32))
+    f("orc_seg_set_postings", None, vp, _u8p, u64, _u64p, _u64p, _u32p, u32)
+    f("orc_bm25_topk", u32, vp, _u32p, _f32p, _f32p, u32, i32, u32, _u32p, _f32p, C.POINTER(u64))
+    f("orc_signal_topk", u32, vp, _u32p, _f32p, _f32p, f32, u32, f64, vp, _f64p, u32, u32, u32, _u32p, _f64p, C.POINTER(u64))
+    f("orc_bm25_topk_batch", None, vp, _u32p, _f32p, _f32p, u32, i32, u32, u32, i32, _u32p, _f32p, _u32p, _u64p)
+    f("orc_signal_topk_batch", None, vp, _u32p, _f32p, _f32p, f32, u32, f64, vp, _f64p, u32, u32, u32, u32, i32, _u32p,
+      _f64p, _u32p, _u64p)
+    f("orc_cursor_open", vp, vp, u32, f32, _f32p)
+    f("orc_cursor_free", None, vp)
+    for name in ("doc", "tf", "advance", "last_doc_in_block"):
+        f(f"orc_cursor_{name}", u32, vp)
+    f("orc_cursor_seek", u32, vp, u32)
+    f("orc_cursor_shallow_seek", None, vp, u32)
+    for name in ("score", "max_score", "block_max_score"):
+        f(f"orc_cursor_{name}", f32, vp)
+
+
+def _L():
+    from .pyoracle import lib
+    return lib()
+
+
+def fieldnorm_to_id(fn):
+    return int(_L().orc_fieldnorm_to_id(int(fn)))
+
+
+def id_to_fieldnorm(i):
+    return int(_L().orc_id_to_fieldnorm(int(i)))
+
+
+FIELDNORM_TABLE = None
+
+
+def fieldnorm_table():
+    global FIELDNORM_TABLE
+    if FIELDNORM_TABLE is None:
+        FIELDNORM_TABLE = np.array([id_to_fieldnorm(i) for i in range(256)], np.uint32)
+    return FIELDNORM_TABLE
+
+
+def fieldnorms_to_ids(fieldnorms):
+    t = fieldnorm_table()
+    return (np.searchsorted(t, np.asarray(fieldnorms, np.uint32), side="right") - 1).astype(np.uint8)
+
+
+def tv_bm25_weight(doc_freq, num_docs, avg_fieldnorm):
+    """tantivy Bm25Weight::for_one_term -> (weight f32, cache[256] f32)."""
+    L = _L()
+    idf = L.orc_tv_idf(int(doc_freq), int(num_docs))
+    w = C.c_float(0)
+    cache = np.zeros(256, np.float32)
+    L.orc_tv_bm25_weight(idf, float(avg_fieldnorm), C.byref(w), cache)
+    return np.float32(w.value), cache
+
+
+def stract_bm25_weight(doc_freq, num_docs, avg_fieldnorm, k1=1.2, b=0.75):
+    L = _L()
+    idf = L.orc_tv_idf(int(doc_freq), int(num_docs))  # same idf expression (core/src/ranking/bm25.rs:23-27)
+    w = C.c_float(0)
+    cache = np.zeros(256, np.float32)
+    L.orc_stract_bm25_weight(idf, float(avg_fieldnorm), float(k1), float(b), C.byref(w), cache)
+    return np.float32(w.value), cache
+
+
+class Segment:
+    """One field of one segment: postings file in tantivy's byte format + fieldnorm ids."""
+
+    def __init__(self, fieldnorm_ids, avg_fieldnorm=None):
+        self.fieldnorm_ids = np.ascontiguousarray(fieldnorm_ids, np.uint8)
+        self.max_doc = int(self.fieldnorm_ids.size)
+        self.L = _L()
+        self.h = self.L.orc_seg_new(self.fieldnorm_ids, self.max_doc)
+        if avg_fieldnorm is not None:
+            self.L.orc_seg_set_avg_fieldnorm(self.h, float(avg_fieldnorm))
+
+    @property
+    def avg_fieldnorm(self):
+        return float(self.L.orc_seg_avg_fieldnorm(self.h))
+
+    def add_term(self, docs, tfs):
+        docs = np.ascontiguousarray(docs, np.uint32); tfs = np.ascontiguousarray(tfs, np.uint32)
+        assert docs.size == tfs.size
+        return int(self.L.orc_seg_add_term(self.h, docs, tfs, docs.size))
+
+    def postings_bytes(self):
+        n = int(self.L.orc_seg_postings_len(self.h))
+        out = np.zeros(max(n, 1), np.uint8)
+        self.L.orc_seg_postings_copy(self.h, out)
+        return out[:n]
+
+    def term_infos(self):
+        n = int(self.L.orc_seg_num_terms(self.h))
+        off = np.zeros(n, np.uint64); ln = np.zeros(n, np.uint64); df = np.zeros(n, np.uint32)
+        o, l, d = C.c_uint64(), C.c_uint64(), C.c_uint32()
+        for t in range(n):
+            self.L.orc_seg_term_info(self.h, t, C.byref(o), C.byref(l), C.byref(d))
+            off[t], ln[t], df[t] = o.value, l.value, d.value
+        return off, ln, df
+
+    def set_postings(self, data, off, ln, df):
+        data = np.ascontiguousarray(data, np.uint8)
+        self.L.orc_seg_set_postings(self.h, data, data.size, np.ascontiguousarray(off, np.uint64),
+                                    np.ascontiguousarray(ln, np.uint64), np.ascontiguousarray(df, np.uint32), len(df))
+
+    def topk(self, terms, weights, caches, mode, k):
+        terms = np.ascontiguousarray(terms, np.uint32); weights = np.ascontiguousarray(weights, np.float32)
+        caches = np.ascontiguousarray(caches, np.float32).reshape(-1)
+        docs = np.zeros(k, np.uint32); scores = np.zeros(k, np.float32); sc = C.c_uint64(0)
+        n = self.L.orc_bm25_topk(self.h, terms, weights, caches, terms.size, mode, k, docs, scores, C.byref(sc))
+        return docs[:n], scores[:n], sc.value
+
+    def topk_batch(self, terms, weights, caches, mode, k, threads=1):
+        terms = np.ascontiguousarray(terms, np.uint32); nq, nt = terms.shape
+        weights = np.ascontiguousarray(weights, np.float32); caches = np.ascontiguousarray(caches, np.float32)
+        docs = np.zeros((nq, k), np.uint32); scores = np.zeros((nq, k), np.float32)
+        n_out = np.zeros(nq, np.uint32); scored = np.zeros(nq, np.uint64)
+        self.L.orc_bm25_topk_batch(self.h, terms.reshape(-1), weights.reshape(-1), caches.reshape(-1), nt, mode, k, nq,
+                                   threads, docs.reshape(-1), scores.reshape(-1), n_out, scored)
+        return docs, scores, n_out, scored
+
+    def _sig(self, signals):
+        sigs = [np.ascontiguousarray(s, np.float64) for s in signals]
+        arr = (C.c_void_p * max(len(sigs), 1))(*[s.ctypes.data for s in sigs])
+        return sigs, arr
+
+    def signal_topk(self, terms, weights, caches, k1, coeff_text, signals, coeffs, k, max_docs=0):
+        terms = np.ascontiguousarray(terms, np.uint32); weights = np.ascontiguousarray(weights, np.float32)
+        caches = np.ascontiguousarray(caches, np.float32).reshape(-1)
+        sigs, arr = self._sig(signals)
+        co = np.ascontiguousarray(coeffs, np.float64) if len(sigs) else np.zeros(1, np.float64)
+        docs = np.zeros(k, np.uint32); totals = np.zeros(k, np.float64); sc = C.c_uint64(0)
+        n = self.L.orc_signal_topk(self.h, terms, weights, caches, float(k1), terms.size, float(coeff_text),
+                                   C.cast(arr, C.c_void_p), co, len(sigs), max_docs, k, docs, totals, C.byref(sc))
+        return docs[:n], totals[:n], sc.value
+
+    def signal_topk_batch(self, terms, weights, caches, k1, coeff_text, signals, coeffs, k, max_docs=0, threads=1):
+        terms = np.ascontiguousarray(terms, np.uint32); nq, nt = terms.shape
+        weights = np.ascontiguousarray(weights, np.float32); caches = np.ascontiguousarray(caches, np.float32)
+        sigs, arr = self._sig(signals)
+        co = np.ascontiguousarray(coeffs, np.float64) if len(sigs) else np.zeros(1, np.float64)
+        docs = np.zeros((nq, k), np.uint32); totals = np.zeros((nq, k), np.float64)
+        n_out = np.zeros(nq, np.uint32); scored = np.zeros(nq, np.uint64)
+        self.L.orc_signal_topk_batch(self.h, terms.reshape(-1), weights.reshape(-1), caches.reshape(-1), float(k1), nt,
+                                     float(coeff_text), C.cast(arr, C.c_void_p), co, len(sigs), max_docs, k, nq, threads,
+                                     docs.reshape(-1), totals.reshape(-1), n_out, scored)
+        return docs, totals, n_out, scored
+
+    def cursor(self, term, weight, cache):
+        return Cursor(self, term, weight, cache)
+
+    def close(self):
+        if self.h:
+            self.L.orc_seg_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Cursor:
+    """TermScorer over SegmentPostings (term_scorer.rs)."""
+
+    def __init__(self, seg, term, weight, cache):
+        self.seg = seg
+        self.L = seg.L
+        self.h = self.L.orc_cursor_open(seg.h, term, float(weight), np.ascontiguousarray(cache, np.float32))
+
+    def __getattr__(self, name):
+        if name in ("doc", "tf", "advance", "last_doc_in_block", "score", "max_score", "block_max_score"):
+            fn = getattr(self.L, f"orc_cursor_{name}")
+            return lambda: fn(self.h)
+        raise AttributeError(name)
+
+    def seek(self, t):
+        return self.L.orc_cursor_seek(self.h, t)
+
+    def shallow_seek(self, t):
+        self.L.orc_cursor_shallow_seek(self.h, t)
+
+    def __del__(self):
+        try:
+            self.L.orc_cursor_free(self.h)
+        except Exception:
+            pass
