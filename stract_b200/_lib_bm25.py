@@ -1,0 +1,41 @@
+"""ctypes prototypes of the path-2 (BM25) entry points (include/stract_b200_bm25.h)."""
+import ctypes as C
+
+
+class TermInfo(C.Structure):
+    _fields_ = [("postings_off", C.c_uint64), ("postings_len", C.c_uint64), ("doc_freq", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class SegmentInfo(C.Structure):
+    _fields_ = [("n_terms", C.c_uint64), ("n_blocks", C.c_uint64), ("n_postings", C.c_uint64), ("hbm_bytes", C.c_uint64),
+                ("max_doc", C.c_uint32), ("_pad", C.c_uint32), ("stage_ms", C.c_double)]
+
+
+class Bm25Batch(C.Structure):
+    _fields_ = [("n_queries", C.c_uint32), ("n_terms", C.c_uint32), ("term_ords", C.c_void_p), ("weights", C.c_void_p),
+                ("tf_cache256", C.c_void_p), ("mode", C.c_int), ("k", C.c_uint32)]
+
+
+class Bm25Stats(C.Structure):
+    _fields_ = [("postings_scored", C.c_uint64), ("docs_scored", C.c_uint64), ("blocks_decoded", C.c_uint64),
+                ("ms", C.c_float), ("kernel_ms", C.c_float)]
+
+
+class SignalBatch(C.Structure):
+    _fields_ = [("q", Bm25Batch), ("k1", C.c_float), ("coeff_text", C.c_double), ("signals", C.c_void_p),
+                ("coeffs", C.c_void_p), ("max_docs", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+def proto(L, f):
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    f("sb200_segment_create", i32, vp, u64, vp, u32, vp, u32, i32, i32, C.POINTER(vp))
+    f("sb200_segment_destroy", None, vp)
+    f("sb200_segment_get_info", i32, vp, C.POINTER(SegmentInfo))
+    f("sb200_signals_create", i32, vp, u32, u32, i32, C.POINTER(vp))
+    f("sb200_signals_destroy", None, vp)
+    f("sb200_bm25_topk_batch", i32, vp, C.POINTER(Bm25Batch), vp, vp, vp, C.POINTER(Bm25Stats))
+    f("sb200_bm25_topk", i32, vp, vp, vp, u32, vp, i32, u32, vp, vp, vp)
+    f("sb200_signal_topk_batch", i32, vp, C.POINTER(SignalBatch), vp, vp, vp, C.POINTER(Bm25Stats))
+    f("sb200_postings_encode", i32, vp, vp, vp, u32, vp, u32, C.c_float, vp, u64, C.POINTER(u64), vp, i32)
+    f("sb200_fieldnorm_id_to_value", u32, C.c_uint8)
+    f("sb200_fieldnorm_value_to_id", C.c_uint8, u32)

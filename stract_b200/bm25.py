@@ -1,0 +1,292 @@
+"""Host-side mirror of the reference's BM25 top-k interface, backed by libstract_b200.so.
+
+Mirrors (same names / argument meaning):
+  fieldnorm_to_id / id_to_fieldnorm       tantivy/src/fieldnorm/code.rs:1-11
+  Bm25Weight.for_one_term / idf            tantivy/src/query/bm25.rs:52-176      (f32 arithmetic, host side)
+  StractBm25Weight                          core/src/ranking/bm25.rs:23-151
+  PostingsWriter                            tantivy/src/postings/serializer.rs (WithFreqs) -- builds segments
+  SegmentReader.open                        InvertedIndexReader + FieldNormReader of one field
+  TopDocs.with_limit(k) + BooleanQuery      tantivy/src/collector/top_score_collector.rs:360-414
+  SignalComputer (one text field + numeric signals)   core/src/ranking/computer/mod.rs, initial.rs:79-93
+
+The weights are computed on the host exactly like the reference does before it opens any posting list
+(f32 `ln` once per term); all per-posting work runs in the CUDA library.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib_bm25 as B
+from ._lib import check, lib
+
+K1 = np.float32(1.2)
+B_ = np.float32(0.75)
+MODE_AND, MODE_OR = 0, 1
+NO_TERM = 0xFFFFFFFF
+
+
+def id_to_fieldnorm(i):
+    return int(lib().sb200_fieldnorm_id_to_value(int(i)))
+
+
+def fieldnorm_to_id(v):
+    return int(lib().sb200_fieldnorm_value_to_id(int(v)))
+
+
+_TABLE = None
+
+
+def fieldnorm_table():
+    global _TABLE
+    if _TABLE is None:
+        _TABLE = np.array([id_to_fieldnorm(i) for i in range(256)], np.uint32)
+    return _TABLE
+
+
+def fieldnorms_to_ids(fieldnorms):
+    return (np.searchsorted(fieldnorm_table(), np.asarray(fieldnorms, np.uint32), side="right") - 1).astype(np.uint8)
+
+
+def idf(doc_freq, doc_count):
+    """tantivy/src/query/bm25.rs:52-56 in f32 (f32 `ln` through libm, like Rust's f32::ln)."""
+    assert doc_count >= doc_freq
+    x = (np.float32(doc_count - doc_freq) + np.float32(0.5)) / (np.float32(doc_freq) + np.float32(0.5))
+    return np.float32(_logf(np.float32(1.0) + x))
+
+
+_libm = C.CDLL("libm.so.6")
+_libm.logf.restype = C.c_float
+_libm.logf.argtypes = [C.c_float]
+
+
+def _logf(x):
+    return _libm.logf(float(x))
+
+
+def compute_tf_cache(average_fieldnorm, k1=K1, b=B_):
+    """cache[id] = K1 * (1 - B + B * fieldnorm(id) / avg) (bm25.rs:58-68), f32 left to right."""
+    fn = fieldnorm_table().astype(np.float32)
+    avg = np.float32(average_fieldnorm)
+    k1 = np.float32(k1); b = np.float32(b)
+    return (k1 * ((np.float32(1.0) - b) + (b * fn) / avg)).astype(np.float32)
+
+
+class Bm25Weight:
+    """tantivy Bm25Weight: weight = idf * (1 + K1), score = weight * (tf / (tf + cache[fieldnorm_id]))."""
+
+    def __init__(self, idf_value, average_fieldnorm):
+        self.weight = np.float32(np.float32(idf_value) * (np.float32(1.0) + K1))
+        self.cache = compute_tf_cache(average_fieldnorm)
+        self.average_fieldnorm = np.float32(average_fieldnorm)
+
+    @classmethod
+    def for_one_term(cls, term_doc_freq, total_num_docs, avg_fieldnorm):
+        return cls(idf(term_doc_freq, total_num_docs), avg_fieldnorm)
+
+    def score(self, fieldnorm_id, term_freq):
+        tf = np.float32(term_freq)
+        return np.float32(self.weight * (tf / (tf + self.cache[fieldnorm_id])))
+
+
+class StractBm25Weight:
+    """core/src/ranking/bm25.rs:110-151: weight = idf, score = idf * ((tf*(k1+1)) / (tf + cache)), tf==0 -> 0."""
+
+    def __init__(self, idf_value, average_fieldnorm, k1=K1, b=B_):
+        self.weight = np.float32(idf_value)
+        self.k1 = np.float32(k1)
+        self.cache = compute_tf_cache(average_fieldnorm, k1, b)
+
+    @classmethod
+    def for_one_term(cls, term_doc_freq, total_num_docs, avg_fieldnorm, k1=K1, b=B_):
+        return cls(idf(term_doc_freq, total_num_docs), avg_fieldnorm, k1, b)
+
+
+def _p(a):
+    return a.ctypes.data if a is not None else None
+
+
+def encode_postings(term_docs, term_tfs, fieldnorm_ids, avg_fieldnorm, threads=8):
+    """PostingsSerializer for a list of terms (WithFreqs).  Returns (bytes u8[], TermInfo array)."""
+    n = len(term_docs)
+    off = np.zeros(n + 1, np.uint64)
+    for i, d in enumerate(term_docs):
+        off[i + 1] = off[i] + len(d)
+    docs = np.concatenate([np.asarray(d, np.uint32) for d in term_docs]) if n else np.zeros(0, np.uint32)
+    tfs = np.concatenate([np.asarray(t, np.uint32) for t in term_tfs]) if n else np.zeros(0, np.uint32)
+    return encode_postings_csr(docs, tfs, off, fieldnorm_ids, avg_fieldnorm, threads)
+
+
+def encode_postings_csr(docs, tfs, off, fieldnorm_ids, avg_fieldnorm, threads=8):
+    L = lib()
+    docs = np.ascontiguousarray(docs, np.uint32); tfs = np.ascontiguousarray(tfs, np.uint32)
+    off = np.ascontiguousarray(off, np.uint64)
+    fn = np.ascontiguousarray(fieldnorm_ids, np.uint8)
+    n = off.size - 1
+    ln = C.c_uint64(0)
+    infos = (B.TermInfo * max(n, 1))()
+    check(L.sb200_postings_encode(_p(docs), _p(tfs), _p(off), n, _p(fn), fn.size, float(avg_fieldnorm), None, 0,
+                                  C.byref(ln), None, threads))
+    out = np.zeros(max(ln.value, 1), np.uint8)
+    check(L.sb200_postings_encode(_p(docs), _p(tfs), _p(off), n, _p(fn), fn.size, float(avg_fieldnorm), _p(out), out.size,
+                                  C.byref(ln), infos, threads))
+    return out[:ln.value], infos
+
+
+class SegmentReader:
+    """One field of one segment resident in HBM (postings file + fieldnorms + block directory)."""
+
+    def __init__(self, postings, term_infos, fieldnorm_ids, device=0, record_option=1, total_num_tokens=None):
+        self._L = lib()
+        self._h = C.c_void_p()
+        postings = np.ascontiguousarray(postings, np.uint8)
+        self.fieldnorm_ids = np.ascontiguousarray(fieldnorm_ids, np.uint8)
+        self.max_doc = int(self.fieldnorm_ids.size)
+        if isinstance(term_infos, tuple):  # (off, len, df) arrays
+            o, l, d = term_infos
+            arr = (B.TermInfo * max(len(d), 1))()
+            for i in range(len(d)):
+                arr[i].postings_off, arr[i].postings_len, arr[i].doc_freq = int(o[i]), int(l[i]), int(d[i])
+            term_infos, n_terms = arr, len(d)
+        else:
+            n_terms = len(term_infos)
+        self.n_terms = n_terms
+        self.doc_freq = np.array([term_infos[i].doc_freq for i in range(n_terms)], np.uint32)
+        check(self._L.sb200_segment_create(_p(postings), postings.size, term_infos, n_terms, _p(self.fieldnorm_ids), self.max_doc,
+                                           record_option, device, C.byref(self._h)))
+        if total_num_tokens is None:
+            total_num_tokens = int(fieldnorm_table()[self.fieldnorm_ids].astype(np.uint64).sum())
+        self.total_num_tokens = total_num_tokens
+        # average_fieldnorm = total_num_tokens as f32 / total_num_docs as f32 (bm25.rs:112-114)
+        self.average_fieldnorm = np.float32(np.float32(total_num_tokens) / np.float32(max(self.max_doc, 1)))
+        self.device = device
+
+    def info(self):
+        si = B.SegmentInfo()
+        check(self._L.sb200_segment_get_info(self._h, C.byref(si)))
+        return {k: getattr(si, k) for k, _ in B.SegmentInfo._fields_ if not k.startswith("_")}
+
+    def close(self):
+        if self._h:
+            self._L.sb200_segment_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SignalTable:
+    """Numeric signal scores per doc, row-major in HBM (sb200_signals)."""
+
+    def __init__(self, columns, device=0):
+        self._L = lib()
+        self._h = C.c_void_p()
+        cols = [np.ascontiguousarray(c, np.float64) for c in columns]
+        self.n_cols = len(cols)
+        self.max_doc = int(cols[0].size) if cols else 0
+        arr = (C.c_void_p * max(self.n_cols, 1))(*[c.ctypes.data for c in cols])
+        check(self._L.sb200_signals_create(arr, self.n_cols, self.max_doc, device, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self._L.sb200_signals_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def score_rank(rank):
+    """non_text.rs:50-59: (10 - log_8(1 + rank)).max(0) with f64::log(base) = ln(x)/ln(base)."""
+    return max(10.0 - math.log(1.0 + float(rank)) / math.log(8.0), 0.0)
+
+
+class TopDocs:
+    """`TopDocs::with_limit(k)` over a BooleanQuery of TermQueries on one field, batched."""
+
+    def __init__(self, limit):
+        assert limit >= 1, "Limit must be strictly greater than 0."  # top_collector.rs:85
+        self.limit = limit
+
+    @classmethod
+    def with_limit(cls, limit):
+        return cls(limit)
+
+    def search_batch(self, segment, term_ords, mode=MODE_AND, weights=None, return_stats=False):
+        """term_ords [n_queries, n_terms] (NO_TERM pads).  Returns (docs [nq,k], scores [nq,k], n_out [nq])."""
+        term_ords = np.ascontiguousarray(term_ords, np.uint32)
+        nq, nt = term_ords.shape
+        if weights is None:  # Bm25Weight::for_terms with the segment's own statistics (bm25.rs:98-134)
+            df = segment.doc_freq[np.minimum(term_ords, segment.n_terms - 1)]
+            uniq = {}
+            weights = np.zeros((nq, nt), np.float32)
+            for q in range(nq):
+                for t in range(nt):
+                    d = int(df[q, t])
+                    w = uniq.get(d)
+                    if w is None:
+                        w = uniq[d] = np.float32(idf(d, segment.max_doc) * (np.float32(1.0) + K1))
+                    weights[q, t] = w
+        weights = np.ascontiguousarray(weights, np.float32)
+        cache = compute_tf_cache(segment.average_fieldnorm)
+        k = self.limit
+        docs = np.zeros((nq, k), np.uint32); scores = np.zeros((nq, k), np.float32); n_out = np.zeros(nq, np.uint32)
+        b = B.Bm25Batch(nq, nt, _p(term_ords), _p(weights), _p(cache), mode, k)
+        st = B.Bm25Stats()
+        check(segment._L.sb200_bm25_topk_batch(segment._h, C.byref(b), _p(docs), _p(scores), _p(n_out), C.byref(st)))
+        if return_stats:
+            return docs, scores, n_out, {k_: getattr(st, k_) for k_, _ in B.Bm25Stats._fields_ if not k_.startswith("_")}
+        return docs, scores, n_out
+
+    def search(self, segment, term_ords, mode=MODE_AND, weights=None):
+        """One query -> list of (score, doc) like the Fruit Vec<(Score, DocAddress)>."""
+        t = np.asarray(term_ords, np.uint32)[None, :]
+        w = None if weights is None else np.asarray(weights, np.float32)[None, :]
+        d, s, n = self.search_batch(segment, t, mode, w)
+        return [(float(s[0, i]), int(d[0, i])) for i in range(int(n[0]))]
+
+
+class SignalComputer:
+    """The recall-stage subset of Stract's SignalComputer this path covers: one text field scored with
+    Stract's BM25 (coefficient `coeff_text`, e.g. Bm25CleanBody 0.005) plus numeric signal columns
+    (coefficient per column), combined in f64 in that order; top-k by (total desc, doc asc)."""
+
+    def __init__(self, segment, signals=None, coefficients=(), coeff_text=0.005, k1=K1, b=B_):
+        self.segment, self.signals = segment, signals
+        self.coefficients = np.ascontiguousarray(coefficients, np.float64)
+        self.coeff_text = float(coeff_text)
+        self.k1, self.b = np.float32(k1), np.float32(b)
+
+    def top_docs_batch(self, term_ords, k, max_docs=0, return_stats=False):
+        seg = self.segment
+        term_ords = np.ascontiguousarray(term_ords, np.uint32)
+        nq, nt = term_ords.shape
+        df = seg.doc_freq[np.minimum(term_ords, seg.n_terms - 1)]
+        uniq = {}
+        weights = np.zeros((nq, nt), np.float32)
+        for q in range(nq):
+            for t in range(nt):
+                d = int(df[q, t])
+                w = uniq.get(d)
+                if w is None:
+                    w = uniq[d] = idf(d, seg.max_doc)
+                weights[q, t] = w
+        cache = compute_tf_cache(seg.average_fieldnorm, self.k1, self.b)
+        docs = np.zeros((nq, k), np.uint32); totals = np.zeros((nq, k), np.float64); n_out = np.zeros(nq, np.uint32)
+        sb = B.SignalBatch()
+        sb.q = B.Bm25Batch(nq, nt, _p(term_ords), _p(weights), _p(cache), MODE_OR, k)
+        sb.k1 = float(self.k1); sb.coeff_text = self.coeff_text
+        sb.signals = self.signals._h if self.signals is not None else None
+        sb.coeffs = _p(self.coefficients) if self.signals is not None else None
+        sb.max_docs = max_docs
+        st = B.Bm25Stats()
+        check(seg._L.sb200_signal_topk_batch(seg._h, C.byref(sb), _p(docs), _p(totals), _p(n_out), C.byref(st)))
+        if return_stats:
+            return docs, totals, n_out, {k_: getattr(st, k_) for k_, _ in B.Bm25Stats._fields_ if not k_.startswith("_")}
+        return docs, totals, n_out

@@ -1,0 +1,176 @@
+"""BM25 legs of bench.py: configs[3] (10M docs, 2-term AND, top-1000, 10k-query batch) and configs[4]
+(100M docs, 5-term OR, Stract BM25 + linear signal combine, 10k-query batch) on one GPU.
+
+Synthetic index (seeded): vocabulary Zipf(1.0), df_r = round(2e6 / r) at 10M docs (x10 at 100M);
+only ranks <= 10 000 are materialised because queries draw ranks from [10, 10 000]; a term's docs are a
+uniform sorted subset drawn through geometric gaps (p = df/max_doc), tf ~ 1 + Geometric(0.6) capped at 255,
+doc length ~ LogNormal(5.5, 0.8) -> fieldnorm id.  Posting lists are written in tantivy's byte format by the
+library's host writer (sb200_postings_encode)."""
+import os
+import time
+
+import numpy as np
+
+from . import bm25
+
+
+def synth_index(max_doc, df_scale, n_ranks=10_000, seed=1234, threads=16):
+    rng = np.random.default_rng(seed)
+    lens = np.minimum(np.maximum(1, rng.lognormal(5.5, 0.8, max_doc)), 2e9).astype(np.uint32)
+    ids = bm25.fieldnorms_to_ids(lens)
+    del lens
+    avg = np.float32(np.float32(bm25.fieldnorm_table()[ids].astype(np.uint64).sum()) / np.float32(max_doc))
+    ranks = np.arange(1, n_ranks + 1)
+    target = np.minimum(np.maximum(1, np.round(df_scale / ranks)), max_doc // 2).astype(np.int64)
+    docs_l, off = [], np.zeros(n_ranks + 1, np.uint64)
+    for i, df in enumerate(target):
+        p = df / max_doc
+        n = int(df * 1.05 + 6 * np.sqrt(df) + 16)
+        d = np.cumsum(rng.geometric(p, n)) - 1
+        d = d[d < max_doc].astype(np.uint32)
+        docs_l.append(d)
+        off[i + 1] = off[i] + d.size
+    docs = np.concatenate(docs_l)
+    del docs_l
+    tfs = np.minimum(rng.geometric(0.6, docs.size), 255).astype(np.uint32)
+    data, infos = bm25.encode_postings_csr(docs, tfs, off, ids, avg, threads=threads)
+    return dict(postings=data, infos=infos, fieldnorm_ids=ids, avg=avg, n_postings=int(docs.size), off=off)
+
+
+def log_uniform_queries(n_queries, n_terms, lo=10, hi=10_000, seed=1):
+    rng = np.random.default_rng(seed)
+    out = np.zeros((n_queries, n_terms), np.uint32)
+    for q in range(n_queries):
+        s = set()
+        while len(s) < n_terms:
+            s.add(int(np.exp(rng.uniform(np.log(lo), np.log(hi)))))
+        out[q] = sorted(s, key=lambda _: rng.random())
+    return out - 1  # rank r is term ordinal r-1
+
+
+def _alg_bytes(infos, terms, docs_scored, k_out_bytes, per_doc_bytes):
+    plen = np.array([infos[i].postings_len for i in range(len(infos))], np.float64)
+    return float(plen[terms].sum()) + per_doc_bytes * docs_scored + k_out_bytes
+
+
+def run_and(device, peaks, max_doc=10_000_000, df_scale=2.0e6, n_queries=10_000, k=1000, steps=5, warmup=3, cpu=True):
+    t0 = time.perf_counter()
+    ix = synth_index(max_doc, df_scale)
+    gen_s = time.perf_counter() - t0
+    seg = bm25.SegmentReader(ix["postings"], ix["infos"], ix["fieldnorm_ids"], device=device)
+    terms = log_uniform_queries(n_queries, 2)
+    top = bm25.TopDocs.with_limit(k)
+    for _ in range(warmup):
+        top.search_batch(seg, terms, bm25.MODE_AND)
+    kms, ems, st = [], [], None
+    for _ in range(steps):
+        t1 = time.perf_counter()
+        d, s, n, st = top.search_batch(seg, terms, bm25.MODE_AND, return_stats=True)
+        ems.append((time.perf_counter() - t1) * 1e3)
+        kms.append(st["kernel_ms"])
+    postings = st["postings_scored"]
+    kern = float(np.median(kms)); e2e = float(np.median(ems))
+    alg = _alg_bytes(ix["infos"], terms, st["docs_scored"], 8.0 * float(n.sum()), 1.0)
+    out = {"workload": f"{max_doc} docs, Zipf vocab (ranks<=10k materialised, {ix['n_postings']} postings), "
+                       f"{n_queries} x 2-term AND, tantivy BM25, top-{k}",
+           "metric": "bm25_postings_scored_per_sec", "value": postings / (kern * 1e-3), "unit": "postings/s",
+           "kernel_ms_per_batch": kern, "postings_per_batch": postings, "docs_scored": st["docs_scored"],
+           "blocks_decoded": st["blocks_decoded"],
+           "e2e": {"value": postings / (e2e * 1e-3), "unit": "postings/s", "ms_per_batch": e2e,
+                   "h2d_bytes_per_step": int(terms.size * 8 + 1024), "d2h_bytes_per_step": int(n_queries * k * 8 + n_queries * 4)},
+           "roofline": {"bound": "hbm", "kernel": "k_topk<AND>", "achieved": alg / (kern * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                        "unit": "GB/s", "frac": alg / (kern * 1e-3) / 1e9 / peaks["hbm_gbs"], "alg_bytes_per_launch": alg, "traffic": None},
+           "index_hbm_bytes": seg.info()["hbm_bytes"], "gen_s": round(gen_s, 1), "stage_ms": seg.info()["stage_ms"]}
+    if cpu:
+        out["cpu_baseline"] = cpu_and(ix, terms, k, seg)
+    seg.close()
+    return out
+
+
+def cpu_and(ix, terms, k, seg, sample=2000):
+    """Oracle (restated tantivy Intersection + TopNComputer, with skipping), one query per thread."""
+    import oracle
+    o = oracle.Segment(ix["fieldnorm_ids"], avg_fieldnorm=ix["avg"])
+    infos = ix["infos"]
+    n = len(infos)
+    o.set_postings(ix["postings"], [infos[i].postings_off for i in range(n)], [infos[i].postings_len for i in range(n)],
+                   [infos[i].doc_freq for i in range(n)])
+    t = terms[:sample]
+    cache = bm25.compute_tf_cache(seg.average_fieldnorm)
+    w = np.zeros(t.shape, np.float32)
+    for q in range(t.shape[0]):
+        for j in range(t.shape[1]):
+            w[q, j] = bm25.Bm25Weight.for_one_term(int(seg.doc_freq[t[q, j]]), seg.max_doc, seg.average_fieldnorm).weight
+    caches = np.tile(cache, (t.size, 1))
+    threads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    o.topk_batch(t, w, caches, 0, k, threads=threads)
+    dt = time.perf_counter() - t0
+    postings = int(seg.doc_freq[t].sum())
+    o.close()
+    return {"value": postings / dt, "unit": "postings/s", "cores": threads, "kind": "port",
+            "sample": f"first {t.shape[0]} queries of the batch, oracle Intersection+skip-list seek+TopNComputer, one query per thread"}
+
+
+def run_signal(device, peaks, max_doc=100_000_000, df_scale=2.0e7, n_queries=10_000, k=1000, steps=3, warmup=1, cpu=True):
+    t0 = time.perf_counter()
+    ix = synth_index(max_doc, df_scale)
+    rng = np.random.default_rng(99)
+    hc = rng.random(max_doc) ** 8
+    rank = np.empty(max_doc, np.int64); rank[np.argsort(-hc, kind="stable")] = np.arange(max_doc)
+    cols = [hc, np.maximum(10.0 - np.log(1.0 + rank.astype(np.float64)) / np.log(8.0), 0.0), rng.random(max_doc),
+            1.0 / (1.0 + rng.integers(0, 1000, max_doc).astype(np.float64))]
+    del rank
+    coeffs = [2.0, 0.02, 2.0, 0.001]
+    gen_s = time.perf_counter() - t0
+    seg = bm25.SegmentReader(ix["postings"], ix["infos"], ix["fieldnorm_ids"], device=device)
+    table = bm25.SignalTable(cols, device=device)
+    comp = bm25.SignalComputer(seg, table, coeffs, coeff_text=0.005)
+    terms = log_uniform_queries(n_queries, 5, seed=2)
+    for _ in range(warmup):
+        comp.top_docs_batch(terms, k)
+    kms, ems, st = [], [], None
+    for _ in range(steps):
+        t1 = time.perf_counter()
+        d, tot, n, st = comp.top_docs_batch(terms, k, return_stats=True)
+        ems.append((time.perf_counter() - t1) * 1e3)
+        kms.append(st["kernel_ms"])
+    postings = st["postings_scored"]
+    kern = float(np.median(kms)); e2e = float(np.median(ems))
+    alg = _alg_bytes(ix["infos"], terms, st["docs_scored"], 12.0 * float(n.sum()), 1.0 + 8.0 * 4)
+    out = {"workload": f"{max_doc} docs, {n_queries} x 5-term OR, Stract BM25 + 4 numeric signals (f64 linear combine), top-{k}",
+           "metric": "bm25_postings_scored_per_sec", "value": postings / (kern * 1e-3), "unit": "postings/s",
+           "kernel_ms_per_batch": kern, "postings_per_batch": postings, "docs_scored": st["docs_scored"],
+           "e2e": {"value": postings / (e2e * 1e-3), "unit": "postings/s", "ms_per_batch": e2e,
+                   "h2d_bytes_per_step": int(terms.size * 8 + 1024), "d2h_bytes_per_step": int(n_queries * k * 12 + n_queries * 4)},
+           "roofline": {"bound": "hbm", "kernel": "k_topk<SIGNAL>", "achieved": alg / (kern * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                        "unit": "GB/s", "frac": alg / (kern * 1e-3) / 1e9 / peaks["hbm_gbs"], "alg_bytes_per_launch": alg, "traffic": None},
+           "index_hbm_bytes": seg.info()["hbm_bytes"], "gen_s": round(gen_s, 1)}
+    if cpu:
+        import oracle
+        o = oracle.Segment(ix["fieldnorm_ids"], avg_fieldnorm=ix["avg"])
+        infos = ix["infos"]; nt = len(infos)
+        o.set_postings(ix["postings"], [infos[i].postings_off for i in range(nt)], [infos[i].postings_len for i in range(nt)],
+                       [infos[i].doc_freq for i in range(nt)])
+        t = terms[:256]
+        cache = bm25.compute_tf_cache(seg.average_fieldnorm)
+        w = np.zeros(t.shape, np.float32)
+        for q in range(t.shape[0]):
+            for j in range(t.shape[1]):
+                w[q, j] = bm25.StractBm25Weight.for_one_term(int(seg.doc_freq[t[q, j]]), seg.max_doc, seg.average_fieldnorm).weight
+        threads = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        o.signal_topk_batch(t, w, np.tile(cache, (t.size, 1)), 1.2, 0.005, cols, coeffs, k, threads=threads)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": int(seg.doc_freq[t].sum()) / dt, "unit": "postings/s", "cores": threads, "kind": "port",
+                               "sample": f"first {t.shape[0]} queries, oracle union + per-term seek + Stract BM25 + f64 combine + TopNComputer, one query per thread"}
+        o.close()
+    table.close(); seg.close()
+    return out
+
+
+def run(device, peaks, peak_src, scale=1.0, cpu=True):
+    res = {"peak_source": peak_src}
+    res["and_top1000_10M"] = run_and(device, peaks, max_doc=int(10_000_000 * scale), df_scale=2.0e6 * scale, cpu=cpu)
+    res["or5_signals_100M"] = run_signal(device, peaks, max_doc=int(100_000_000 * scale), df_scale=2.0e7 * scale, cpu=cpu)
+    return res

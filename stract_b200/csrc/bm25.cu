@@ -1,0 +1,741 @@
+// bm25.cu -- hot path 2: BM25 posting-list scoring + top-k on the device (see stract_b200_bm25.h).
+//
+// Data layout in HBM (per segment/field)
+//   postings   the tantivy postings file, byte for byte                       ~1.0-1.5 B / posting
+//   fieldnorm  1 byte per doc (FieldNormReader)                               1 B / doc
+//   directory  built once from the skip lists: per 128-doc block {last_doc u32, byte offset u32,
+//              bit widths u16}; per term {data offset, end offset, doc_freq, first block slot}
+//   signals    optional row-major [max_doc][n_cols] f64 numeric signal scores (one 32-B sector per doc at 4 cols)
+//
+// Kernel k_topk<MODE>: one CTA (128 threads) per query, exhaustive scoring, exact top-k.
+//   The CTA walks all query terms' posting lists block-synchronously: every term keeps one decoded 128-doc
+//   block in shared memory (BitPacker4x unpack: thread k extracts value k from its lane stream, block-wide
+//   prefix sum of the strict deltas).  Each round takes `bound` = the smallest last-doc among the current
+//   blocks; every posting with doc <= bound is final (no later block of any term can contain such a doc),
+//   so membership of a doc in the other terms is a 7-step binary search in their current block.  The term
+//   with the lowest slot that contains the doc "owns" it and computes the score in the reference's f32/f64
+//   operation order; no sort or merge of the lists is needed.  Candidates are pushed (smem atomics) into a
+//   2k-entry buffer with a running threshold exactly like TopNComputer (top_score_collector.rs:501-554);
+//   when it fills, a bitonic sort keeps the best k.  Keys are (order-preserving score bits, ~doc) so the
+//   result order is the reference's (score desc, doc asc) total order.
+// Roofline: HBM by bytes (posting bytes + 1 B fieldnorm (+ 8 B x n_cols signals) per scored doc), but at the
+// configured sizes the postings file is L2-resident and the kernel is bound by unpack/search issue rate.
+#include "common.cuh"
+#include "../../include/stract_b200_bm25.h"
+
+#include <algorithm>
+#include <vector>
+
+namespace sb200 {
+uint32_t fieldnorm_value(uint8_t id);
+}
+
+struct sb200_signals {
+  int device = 0;
+  uint32_t n_cols = 0, max_doc = 0;
+  sb200::DevBuf<double> rows;
+};
+
+struct sb200_segment {
+  int device = 0, record = 1, stride = 8;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+  uint32_t max_doc = 0, n_terms = 0;
+  uint64_t postings_len = 0, n_blocks = 0, n_postings = 0;
+  double stage_ms = 0;
+  sb200::DevBuf<uint8_t> postings, fieldnorm;
+  sb200::DevBuf<uint64_t> t_data_off, t_end_off;
+  sb200::DevBuf<uint32_t> t_df, t_first;
+  sb200::DevBuf<uint32_t> b_last, b_off;
+  sb200::DevBuf<uint16_t> b_bits;
+  std::vector<uint32_t> h_df;  // host copy (query planning: Intersection sorts by size_hint)
+  // per-batch scratch (grown on demand)
+  sb200::DevBuf<uint32_t> q_terms, q_nterms, o_docs, o_n;
+  sb200::DevBuf<float> q_weights, q_cache, o_scores;
+  sb200::DevBuf<double> o_totals, q_coeffs;
+  sb200::DevBuf<unsigned long long> counters;
+};
+
+namespace sb200 {
+
+constexpr int NT = 128;            // threads per CTA == postings per block
+constexpr int MAXT = SB200_MAX_QUERY_TERMS;
+constexpr uint32_t TERMINATED = 0x7FFFFFFFu;
+
+struct SegView {
+  const uint32_t* p32; uint64_t postings_len;
+  const uint8_t* fieldnorm; uint32_t max_doc;
+  const uint64_t *t_data_off, *t_end_off; const uint32_t *t_df, *t_first;
+  const uint32_t *b_last, *b_off; const uint16_t* b_bits;
+  int record;
+};
+
+// ------------------------------------------------------------------ directory build -------------
+// one warp per term: parse [VInt skip_len] and turn the skip entries into randomly addressable block records
+__global__ void k_build_directory(const uint8_t* __restrict__ postings, const sb200_term_info* __restrict__ terms,
+                                  uint32_t n_terms, int stride, const uint32_t* __restrict__ t_first,
+                                  uint64_t* t_data_off, uint64_t* t_end_off, uint32_t* t_df, uint32_t* b_last,
+                                  uint32_t* b_off, uint16_t* b_bits, uint64_t postings_len, int* err) {
+  const uint32_t t = (blockIdx.x * (uint32_t)blockDim.x + threadIdx.x) >> 5;
+  if (t >= n_terms) return;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t off = terms[t].postings_off, len = terms[t].postings_len;
+  const uint32_t df = terms[t].doc_freq;
+  const uint32_t nfull = df >> 7, first = t_first[t];
+  if (off + len > postings_len) { if (lane == 0) *err = 1; return; }
+  uint64_t skip_start = off, skip_len = 0;
+  if (df >= 128) {  // split_into_skips_and_postings, block_segment_postings.rs:78-88
+    int sh = 0; uint64_t p = off;
+    for (int i = 0; i < 10; i++) { const uint8_t b = postings[p++]; skip_len |= (uint64_t)(b & 127u) << sh; if (b & 128u) break; sh += 7; }
+    skip_start = p;
+    if (skip_len != (uint64_t)nfull * stride) { if (lane == 0) *err = 2; return; }
+  }
+  const uint64_t data_off = skip_start + skip_len;
+  if (lane == 0) { t_data_off[t] = data_off; t_end_off[t] = off + len; t_df[t] = df; }
+  uint32_t run = 0;
+  for (uint32_t base = 0; base < nfull; base += 32) {
+    const uint32_t j = base + lane;
+    uint32_t size = 0, last = 0; uint16_t bits = 0;
+    if (j < nfull) {
+      const uint8_t* e = postings + skip_start + (uint64_t)j * stride;  // skip.rs:186-238
+      last = (uint32_t)e[0] | ((uint32_t)e[1] << 8) | ((uint32_t)e[2] << 16) | ((uint32_t)e[3] << 24);
+      const uint32_t db = e[4] & 0x3fu, strict = (e[4] >> 6) & 1u;
+      const uint32_t tb = (stride >= 8) ? e[5] : 0u;
+      bits = (uint16_t)(db | (strict << 6) | (tb << 8));
+      size = (db + tb) * 16u;
+      if (db > 32 || tb > 32) *err = 3;
+    }
+    uint32_t incl = size;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+    if (j < nfull) { b_last[first + j] = last; b_bits[first + j] = bits; b_off[first + j] = run + incl - size; }
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) {
+    b_off[first + nfull] = run; b_last[first + nfull] = TERMINATED; b_bits[first + nfull] = 0;
+    if (data_off + run > off + len) *err = 4;
+  }
+}
+
+// ------------------------------------------------------------------ device helpers ---------------
+__device__ __forceinline__ uint32_t ord_f32(float f) { const uint32_t b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+__device__ __forceinline__ float unord_f32(uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o); }
+__device__ __forceinline__ uint64_t ord_f64(double f) { const uint64_t b = (uint64_t)__double_as_longlong(f); return (b >> 63) ? ~b : (b | 0x8000000000000000ull); }
+__device__ __forceinline__ double unord_f64(uint64_t o) { return __longlong_as_double((long long)((o >> 63) ? (o & 0x7FFFFFFFFFFFFFFFull) : ~o)); }
+
+struct TermState {
+  uint64_t data_off, end_off;
+  uint32_t first, nfull, df, cur_blk, len, pos, last_doc, prev_last, done, tail_done;
+  float weight;
+};
+
+struct Smem {
+  uint32_t* docs; uint32_t* tfs;    // [MAXT][128]
+  uint32_t* stage;                   // 336 words: one packed block (<= 1024 B) or the vint tail (<= 1280 B)
+  uint32_t* vals;                    // 256 tail values
+  float* cache;                      // 256
+  TermState* st;                     // [MAXT]
+  uint64_t* khi; uint32_t* klo;      // [CAP]
+  uint32_t* misc;                    // [32] scratch: warp totals, counters
+};
+
+__device__ __forceinline__ uint32_t extract_bits(const uint32_t* words, uint32_t nb, uint32_t k) {
+  if (nb == 0) return 0;
+  const uint32_t lane4 = k & 3u, slot = k >> 2, bit = slot * nb, w = bit >> 5, sh = bit & 31u;
+  const uint32_t lo = words[w * 4 + lane4];
+  const uint32_t hi = (sh + nb > 32) ? words[(w + 1) * 4 + lane4] : 0u;
+  const uint32_t v = __funnelshift_r(lo, hi, sh);
+  return nb == 32 ? v : (v & ((1u << nb) - 1u));
+}
+
+// inclusive scan over the 128 threads of the CTA (wrapping u32); uses misc[0..3]; two barriers
+__device__ __forceinline__ uint32_t cta_scan_incl(uint32_t x, uint32_t* misc) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += n; }
+  if (lane == 31) misc[warp] = x;
+  __syncthreads();
+  uint32_t add = 0;
+  for (uint32_t w = 0; w < warp; w++) add += misc[w];
+  __syncthreads();
+  return x + add;
+}
+
+// stage `nbytes` of the postings file starting at absolute byte `gbyte` into aligned shared words
+__device__ __forceinline__ void stage_bytes(const SegView& S, uint64_t gbyte, uint32_t nbytes, uint32_t* stage) {
+  const uint64_t w0 = gbyte >> 2; const uint32_t sh = (uint32_t)(gbyte & 3u) * 8u;
+  const uint32_t nwords = (nbytes + 3) >> 2;
+  for (uint32_t w = threadIdx.x; w < nwords; w += NT) {
+    const uint32_t lo = __ldg(S.p32 + w0 + w), hi = __ldg(S.p32 + w0 + w + 1);
+    stage[w] = __funnelshift_r(lo, hi, sh);
+  }
+}
+
+// decode the next block of term slot s into docs[s]/tfs[s]; every thread of the CTA calls it
+__device__ void decode_next(const SegView& S, Smem& M, int s) {
+  TermState& T = M.st[s];
+  uint32_t* docs = M.docs + s * 128; uint32_t* tfs = M.tfs + s * 128;
+  __syncthreads();
+  const uint32_t blk = T.cur_blk, prev_last = T.prev_last;
+  if (blk < T.nfull) {
+    const uint32_t idx = T.first + blk;
+    const uint32_t bits = S.b_bits[idx], db = bits & 0x3fu, strict = (bits >> 6) & 1u, tb = bits >> 8;
+    stage_bytes(S, T.data_off + S.b_off[idx], (db + tb) * 16u, M.stage);
+    __syncthreads();
+    const uint32_t k = threadIdx.x;
+    const uint32_t delta = extract_bits(M.stage, db, k) + strict;
+    const uint32_t tf = (S.record >= 1) ? extract_bits(M.stage + db * 4, tb, k) + strict : 1u;
+    const uint32_t pre = cta_scan_incl(delta, M.misc);
+    const uint32_t base = (strict && prev_last == 0) ? 0xFFFFFFFFu : prev_last;  // offset 0 == None (compression/mod.rs:36)
+    docs[k] = base + pre; tfs[k] = tf;
+    __syncthreads();
+    if (threadIdx.x == 0) { T.len = 128; T.pos = 0; T.last_doc = docs[127]; T.prev_last = docs[127]; T.cur_blk = blk + 1; }
+  } else {
+    const uint32_t n = T.df - T.nfull * 128u;
+    const uint64_t tail_off = T.data_off + S.b_off[T.first + T.nfull];
+    const uint32_t nbytes = (uint32_t)min((uint64_t)1340, T.end_off - tail_off);
+    stage_bytes(S, tail_off, nbytes, M.stage);
+    for (uint32_t i = threadIdx.x; i < 256; i += NT) M.vals[i] = (i < 128) ? 0u : 1u;
+    __syncthreads();
+    if (threadIdx.x < 32) {  // warp 0: vint values = runs of bytes ending with the stop bit (compression/vint.rs)
+      const uint8_t* bytes = (const uint8_t*)M.stage;
+      const uint32_t lane = threadIdx.x;
+      uint32_t seen = 0;
+      const uint32_t want = (S.record >= 1) ? 2 * n : n;
+      for (uint32_t base = 0; base < nbytes && seen < want; base += 32) {
+        const uint32_t b = base + lane;
+        const bool stop = (b < nbytes) && (bytes[b] & 0x80u);
+        const unsigned m = __ballot_sync(0xffffffffu, stop);
+        if (stop) {
+          const uint32_t idx = seen + __popc(m & ((1u << lane) - 1u));
+          if (idx < want) {
+            uint32_t start = b;
+            while (start > 0 && !(bytes[start - 1] & 0x80u) && b - start < 4) start--;
+            uint32_t v = 0;
+            for (uint32_t i = start; i <= b; i++) v += (uint32_t)(bytes[i] & 0x7Fu) << (7 * (i - start));
+            M.vals[idx < n ? idx : 128 + (idx - n)] = v;
+          }
+        }
+        seen += __popc(m);
+      }
+    }
+    __syncthreads();
+    const uint32_t k = threadIdx.x;
+    const uint32_t pre = cta_scan_incl(k < n ? M.vals[k] : 0u, M.misc);
+    docs[k] = (k < n) ? prev_last + pre : TERMINATED;
+    tfs[k] = (k < n) ? M.vals[128 + k] : 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) { T.len = n; T.pos = 0; T.last_doc = n ? docs[n - 1] : 0; T.prev_last = T.last_doc; T.cur_blk = blk + 1; T.tail_done = 1; }
+  }
+  __syncthreads();
+}
+
+// first index in the sorted 128-entry block with value >= x (branchless, block_search.rs:23-34)
+__device__ __forceinline__ uint32_t lower_bound128(const uint32_t* a, uint32_t x) {
+  uint32_t start = 0;
+#pragma unroll
+  for (uint32_t len = 64; len >= 1; len >>= 1) if (a[start + len - 1] < x) start += len;
+  return start;
+}
+
+__device__ __forceinline__ bool key_gt(uint64_t ah, uint32_t al, uint64_t bh, uint32_t bl) { return ah > bh || (ah == bh && al > bl); }
+
+// sort the CAP-entry key buffer descending (bitonic), CAP a power of two
+__device__ void sort_keys_desc(Smem& M, uint32_t cap) {
+  for (uint32_t size = 2; size <= cap; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < (cap >> 1); i += NT) {
+        const uint32_t lo = 2 * i - (i & (stride - 1));
+        const uint32_t hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const uint64_t ah = M.khi[lo], bh = M.khi[hi]; const uint32_t al = M.klo[lo], bl = M.klo[hi];
+        const bool swap = desc ? key_gt(bh, bl, ah, al) : key_gt(ah, al, bh, bl);
+        if (swap) { M.khi[lo] = bh; M.klo[lo] = bl; M.khi[hi] = ah; M.klo[hi] = al; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+struct Params {
+  SegView S;
+  const uint32_t* q_terms; const uint32_t* q_nterms; const float* q_weights; const float* cache;
+  uint32_t n_terms_max, k, cap;
+  // path B
+  float k1p1; double coeff_text; const double* sig; uint32_t n_cols; const double* coeffs; uint32_t max_docs;
+  // out
+  uint32_t* o_docs; float* o_scores; double* o_totals; uint32_t* o_n; unsigned long long* counters;
+};
+
+// MODE 0: AND (tantivy Intersection order), 1: OR (tantivy weights, query-order sum), 2: Stract signal combine
+template <int MODE>
+__global__ void __launch_bounds__(NT) k_topk(const Params P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem M;
+  {
+    unsigned char* p = smem_raw;
+    M.khi = (uint64_t*)p; p += (size_t)P.cap * 8;
+    M.st = (TermState*)p; p += sizeof(TermState) * MAXT;
+    M.klo = (uint32_t*)p; p += (size_t)P.cap * 4;
+    M.docs = (uint32_t*)p; p += MAXT * 128 * 4;
+    M.tfs = (uint32_t*)p; p += MAXT * 128 * 4;
+    M.stage = (uint32_t*)p; p += 344 * 4;
+    M.vals = (uint32_t*)p; p += 256 * 4;
+    M.cache = (float*)p; p += 256 * 4;
+    M.misc = (uint32_t*)p;
+  }
+  const SegView& S = P.S;
+  const uint32_t q = blockIdx.x;
+  const uint32_t T = P.q_nterms[q];
+  const uint32_t tid = threadIdx.x;
+  uint32_t* s_count = M.misc + 8;     // entries in the key buffer
+  uint32_t* s_flag = M.misc + 9;      // threshold valid
+  uint32_t* s_rstart = M.misc + 12;   // [MAXT+1] prefix of the round's per-term entry counts
+  uint32_t* s_rhi = M.misc + 22;      // [MAXT]
+  uint64_t* s_thr_hi = (uint64_t*)(M.misc + 30); uint32_t* s_thr_lo = M.misc + 10;
+  for (uint32_t i = tid; i < 256; i += NT) M.cache[i] = P.cache[i];
+  for (uint32_t i = tid; i < P.cap; i += NT) { M.khi[i] = 0; M.klo[i] = 0; }
+  if (tid < MAXT) {
+    TermState& t = M.st[tid];
+    t.done = 1; t.len = 0; t.pos = 0;
+    if (tid < T) {
+      const uint32_t ord = P.q_terms[(size_t)q * P.n_terms_max + tid];
+      t.data_off = S.t_data_off[ord]; t.end_off = S.t_end_off[ord]; t.first = S.t_first[ord]; t.df = S.t_df[ord];
+      t.nfull = t.df >> 7; t.cur_blk = 0; t.last_doc = 0; t.prev_last = 0; t.tail_done = 0;
+      t.done = (t.df == 0); t.weight = P.q_weights[(size_t)q * P.n_terms_max + tid];
+    }
+  }
+  if (tid == 0) { *s_count = 0; *s_flag = 0; *s_thr_hi = 0; *s_thr_lo = 0; }
+  __syncthreads();
+  unsigned long long my_docs = 0, my_blocks = 0;
+  uint32_t cand_seen = 0;  // path B short-circuit counter (uniform)
+  bool stop_all = (T == 0);
+
+  while (!stop_all) {
+    // (1) refill exhausted blocks
+    for (uint32_t s = 0; s < T; s++) {
+      const TermState& t = M.st[s];
+      if (!t.done && t.pos >= t.len) {
+        const bool more = (t.cur_blk < t.nfull) || (t.cur_blk == t.nfull && !t.tail_done && (t.df & 127u));
+        if (more) { decode_next(S, M, s); my_blocks++; }
+        else { __syncthreads(); if (tid == 0) M.st[s].done = 1; __syncthreads(); }
+      }
+    }
+    // (2) the round's bound
+    uint32_t bound = 0xFFFFFFFFu; bool any = false, all = true;
+    for (uint32_t s = 0; s < T; s++) { const TermState& t = M.st[s]; if (!t.done) { bound = min(bound, t.last_doc); any = true; } else all = false; }
+    if (!any || (MODE == 0 && !all)) break;
+    // (3) per-term ranges [pos, hi): docs <= bound
+    if (tid < T) {
+      const TermState& t = M.st[tid];
+      uint32_t hi = t.pos;
+      if (!t.done) { hi = lower_bound128(M.docs + tid * 128, bound + 1u); if (hi > t.len) hi = t.len; if (bound == 0xFFFFFFFFu) hi = t.len; }
+      s_rhi[tid] = hi;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t acc = 0;
+      for (uint32_t s = 0; s < T; s++) { s_rstart[s] = acc; if (MODE != 0 || s == 0) acc += s_rhi[s] - M.st[s].pos; }
+      s_rstart[T] = acc;
+    }
+    __syncthreads();
+    const uint32_t R = s_rstart[T];
+    if (*s_count + R > P.cap) {  // make room: keep the best k (TopNComputer::truncate_top_n)
+      sort_keys_desc(M, P.cap);
+      if (tid == 0) {
+        const uint32_t c = min(*s_count, P.k);
+        *s_count = c;
+        if (c == P.k) { *s_flag = 1; *s_thr_hi = M.khi[P.k - 1]; *s_thr_lo = M.klo[P.k - 1]; }
+      }
+      __syncthreads();
+      for (uint32_t i = P.k + tid; i < P.cap; i += NT) { M.khi[i] = 0; M.klo[i] = 0; }
+      __syncthreads();
+    }
+    uint32_t cutoff = 0xFFFFFFFFu;  // path B short circuit: largest doc still inside max_docs
+    bool last_round = false;
+    if (MODE == 2 && P.max_docs) {
+      // count this round's owners; if they overflow max_docs, find the doc cutoff by sorting them
+      uint32_t mine = 0;
+      for (uint32_t e = tid; e < R; e += NT) {
+        uint32_t i = 0; while (e >= s_rstart[i + 1]) i++;
+        const uint32_t d = M.docs[i * 128 + M.st[i].pos + (e - s_rstart[i])];
+        bool owner = true;
+        for (uint32_t x = 0; x < i && owner; x++) if (!M.st[x].done) { const uint32_t j = lower_bound128(M.docs + x * 128, d); if (j < M.st[x].len && M.docs[x * 128 + j] == d) owner = false; }
+        mine += owner;
+      }
+      const uint32_t incl = cta_scan_incl(mine, M.misc);
+      const uint32_t round_owners = __shfl_sync(0xffffffffu, incl, 31);  // lane 31 of the last warp has the total...
+      __syncthreads();
+      if (tid == NT - 1) M.misc[4] = incl;
+      __syncthreads();
+      const uint32_t total_owners = M.misc[4]; (void)round_owners;
+      if (cand_seen + total_owners >= P.max_docs) {
+        last_round = true;
+        const uint32_t remaining = P.max_docs - cand_seen;
+        // owners' docs -> vals/stage scratch is too small for 1024; reuse the (sorted, truncated) tail of the key buffer?  simpler:
+        // select the `remaining`-th smallest owner doc by counting: binary search on the doc value
+        uint32_t lo = 0, hi = bound;
+        while (lo < hi) {
+          const uint32_t mid = lo + ((hi - lo) >> 1);
+          uint32_t c = 0;
+          for (uint32_t e = tid; e < R; e += NT) {
+            uint32_t i = 0; while (e >= s_rstart[i + 1]) i++;
+            const uint32_t d = M.docs[i * 128 + M.st[i].pos + (e - s_rstart[i])];
+            if (d > mid) continue;
+            bool owner = true;
+            for (uint32_t x = 0; x < i && owner; x++) if (!M.st[x].done) { const uint32_t j = lower_bound128(M.docs + x * 128, d); if (j < M.st[x].len && M.docs[x * 128 + j] == d) owner = false; }
+            c += owner;
+          }
+          const uint32_t inc2 = cta_scan_incl(c, M.misc);
+          __syncthreads();
+          if (tid == NT - 1) M.misc[4] = inc2;
+          __syncthreads();
+          if (M.misc[4] >= remaining) hi = mid; else lo = mid + 1;
+          __syncthreads();
+        }
+        cutoff = lo;
+      }
+      cand_seen += total_owners;
+    }
+    // (4) score the round's postings
+    const bool thr_on = *s_flag != 0; const uint64_t thr_hi = *s_thr_hi; const uint32_t thr_lo = *s_thr_lo;
+    for (uint32_t e = tid; e < R; e += NT) {
+      uint32_t i = 0; while (e >= s_rstart[i + 1]) i++;
+      const uint32_t j = M.st[i].pos + (e - s_rstart[i]);
+      const uint32_t d = M.docs[i * 128 + j];
+      if (d > cutoff) continue;
+      uint32_t tf[MAXT];
+      bool ok = true;
+#pragma unroll
+      for (uint32_t x = 0; x < MAXT; x++) {
+        tf[x] = 0;
+        if (x >= T || !ok) continue;
+        if (x == i) { tf[x] = M.tfs[i * 128 + j]; continue; }
+        bool found = false;
+        if (!M.st[x].done) {
+          const uint32_t jj = lower_bound128(M.docs + x * 128, d);
+          if (jj < M.st[x].len && M.docs[x * 128 + jj] == d) { found = true; tf[x] = M.tfs[x * 128 + jj]; }
+        }
+        if (MODE == 0) { if (!found) ok = false; }
+        else if (found && x < i) ok = false;  // a lower slot owns this doc
+      }
+      if (!ok) continue;
+      my_docs++;
+      const uint32_t fid = S.fieldnorm[d];
+      const float norm = M.cache[fid];
+      uint64_t khi;
+      if (MODE == 2) {
+        float bm = 0.0f;  // MultiBm25Weight::score: f32 sum over the query terms in query order (bm25.rs:97-102)
+#pragma unroll
+        for (uint32_t x = 0; x < MAXT; x++) if (x < T) {
+          float sc = 0.0f;
+          if (tf[x]) { const float t = (float)tf[x]; sc = __fmul_rn(M.st[x].weight, __fdiv_rn(__fmul_rn(t, P.k1p1), __fadd_rn(t, norm))); }
+          bm = __fadd_rn(bm, sc);
+        }
+        double total = __dadd_rn(0.0, __dmul_rn(P.coeff_text, (double)bm));  // initial.rs:80-85: sum of coefficient * score
+        for (uint32_t c = 0; c < P.n_cols; c++) total = __dadd_rn(total, __dmul_rn(P.coeffs[c], P.sig[(size_t)d * P.n_cols + c]));
+        khi = ord_f64(total);
+      } else {
+        float sc[MAXT];
+#pragma unroll
+        for (uint32_t x = 0; x < MAXT; x++) { sc[x] = 0.0f; if (x < T && tf[x]) { const float t = (float)tf[x]; sc[x] = __fmul_rn(M.st[x].weight, __fdiv_rn(t, __fadd_rn(t, norm))); } }
+        float total;
+        if (MODE == 0) {  // Intersection::score = left + right + sum(others) (intersection.rs:153-157)
+          if (T == 1) total = sc[0];
+          else {
+            float others = 0.0f;
+#pragma unroll
+            for (uint32_t x = 2; x < MAXT; x++) if (x < T) others = __fadd_rn(others, sc[x]);
+            total = __fadd_rn(__fadd_rn(sc[0], sc[1]), others);
+          }
+        } else {
+          total = 0.0f;
+#pragma unroll
+          for (uint32_t x = 0; x < MAXT; x++) if (x < T && tf[x]) total = __fadd_rn(total, sc[x]);
+        }
+        khi = (uint64_t)ord_f32(total) << 32;
+      }
+      const uint32_t klo = ~d;
+      if (thr_on && !key_gt(khi, klo, thr_hi, thr_lo)) continue;
+      const uint32_t at = atomicAdd(s_count, 1u);
+      M.khi[at] = khi; M.klo[at] = klo;
+    }
+    __syncthreads();
+    if (tid < T && !M.st[tid].done && (MODE != 0 || true)) M.st[tid].pos = s_rhi[tid];
+    __syncthreads();
+    if (last_round) break;
+  }
+  // final: sort and emit the best k
+  sort_keys_desc(M, P.cap);
+  const uint32_t n = min(*s_count, P.k);
+  for (uint32_t i = tid; i < n; i += NT) {
+    P.o_docs[(size_t)q * P.k + i] = ~M.klo[i];
+    if (MODE == 2) P.o_totals[(size_t)q * P.k + i] = unord_f64(M.khi[i]);
+    else P.o_scores[(size_t)q * P.k + i] = unord_f32((uint32_t)(M.khi[i] >> 32));
+  }
+  if (tid == 0) P.o_n[q] = n;
+  for (int o = 16; o; o >>= 1) { my_docs += __shfl_down_sync(0xffffffffu, my_docs, o); }
+  if ((tid & 31) == 0 && my_docs) atomicAdd(P.counters + 0, my_docs);
+  if (tid == 0 && my_blocks) atomicAdd(P.counters + 1, my_blocks);
+}
+
+__global__ void k_interleave_signals(const double* const* cols, uint32_t n_cols, uint32_t max_doc, double* rows) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= (uint64_t)max_doc * n_cols) return;
+  const uint32_t d = (uint32_t)(i / n_cols), c = (uint32_t)(i % n_cols);
+  rows[i] = cols[c][d];
+}
+
+static size_t smem_bytes(uint32_t cap) {
+  return (size_t)cap * 12 + sizeof(TermState) * MAXT + MAXT * 128 * 8 + 344 * 4 + 256 * 4 + 256 * 4 + 40 * 4;
+}
+
+template <int MODE>
+static int launch_topk(const Params& P, uint32_t n_queries, cudaStream_t s) {
+  const size_t sm = smem_bytes(P.cap);
+  static size_t configured[3] = {0, 0, 0};
+  if (sm > 48 * 1024 && configured[MODE] < sm) {
+    SB_CUDA(cudaFuncSetAttribute(k_topk<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    configured[MODE] = sm;
+  }
+  SB_LAUNCH(k_topk<MODE>, n_queries, NT, sm, s, P);
+  SB_CHECK_LAUNCH();
+  return SB200_OK;
+}
+
+template <class T>
+static int ensure(DevBuf<T>& b, size_t n) { if (b.n < n) return b.alloc(n + (n >> 2) + 16); return SB200_OK; }
+
+static int run_batch(sb200_segment* g, const sb200_bm25_batch* b, int mode, const sb200_signal_batch* sb, uint32_t* docs,
+                     float* scores, double* totals, uint32_t* n_out, sb200_bm25_stats* stats) {
+  cudaStream_t s = g->stream;
+  if (!b || !b->term_ords || !b->weights || !b->tf_cache256 || !docs || !n_out) SB_FAIL(SB200_EINVAL, "NULL argument");
+  const uint32_t nq = b->n_queries, nt = b->n_terms, k = b->k;
+  if (nt == 0 || nt > MAXT) SB_FAIL(SB200_ERANGE, "n_terms %u outside [1,%d]", nt, MAXT);
+  if (k == 0 || k > SB200_MAX_K) SB_FAIL(SB200_ERANGE, "k %u outside [1,%d]", k, SB200_MAX_K);
+  if (nq == 0) return SB200_OK;
+  // host-side planning: drop padding; AND sorts the clauses by doc_freq (stable) like intersect_scorers (intersection.rs:24)
+  std::vector<uint32_t> terms((size_t)nq * nt), nterms(nq);
+  std::vector<float> weights((size_t)nq * nt);
+  unsigned long long postings = 0;
+  for (uint32_t q = 0; q < nq; q++) {
+    uint32_t idx[MAXT]; uint32_t c = 0;
+    for (uint32_t t = 0; t < nt; t++) {
+      const uint32_t ord = b->term_ords[(size_t)q * nt + t];
+      if (ord == SB200_NO_TERM) continue;
+      if (ord >= g->n_terms) SB_FAIL(SB200_EINVAL, "query %u: term ordinal %u >= %u", q, ord, g->n_terms);
+      idx[c++] = t;
+    }
+    if (mode == SB200_MODE_AND) std::stable_sort(idx, idx + c, [&](uint32_t a, uint32_t bb) { return g->h_df[b->term_ords[(size_t)q * nt + a]] < g->h_df[b->term_ords[(size_t)q * nt + bb]]; });
+    for (uint32_t i = 0; i < c; i++) {
+      terms[(size_t)q * nt + i] = b->term_ords[(size_t)q * nt + idx[i]];
+      weights[(size_t)q * nt + i] = b->weights[(size_t)q * nt + idx[i]];
+      postings += g->h_df[terms[(size_t)q * nt + i]];
+    }
+    nterms[q] = c;
+  }
+  SB_TRY(ensure(g->q_terms, (size_t)nq * nt)); SB_TRY(ensure(g->q_weights, (size_t)nq * nt)); SB_TRY(ensure(g->q_nterms, nq));
+  SB_TRY(ensure(g->q_cache, 256)); SB_TRY(ensure(g->o_docs, (size_t)nq * k)); SB_TRY(ensure(g->o_n, nq));
+  if (totals) SB_TRY(ensure(g->o_totals, (size_t)nq * k)); else SB_TRY(ensure(g->o_scores, (size_t)nq * k));
+  SB_TRY(ensure(g->counters, 4));
+  SB_CUDA(cudaEventRecord(g->ev0, s));
+  SB_CUDA(cudaMemcpyAsync(g->q_terms.p, terms.data(), terms.size() * 4, cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(g->q_weights.p, weights.data(), weights.size() * 4, cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(g->q_nterms.p, nterms.data(), nterms.size() * 4, cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(g->q_cache.p, b->tf_cache256, 256 * 4, cudaMemcpyDefault, s));
+  SB_CUDA(cudaMemsetAsync(g->counters.p, 0, 4 * sizeof(unsigned long long), s));
+  Params P;
+  memset(&P, 0, sizeof(P));
+  P.S.p32 = (const uint32_t*)g->postings.p; P.S.postings_len = g->postings_len; P.S.fieldnorm = g->fieldnorm.p; P.S.max_doc = g->max_doc;
+  P.S.t_data_off = g->t_data_off.p; P.S.t_end_off = g->t_end_off.p; P.S.t_df = g->t_df.p; P.S.t_first = g->t_first.p;
+  P.S.b_last = g->b_last.p; P.S.b_off = g->b_off.p; P.S.b_bits = g->b_bits.p; P.S.record = g->record;
+  P.q_terms = g->q_terms.p; P.q_nterms = g->q_nterms.p; P.q_weights = g->q_weights.p; P.cache = g->q_cache.p;
+  P.n_terms_max = nt; P.k = k;
+  uint32_t cap = 1024; while (cap < k + nt * 128u) cap <<= 1;
+  P.cap = cap;
+  P.o_docs = g->o_docs.p; P.o_scores = g->o_scores.p; P.o_totals = g->o_totals.p; P.o_n = g->o_n.p; P.counters = g->counters.p;
+  SB_CUDA(cudaEventRecord(g->evk0, s));
+  if (sb) {
+    P.k1p1 = sb->k1 + 1.0f;  // constants.k1 + 1.0 in f32 (core/src/ranking/bm25.rs:149)
+    P.coeff_text = sb->coeff_text; P.max_docs = sb->max_docs;
+    if (sb->signals && sb->signals->n_cols) {
+      if (sb->signals->max_doc < g->max_doc) SB_FAIL(SB200_EINVAL, "signal table covers %u docs, segment has %u", sb->signals->max_doc, g->max_doc);
+      if (!sb->coeffs) SB_FAIL(SB200_EINVAL, "coeffs is NULL");
+      SB_TRY(ensure(g->q_coeffs, sb->signals->n_cols));
+      SB_CUDA(cudaMemcpyAsync(g->q_coeffs.p, sb->coeffs, sb->signals->n_cols * 8, cudaMemcpyDefault, s));
+      P.sig = sb->signals->rows.p; P.n_cols = sb->signals->n_cols; P.coeffs = g->q_coeffs.p;
+    }
+    SB_TRY(launch_topk<2>(P, nq, s));
+  } else if (mode == SB200_MODE_AND) SB_TRY(launch_topk<0>(P, nq, s));
+  else if (mode == SB200_MODE_OR) SB_TRY(launch_topk<1>(P, nq, s));
+  else SB_FAIL(SB200_EINVAL, "mode %d", mode);
+  SB_CUDA(cudaEventRecord(g->evk1, s));
+  SB_CUDA(cudaMemcpyAsync(docs, g->o_docs.p, (size_t)nq * k * 4, cudaMemcpyDefault, s));
+  if (totals) SB_CUDA(cudaMemcpyAsync(totals, g->o_totals.p, (size_t)nq * k * 8, cudaMemcpyDefault, s));
+  else if (scores) SB_CUDA(cudaMemcpyAsync(scores, g->o_scores.p, (size_t)nq * k * 4, cudaMemcpyDefault, s));
+  SB_CUDA(cudaMemcpyAsync(n_out, g->o_n.p, (size_t)nq * 4, cudaMemcpyDefault, s));
+  unsigned long long h[4] = {0, 0, 0, 0};
+  SB_CUDA(cudaMemcpyAsync(h, g->counters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  SB_CUDA(cudaEventRecord(g->ev1, s));
+  SB_CUDA(cudaStreamSynchronize(s));
+  if (stats) {
+    float ms = 0; cudaEventElapsedTime(&ms, g->ev0, g->ev1);
+    stats->postings_scored = postings; stats->docs_scored = h[0]; stats->blocks_decoded = h[1]; stats->ms = ms; cudaEventElapsedTime(&stats->kernel_ms, g->evk0, g->evk1);
+  }
+  return SB200_OK;
+}
+
+}  // namespace sb200
+using namespace sb200;
+
+extern "C" {
+
+int sb200_segment_create(const uint8_t* postings_file, uint64_t postings_len, const sb200_term_info* terms, uint32_t n_terms,
+                         const uint8_t* fieldnorm_ids, uint32_t max_doc, int record_option, int device, sb200_segment** out) {
+  if (!out) SB_FAIL(SB200_EINVAL, "out is NULL");
+  *out = nullptr;
+  if ((postings_len && !postings_file) || (n_terms && !terms) || (max_doc && !fieldnorm_ids)) SB_FAIL(SB200_EINVAL, "NULL argument");
+  if (record_option < 0 || record_option > 2) SB_FAIL(SB200_EINVAL, "record_option %d", record_option);
+  if (max_doc >= TERMINATED) SB_FAIL(SB200_ERANGE, "max_doc must be < 2^31-1 (TERMINATED, tantivy/src/docset.rs:9)");
+  int ndev = 0;
+  SB_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) SB_FAIL(SB200_EINVAL, "device %d not in [0,%d)", device, ndev);
+  SB_CUDA(cudaSetDevice(device));
+  sb200_segment* g = new (std::nothrow) sb200_segment();
+  if (!g) SB_FAIL(SB200_ENOMEM, "host allocation failed");
+  g->device = device; g->record = record_option; g->stride = record_option == 0 ? 5 : (record_option == 1 ? 8 : 12);
+  g->max_doc = max_doc; g->n_terms = n_terms; g->postings_len = postings_len;
+  auto body = [&]() -> int {
+    SB_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+    SB_CUDA(cudaEventCreate(&g->ev0)); SB_CUDA(cudaEventCreate(&g->ev1));
+    SB_CUDA(cudaEventCreate(&g->evk0)); SB_CUDA(cudaEventCreate(&g->evk1));
+    cudaStream_t s = g->stream;
+    SB_CUDA(cudaEventRecord(g->ev0, s));
+    SB_TRY(g->postings.alloc(postings_len + 64));
+    SB_CUDA(cudaMemsetAsync(g->postings.p + postings_len, 0, 64, s));
+    SB_TRY(copy_in(g->postings.p, postings_file, postings_len, s));
+    SB_TRY(g->fieldnorm.alloc((size_t)max_doc + 16));
+    SB_TRY(copy_in(g->fieldnorm.p, fieldnorm_ids, max_doc, s));
+    // block slots: n_full + 1 per term (the extra one records where the vint tail starts)
+    std::vector<sb200_term_info> h_terms;
+    const sb200_term_info* ht = terms;
+    if (n_terms && is_device_ptr(terms)) { h_terms.resize(n_terms); SB_CUDA(cudaMemcpy(h_terms.data(), terms, (size_t)n_terms * sizeof(sb200_term_info), cudaMemcpyDeviceToHost)); ht = h_terms.data(); }
+    std::vector<uint32_t> first(n_terms + 1);
+    g->h_df.resize(n_terms);
+    uint64_t slots = 0, postings = 0;
+    for (uint32_t t = 0; t < n_terms; t++) {
+      first[t] = (uint32_t)slots; slots += (ht[t].doc_freq >> 7) + 1; g->h_df[t] = ht[t].doc_freq; postings += ht[t].doc_freq;
+      if (slots >= 0xFFFFFFF0ull) SB_FAIL(SB200_ERANGE, "more than 2^32 posting blocks");
+      if (ht[t].postings_len >= 0xFFFFFFFFull) SB_FAIL(SB200_ERANGE, "term %u: posting list larger than 4 GiB", t);
+    }
+    first[n_terms] = (uint32_t)slots;
+    g->n_blocks = slots - n_terms; g->n_postings = postings;
+    SB_TRY(g->t_first.alloc(n_terms + 1)); SB_TRY(g->t_data_off.alloc(n_terms + 1)); SB_TRY(g->t_end_off.alloc(n_terms + 1)); SB_TRY(g->t_df.alloc(n_terms + 1));
+    SB_TRY(g->b_last.alloc(slots + 1)); SB_TRY(g->b_off.alloc(slots + 1)); SB_TRY(g->b_bits.alloc(slots + 1));
+    SB_CUDA(cudaMemcpyAsync(g->t_first.p, first.data(), (size_t)(n_terms + 1) * 4, cudaMemcpyHostToDevice, s));
+    DevBuf<sb200_term_info> d_terms; DevBuf<int> d_err;
+    SB_TRY(d_terms.alloc(n_terms + 1)); SB_TRY(d_err.alloc(1));
+    SB_CUDA(cudaMemcpyAsync(d_terms.p, ht, (size_t)n_terms * sizeof(sb200_term_info), cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), s));
+    if (n_terms) {
+      SB_LAUNCH(k_build_directory, div_up((uint64_t)n_terms * 32, 256), 256, 0, s, g->postings.p, d_terms.p, n_terms, g->stride,
+                g->t_first.p, g->t_data_off.p, g->t_end_off.p, g->t_df.p, g->b_last.p, g->b_off.p, g->b_bits.p, postings_len, d_err.p);
+      SB_CHECK_LAUNCH();
+    }
+    int h_err = 0;
+    SB_CUDA(cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaEventRecord(g->ev1, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    if (h_err) SB_FAIL(SB200_EFORMAT, "malformed postings (code %d): term range outside the file, skip length != blocks x %d, or bit width > 32", h_err, g->stride);
+    float ms = 0; cudaEventElapsedTime(&ms, g->ev0, g->ev1); g->stage_ms = ms;
+    return SB200_OK;
+  };
+  const int rc = body();
+  if (rc != SB200_OK) { sb200_segment_destroy(g); return rc; }
+  *out = g;
+  return SB200_OK;
+}
+
+void sb200_segment_destroy(sb200_segment* g) {
+  if (!g) return;
+  cudaSetDevice(g->device);
+  if (g->stream) cudaStreamSynchronize(g->stream);
+  if (g->ev0) cudaEventDestroy(g->ev0);
+  if (g->ev1) cudaEventDestroy(g->ev1);
+  if (g->evk0) cudaEventDestroy(g->evk0);
+  if (g->evk1) cudaEventDestroy(g->evk1);
+  cudaStream_t s = g->stream;
+  delete g;
+  if (s) cudaStreamDestroy(s);
+}
+
+int sb200_segment_get_info(const sb200_segment* g, sb200_segment_info* info) {
+  if (!g || !info) SB_FAIL(SB200_EINVAL, "NULL argument");
+  info->n_terms = g->n_terms; info->n_blocks = g->n_blocks; info->n_postings = g->n_postings; info->max_doc = g->max_doc; info->_pad = 0;
+  info->hbm_bytes = g->postings.bytes() + g->fieldnorm.bytes() + g->t_first.bytes() + g->t_data_off.bytes() + g->t_end_off.bytes() +
+                    g->t_df.bytes() + g->b_last.bytes() + g->b_off.bytes() + g->b_bits.bytes();
+  info->stage_ms = g->stage_ms;
+  return SB200_OK;
+}
+
+int sb200_signals_create(const double* const* columns, uint32_t n_cols, uint32_t max_doc, int device, sb200_signals** out) {
+  if (!out) SB_FAIL(SB200_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (n_cols && !columns) SB_FAIL(SB200_EINVAL, "columns is NULL");
+  if (n_cols > 64) SB_FAIL(SB200_ERANGE, "at most 64 signal columns");
+  SB_CUDA(cudaSetDevice(device));
+  sb200_signals* sg = new (std::nothrow) sb200_signals();
+  if (!sg) SB_FAIL(SB200_ENOMEM, "host allocation failed");
+  sg->device = device; sg->n_cols = n_cols; sg->max_doc = max_doc;
+  auto body = [&]() -> int {
+    if (!n_cols || !max_doc) return SB200_OK;
+    SB_TRY(sg->rows.alloc((size_t)max_doc * n_cols));
+    std::vector<DevBuf<double>> tmp(n_cols);
+    std::vector<const double*> ptrs(n_cols);
+    for (uint32_t c = 0; c < n_cols; c++) {
+      if (!columns[c]) SB_FAIL(SB200_EINVAL, "column %u is NULL", c);
+      if (is_device_ptr(columns[c])) ptrs[c] = columns[c];
+      else { SB_TRY(tmp[c].alloc(max_doc)); SB_CUDA(cudaMemcpy(tmp[c].p, columns[c], (size_t)max_doc * 8, cudaMemcpyHostToDevice)); ptrs[c] = tmp[c].p; }
+    }
+    DevBuf<const double*> d_ptrs; SB_TRY(d_ptrs.alloc(n_cols));
+    SB_CUDA(cudaMemcpy(d_ptrs.p, ptrs.data(), n_cols * sizeof(double*), cudaMemcpyHostToDevice));
+    SB_LAUNCH(k_interleave_signals, div_up((uint64_t)max_doc * n_cols, 256), 256, 0, 0, d_ptrs.p, n_cols, max_doc, sg->rows.p);
+    SB_CHECK_LAUNCH();
+    SB_CUDA(cudaDeviceSynchronize());
+    return SB200_OK;
+  };
+  const int rc = body();
+  if (rc != SB200_OK) { delete sg; return rc; }
+  *out = sg;
+  return SB200_OK;
+}
+void sb200_signals_destroy(sb200_signals* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  delete s;
+}
+
+int sb200_bm25_topk_batch(sb200_segment* seg, const sb200_bm25_batch* batch, uint32_t* docs, float* scores, uint32_t* n_out,
+                          sb200_bm25_stats* stats) {
+  if (!seg) SB_FAIL(SB200_EINVAL, "NULL segment handle");
+  SB_CUDA(cudaSetDevice(seg->device));
+  if (!scores) SB_FAIL(SB200_EINVAL, "scores is NULL");
+  if (!batch) SB_FAIL(SB200_EINVAL, "batch is NULL");
+  return run_batch(seg, batch, batch->mode, nullptr, docs, scores, nullptr, n_out, stats);
+}
+
+int sb200_bm25_topk(sb200_segment* seg, const uint32_t* term_ords, const float* weights, uint32_t n_terms, const float* tf_cache256,
+                    int mode, uint32_t k, uint32_t* docs, float* scores, uint32_t* n_out) {
+  sb200_bm25_batch b;
+  b.n_queries = 1; b.n_terms = n_terms; b.term_ords = term_ords; b.weights = weights; b.tf_cache256 = tf_cache256; b.mode = mode; b.k = k;
+  return sb200_bm25_topk_batch(seg, &b, docs, scores, n_out, nullptr);
+}
+
+int sb200_signal_topk_batch(sb200_segment* seg, const sb200_signal_batch* batch, uint32_t* docs, double* totals, uint32_t* n_out,
+                            sb200_bm25_stats* stats) {
+  if (!seg) SB_FAIL(SB200_EINVAL, "NULL segment handle");
+  SB_CUDA(cudaSetDevice(seg->device));
+  if (!batch || !totals) SB_FAIL(SB200_EINVAL, "NULL argument");
+  return run_batch(seg, &batch->q, SB200_MODE_OR, batch, docs, nullptr, totals, n_out, stats);
+}
+
+}  // extern "C"

@@ -497,6 +497,7 @@ static int run_push(sb200_graph* g, const uint4* oldr, uint4* newr, const uint32
   cudaStream_t s = g->stream;
   const uint64_t N = g->N, words = (N + 31) / 32;
   const uint64_t nf = g->n_changed_prev, slots = g->frontier_edges_prev;
+  if (nf == 0) return SB200_OK;  // empty frontier: a converged state is a fixed point
   if (g->frontier_list.n < nf + 1) { SB_TRY(g->frontier_list.alloc(nf + 1 + (nf >> 2))); }
   if (g->frontier_off.n < 2 * (nf + 1)) { SB_TRY(g->frontier_off.alloc(2 * (nf + 1) + (nf >> 1))); }
   uint32_t* outdeg = g->frontier_off.p + (g->frontier_off.n / 2);
