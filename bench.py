@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-bm25", action="store_true")
+    ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL broadcast exchange instead of the fused peer-memory stores")
     ap.add_argument("--cpu-nodes", type=int, default=1_000_000)
     ap.add_argument("--cpu-edges", type=int, default=20_000_000)
     ap.add_argument("--ref-nodes", type=int, default=50_000)
@@ -271,34 +272,17 @@ def main():
         # (device ms of the step kernels) + exchange wall time => use wall clock around the loop
         from stract_b200.webgraph import DeviceGraph as _DG
         dg = _DG(graph, device=local_rank, rank=rank, world_size=world)
+        if not args.no_p2p:
+            dg.enable_p2p()
         info = dg.info()
         E = info["n_edges_kept"]
         ranges = dg.row_ranges()
-        from stract_b200.webgraph import _as_tensor, _global_rank
+        from stract_b200.webgraph import run_sharded_loop
 
         def one_step():
             dg.reset()
-            t = 0
-            while True:
-                st = dg.step()
-                rp, rb, fp, fb = dg.exchange_ptrs()
-                regs = _as_tensor(rp, rb, torch.uint8, dev); fr = _as_tensor(fp, fb, torch.int32, dev)
-                cnt = torch.tensor([st["n_changed"]], dtype=torch.int64, device=dev)
-                works = []
-                for r in range(world):
-                    b, e = ranges[r], ranges[r + 1]
-                    if e > b:
-                        works.append(dist.broadcast(regs[b * 64:e * 64], src=r, async_op=True))
-                        works.append(dist.broadcast(fr[b // 32:(e + 31) // 32], src=r, async_op=True))
-                works.append(dist.all_reduce(cnt, async_op=True))
-                for w in works:
-                    w.wait()
-                torch.cuda.synchronize()
-                total = int(cnt.item())
-                dg.exchange_done(total)
-                t += 1
-                if total == 0:
-                    return t
+            t, _ = run_sharded_loop(dg, world)
+            return t
         for _ in range(max(args.warmup, 3)):
             one_step()
         sampler = ClockSampler(local_rank); sampler.start()
@@ -381,7 +365,7 @@ def main():
                            "kept_edges": result["E"], "n_nodes": result["info"]["n_nodes"],
                            "iterations_per_step": result["iters"],
                            "l2_policy": "inputs >> L2: 2 x 3.2 GB register arrays + 4 GB CSR per iteration",
-                           "parallelism": "1 GPU" if world == 1 else f"destination-row partition x{world}, per-iteration all-gather of owned register rows (NCCL broadcast group)",
+                           "parallelism": "1 GPU" if world == 1 else (f"destination-row partition x{world}, " + ("NCCL broadcast of owned register rows per iteration" if args.no_p2p else "fused exchange: pull kernels store produced rows into all peers' replicas over NVLink (CUDA IPC), NCCL all-reduce of the changed count as barrier")),
                            "hbm_bytes": result["info"]["hbm_bytes"], "gen_s": round(gen_s, 2),
                            "stage_ms": result["info"]["stage_ms"]},
                 "clocks": result["clocks"], "gpu_launches": result["launches"], "roofline": result["roofline"],

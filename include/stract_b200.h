@@ -148,6 +148,17 @@ SB200_API int sb200_graph_node_ids(sb200_graph* g, uint64_t first, uint64_t coun
 SB200_API int sb200_hyperball_exchange_ptrs(sb200_graph* g, void** regs, uint64_t* regs_bytes,
                                   void** frontier_words, uint64_t* frontier_bytes);
 SB200_API int sb200_graph_row_ranges(sb200_graph* g, uint64_t* begins /* world_size+1 */);
+/* Fused exchange (one process per GPU on one NVLink/NVSwitch box): every rank exports CUDA IPC handles of its two
+ * register arrays and two bitmaps, imports those of all other ranks (any order) and enables p2p.  From then on
+ * sb200_hyperball_step stores every produced row, and ORs every changed bit, directly into the peers' replicas from
+ * inside the pull kernels (st.global / atom.or.sys on peer pointers), so no all-gather is needed: between steps the
+ * caller only needs a barrier plus the sum of the per-rank changed counts (one small all-reduce does both), then
+ * sb200_hyperball_exchange_done.  A barrier is also required after create/reset before the first step. */
+#define SB200_IPC_HANDLE_BYTES 64
+SB200_API int sb200_hyperball_ipc_export(sb200_graph* g, uint8_t* out /* 4 * SB200_IPC_HANDLE_BYTES */);
+SB200_API int sb200_hyperball_ipc_import(sb200_graph* g, const uint8_t* handles /* one peer's 4 handles */);
+SB200_API int sb200_hyperball_p2p_enable(sb200_graph* g, int on);
+
 /* after the exchange: tell the library the global changed count so every rank picks the same mode */
 SB200_API int sb200_hyperball_exchange_done(sb200_graph* g, uint64_t global_n_changed);
 

@@ -66,6 +66,9 @@ def lib():
     f("sb200_hyperball_exchange_ptrs", i32, vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), C.POINTER(u64))
     f("sb200_graph_row_ranges", i32, vp, C.POINTER(u64))
     f("sb200_hyperball_exchange_done", i32, vp, u64)
+    f("sb200_hyperball_ipc_export", i32, vp, vp)
+    f("sb200_hyperball_ipc_import", i32, vp, vp)
+    f("sb200_hyperball_p2p_enable", i32, vp, i32)
     try:
         from . import _lib_bm25
         _lib_bm25.proto(L, f)

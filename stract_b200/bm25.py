@@ -290,3 +290,39 @@ class SignalComputer:
         if return_stats:
             return docs, totals, n_out, {k_: getattr(st, k_) for k_, _ in B.Bm25Stats._fields_ if not k_.startswith("_")}
         return docs, totals, n_out
+
+
+def smoke():
+    """One small invocation of path 2 on cuda:0 checked against the CPU oracle (called by __graft_entry__.smoke)."""
+    import oracle  # test infrastructure; only smoke()/tests/bench may import it
+    rng = np.random.default_rng(3)
+    max_doc = 20_000
+    lens = np.maximum(1, rng.lognormal(4.0, 0.8, max_doc)).astype(np.uint32)
+    ids = fieldnorms_to_ids(lens)
+    oseg = oracle.Segment(ids)
+    td, tt = [], []
+    for df in [int(x) for x in np.geomspace(50, 8000, 24)]:
+        d = np.sort(rng.choice(max_doc, df, replace=False)).astype(np.uint32)
+        t = np.minimum(rng.geometric(0.6, df), 255).astype(np.uint32)
+        td.append(d); tt.append(t); oseg.add_term(d, t)
+    data, infos = encode_postings(td, tt, ids, oseg.avg_fieldnorm)
+    assert np.array_equal(data, oseg.postings_bytes())
+    seg = SegmentReader(data, infos, ids)
+    nq = 32
+    terms = np.stack([rng.choice(24, 2, replace=False) for _ in range(nq)]).astype(np.uint32)
+    cache = compute_tf_cache(seg.average_fieldnorm)
+    w = np.array([[Bm25Weight.for_one_term(int(seg.doc_freq[t]), max_doc, seg.average_fieldnorm).weight for t in row] for row in terms], np.float32)
+    od, os_, on, _ = oseg.topk_batch(terms, w, np.tile(cache, (nq * 2, 1)), 0, 100, threads=4)
+    gd, gs, gn = TopDocs.with_limit(100).search_batch(seg, terms, MODE_AND)
+    assert np.array_equal(gn, on)
+    for q in range(nq):
+        assert np.array_equal(gd[q, :gn[q]], od[q, :on[q]]) and np.array_equal(gs[q, :gn[q]], os_[q, :on[q]])
+    cols = [rng.random(max_doc), rng.random(max_doc) ** 4]
+    comp = SignalComputer(seg, SignalTable(cols), [2.0, 0.02], coeff_text=0.005)
+    t5 = np.stack([rng.choice(24, 5, replace=False) for _ in range(8)]).astype(np.uint32)
+    w5 = np.array([[StractBm25Weight.for_one_term(int(seg.doc_freq[t]), max_doc, seg.average_fieldnorm).weight for t in row] for row in t5], np.float32)
+    od, ot, on, _ = oseg.signal_topk_batch(t5, w5, np.tile(cache, (40, 1)), 1.2, 0.005, cols, [2.0, 0.02], 50, threads=4)
+    gd, gt, gn = comp.top_docs_batch(t5, 50)
+    assert np.array_equal(gd, od) and np.array_equal(gt, ot) and np.array_equal(gn, on)
+    seg.close()
+    print(f"smoke path2 ok: {nq} AND queries + 8 signal queries bit-exact against the oracle")

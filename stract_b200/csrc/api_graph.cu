@@ -73,6 +73,10 @@ void sb200_graph_destroy(sb200_graph* g) {
   if (!g) return;
   cudaSetDevice(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);
+  for (int p = 0; p < g->n_peers; p++) for (int i = 0; i < 2; i++) {
+    if (g->peer_regs[i][p]) cudaIpcCloseMemHandle(g->peer_regs[i][p]);
+    if (g->peer_bm[i][p]) cudaIpcCloseMemHandle(g->peer_bm[i][p]);
+  }
   if (g->h_counters) cudaFreeHost(g->h_counters);
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
@@ -185,6 +189,41 @@ int sb200_graph_row_ranges(sb200_graph* g, uint64_t* begins) {
   for (int r = 0; r <= g->world; r++) begins[r] = g->range_begins[r];
   return SB200_OK;
 }
+// ---- fused exchange over NVLink peer memory (CUDA IPC between the per-GPU processes) ----------------------
+int sb200_hyperball_ipc_export(sb200_graph* g, uint8_t* out /* 4 x 64 bytes */) {
+  SB_ENTER(g);
+  if (!out) SB_FAIL(SB200_EINVAL, "out is NULL");
+  void* ptrs[4] = {g->regs[0].p, g->regs[1].p, g->bm[0].p, g->bm[1].p};
+  for (int i = 0; i < 4; i++) {
+    cudaIpcMemHandle_t h;
+    SB_CUDA(cudaIpcGetMemHandle(&h, ptrs[i]));
+    static_assert(sizeof(h) == SB200_IPC_HANDLE_BYTES, "IPC handle size");
+    memcpy(out + (size_t)i * SB200_IPC_HANDLE_BYTES, &h, sizeof(h));
+  }
+  return SB200_OK;
+}
+int sb200_hyperball_ipc_import(sb200_graph* g, const uint8_t* handles) {
+  SB_ENTER(g);
+  if (!handles) SB_FAIL(SB200_EINVAL, "handles is NULL");
+  if (g->n_peers >= sb200::MAX_PEERS) SB_FAIL(SB200_ERANGE, "more than %d peers", sb200::MAX_PEERS);
+  void* opened[4];
+  for (int i = 0; i < 4; i++) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)i * SB200_IPC_HANDLE_BYTES, sizeof(h));
+    SB_CUDA(cudaIpcOpenMemHandle(&opened[i], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  const int p = g->n_peers++;
+  g->peer_regs[0][p] = opened[0]; g->peer_regs[1][p] = opened[1];
+  g->peer_bm[0][p] = opened[2]; g->peer_bm[1][p] = opened[3];
+  return SB200_OK;
+}
+int sb200_hyperball_p2p_enable(sb200_graph* g, int on) {
+  SB_ENTER(g);
+  if (on && g->n_peers != g->world - 1) SB_FAIL(SB200_ESTATE, "imported %d peers, world_size-1 = %d", g->n_peers, g->world - 1);
+  g->p2p = on != 0;
+  return SB200_OK;
+}
+
 int sb200_hyperball_exchange_done(sb200_graph* g, uint64_t global_n_changed) {
   SB_ENTER(g);
   g->n_changed_prev = global_n_changed;

@@ -309,8 +309,13 @@ __global__ void __launch_bounds__(NT) k_topk(const Params P) {
   unsigned long long my_docs = 0, my_blocks = 0;
   uint32_t cand_seen = 0;  // path B short-circuit counter (uniform)
   bool stop_all = (T == 0);
+  // watchdog: every pass of the loop below consumes a block, skips blocks or advances a cursor; a corrupt file
+  // must not be able to spin a CTA forever
+  unsigned long long budget = 64;
+  for (uint32_t s = 0; s < T; s++) budget += 132ull * (M.st[s].nfull + 2);
 
   while (!stop_all) {
+    if (budget-- == 0) { if (tid == 0) atomicAdd(P.counters + 2, 1ull); break; }
     // (1) refill exhausted blocks
     for (uint32_t s = 0; s < T; s++) {
       const TermState& t = M.st[s];
@@ -318,6 +323,53 @@ __global__ void __launch_bounds__(NT) k_topk(const Params P) {
         const bool more = (t.cur_blk < t.nfull) || (t.cur_blk == t.nfull && !t.tail_done && (t.df & 127u));
         if (more) { decode_next(S, M, s); my_blocks++; }
         else { __syncthreads(); if (tid == 0) M.st[s].done = 1; __syncthreads(); }
+      }
+    }
+    // (1b) AND: block-level leapfrog.  A match is >= every term's head, so with L = max head any block whose
+    // last doc is < L is dead: jump over it (and its successors) through the directory without decoding, the
+    // way Intersection::advance seeks the skip lists (intersection.rs:95-125, skip.rs:243-254).
+    if (MODE == 0 && T > 1) {
+      bool alive = true; uint32_t L = 0;
+      for (uint32_t s = 0; s < T; s++) { const TermState& t = M.st[s]; if (t.done) alive = false; else L = max(L, M.docs[s * 128 + t.pos]); }
+      if (alive) {
+        int victim = -1;
+        for (uint32_t s = 0; s < T; s++) if (M.st[s].last_doc < L) { victim = (int)s; break; }
+        if (victim >= 0) {
+          __syncthreads();
+          const TermState& t = M.st[victim];
+          const uint32_t first = t.first, nfull = t.nfull;
+          uint32_t j = nfull;
+          for (uint32_t base = t.cur_blk; base < nfull; base += NT) {
+            const uint32_t idx = base + tid;
+            const bool pred = idx < nfull && __ldg(S.b_last + first + idx) >= L;
+            const unsigned m = __ballot_sync(0xffffffffu, pred);
+            if ((tid & 31) == 0) M.misc[tid >> 5] = m ? base + (tid & ~31u) + (uint32_t)__ffs(m) - 1u : 0xFFFFFFFFu;
+            __syncthreads();
+            const uint32_t best = min(min(M.misc[0], M.misc[1]), min(M.misc[2], M.misc[3]));
+            __syncthreads();
+            if (best != 0xFFFFFFFFu) { j = best; break; }
+          }
+          if (tid == 0) {
+            TermState& w = M.st[victim];
+            if (j > w.cur_blk || w.cur_blk > nfull) { w.cur_blk = max(j, w.cur_blk); }
+            w.prev_last = (w.cur_blk > 0 && w.cur_blk <= nfull) ? S.b_last[first + w.cur_blk - 1] : w.prev_last;
+            w.pos = 0; w.len = 0;
+          }
+          __syncthreads();
+          continue;  // refill decodes the target block (or marks the term exhausted)
+        }
+        // all current blocks reach L: drop their docs below L
+        __syncthreads();
+        if (tid < T) {
+          const uint32_t p = lower_bound128(M.docs + tid * 128, L);
+          s_rhi[tid] = (p > M.st[tid].pos) ? 1u : 0u;
+          if (p > M.st[tid].pos) M.st[tid].pos = min(p, M.st[tid].len);
+        }
+        __syncthreads();
+        bool moved = false;
+        for (uint32_t s = 0; s < T; s++) moved |= (s_rhi[s] != 0);
+        __syncthreads();
+        if (moved) continue;  // heads rose: L may have risen too
       }
     }
     // (2) the round's bound
@@ -577,6 +629,7 @@ static int run_batch(sb200_segment* g, const sb200_bm25_batch* b, int mode, cons
   SB_CUDA(cudaMemcpyAsync(h, g->counters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
   SB_CUDA(cudaEventRecord(g->ev1, s));
   SB_CUDA(cudaStreamSynchronize(s));
+  if (h[2]) SB_FAIL(SB200_EFORMAT, "%llu queries hit the decode watchdog (inconsistent posting data)", h[2]);
   if (stats) {
     float ms = 0; cudaEventElapsedTime(&ms, g->ev0, g->ev1);
     stats->postings_scored = postings; stats->docs_scored = h[0]; stats->blocks_decoded = h[1]; stats->ms = ms; cudaEventElapsedTime(&stats->kernel_ms, g->evk0, g->evk1);

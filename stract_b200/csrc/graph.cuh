@@ -14,6 +14,11 @@
 #pragma once
 #include "common.cuh"
 
+namespace sb200 {
+constexpr int MAX_PEERS = 15;
+struct PeerOut { uint4* newr[MAX_PEERS]; uint32_t* bmc[MAX_PEERS]; int n; };
+}
+
 struct sb200_graph {
   int device = 0, rank = 0, world = 1;
   cudaStream_t stream = nullptr;
@@ -56,6 +61,11 @@ struct sb200_graph {
   bool has_changes = true;
   uint64_t n_changed_prev = 0, frontier_edges_prev = 0;
   bool exchange_pending = false;
+  // fused multi-GPU exchange over peer memory (CUDA IPC): replicas of regs[2]/bm[2] on the other ranks
+  int n_peers = 0;
+  bool p2p = false;
+  void* peer_regs[2][sb200::MAX_PEERS] = {{nullptr}};
+  void* peer_bm[2][sb200::MAX_PEERS] = {{nullptr}};
   double dense_frac = 0.35, push_div = 48.0;  // mode policy (see hb_step)
   int force_mode = -1;
 

@@ -16,6 +16,8 @@
 
 #include <cub/cub.cuh>
 #include <algorithm>
+#include <ctime>
+#include <cstdlib>
 #include <vector>
 
 namespace sb200 {
@@ -248,6 +250,20 @@ static int exclusive_scan_u32(DevBuf<uint8_t>& tmp, const T* in, uint32_t* out, 
   return SB200_OK;
 }
 
+// optional per-phase wall timing of the staging pipeline (SB200_STAGE_TIMING=1 prints to stderr)
+struct PhaseTimer {
+  bool on; cudaStream_t s; double t0; const char* name = nullptr;
+  explicit PhaseTimer(cudaStream_t st) : s(st) { on = getenv("SB200_STAGE_TIMING") != nullptr; t0 = now(); }
+  static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+  void mark(const char* next) {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    const double t = now();
+    if (name) fprintf(stderr, "[sb200 stage] %-28s %9.2f ms\n", name, t - t0);
+    name = next; t0 = t;
+  }
+};
+
 static int bits_for(uint64_t n) { int b = 1; while (b < 32 && (1ull << b) < n) b++; return b; }
 
 int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi, const uint64_t* to_lo,
@@ -257,6 +273,8 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
   g->E_in = n_edges;
   if (n_edges >= 0xFFFFFFF0ull) SB_FAIL(SB200_ERANGE, "n_edges %llu exceeds the 2^32-16 limit of u32 CSR offsets", (unsigned long long)n_edges);
   SB_CUDA(cudaEventRecord(g->ev0, s));
+  PhaseTimer pt(s);
+  pt.mark("0 copy-in");
 
   // ---- 0. bring the SoA edge stream into HBM (no copy if the caller already has it there) ----
   DevBuf<uint64_t> in_copy[5];
@@ -274,6 +292,7 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
   unsigned long long h_ctr[8]; int h_flags[2];
   DevBuf<uint8_t>& tmp = g->cub_tmp;
 
+  pt.mark("1a hash insert");
   // ---- 1. node dictionary ---------------------------------------------------------------------
   DevBuf<ulonglong2> table;
   uint64_t cap = 1ull << 12;
@@ -297,6 +316,7 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
     cap <<= 2;  // load factor exceeded 1/2: grow and redo (still linear overall)
     if (cap > (1ull << 34)) SB_FAIL(SB200_ENOMEM, "node hash set would exceed 2^34 slots");
   }
+  pt.mark("1b compact+sort ids");
   const uint64_t N = n_keys + (has_max ? 1 : 0);
   g->N = N;
   if (N >= 0xFFFFFFFEull) SB_FAIL(SB200_ERANGE, "%llu nodes exceed the u32 index space", (unsigned long long)N);
@@ -330,12 +350,14 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
     }
     SB_CUDA(cudaStreamSynchronize(s));
   }
+  pt.mark("1c assign ranks");
   DevBuf<uint32_t> slot_val; SB_TRY(slot_val.alloc(cap));
   if (n_keys) {
     SB_LAUNCH(k_assign_ranks, div_up(n_keys, TPB), TPB, 0, s, g->id_lo.p, g->id_hi.p, n_keys, table.p, slot_val.p, cap - 1);
     SB_CHECK_LAUNCH();
   }
 
+  pt.mark("2a map edges");
   // ---- 2. edges -> (to_rank<<32|from_rank), stable sort, unique_by first-wins, drop skipped ----
   DevBuf<uint64_t> keys_a, keys_b; SB_TRY(keys_a.alloc(n_edges)); SB_TRY(keys_b.alloc(n_edges));
   DevBuf<uint8_t> skip_a, skip_b; SB_TRY(skip_a.alloc(n_edges)); SB_TRY(skip_b.alloc(n_edges));
@@ -346,6 +368,7 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
   for (int a = 0; a < 5; a++) in_copy[a].release();
   table.release(); slot_val.release();
 
+  pt.mark("2b sort pairs + select");
   const int nb = bits_for(N);
   uint64_t *k = keys_a.p, *k_alt = keys_b.p; uint8_t *sk = skip_a.p, *sk_alt = skip_b.p;
   SB_TRY((sort_pairs<uint64_t, uint8_t>(tmp, k, k_alt, sk, sk_alt, n_edges, 0, 32 + nb, false, s)));
@@ -365,6 +388,7 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
   std::swap(k, k_alt);  // k = kept keys in rank space, sorted by (to, from)
   skip_a.release(); skip_b.release();
 
+  pt.mark("3a degrees + node sort");
   // ---- 3. degree-sorted relabel + CSR (both directions) ------------------------------------------
   DevBuf<uint32_t> deg_a, deg_b, val_b; SB_TRY(deg_a.alloc(N)); SB_TRY(deg_b.alloc(N)); SB_TRY(val_b.alloc(N));
   SB_CUDA(cudaMemsetAsync(deg_a.p, 0, N * 4, s));
@@ -400,6 +424,7 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
   g->row_begin = g->range_begins[g->rank];
   g->row_end = g->range_begins[g->rank + 1];
 
+  pt.mark("3b remap + sort (dst CSR)");
   // destination-major CSR in internal ids
   DevBuf<uint32_t> col_full; SB_TRY(col_full.alloc(E));
   if (E) {
@@ -410,6 +435,7 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
     uint64_t* c = keys_c.p;
     SB_TRY(sort_keys<uint64_t>(tmp, a, c, E, 0, 32 + nb, s));
     SB_LAUNCH(k_lo32, div_up(E, TPB), TPB, 0, s, a, E, col_full.p); SB_CHECK_LAUNCH();
+    pt.mark("3c remap + sort (fwd CSR)");
     // source-major CSR (single-rank handles only: the push branch needs every out-edge)
     if (g->world == 1) {
       uint64_t* other = c;  // scratch half of the last sort
@@ -433,6 +459,7 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
   }
   keys_a.release(); keys_b.release();
 
+  pt.mark("4 partition");
   // ---- 4. owned slice of the CSR + pull work partition --------------------------------------------
   uint32_t h_rp[2] = {0, 0};
   SB_CUDA(cudaMemcpyAsync(&h_rp[0], g->row_ptr.p + g->row_begin, 4, cudaMemcpyDeviceToHost, s));
@@ -481,6 +508,7 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
     SB_TRY(g->partial.alloc((size_t)std::max<uint64_t>(1, g->n_multi_items) * 4));
     SB_CUDA(cudaStreamSynchronize(s));
   }
+  pt.mark(nullptr);
   SB_CUDA(cudaEventRecord(g->ev1, s));
   SB_CUDA(cudaStreamSynchronize(s));
   float ms = 0; cudaEventElapsedTime(&ms, g->ev0, g->ev1);

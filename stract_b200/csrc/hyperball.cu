@@ -157,6 +157,20 @@ __global__ void k_bm_fill(uint32_t* bm, uint64_t N, uint64_t words) {
   bm[i] = m;
 }
 
+// Fused exchange: a produced row is stored into the local `new` array AND, over NVLink peer memory, into every
+// other rank's replica of it (one writer per row, so plain 16-B stores; the changed bit goes through a
+// system-scope atomic OR).  This replaces the per-iteration all-gather: the transfer of a row overlaps the
+// gathers of the rows still being computed, and rows that did not change never cross the link.
+__device__ __forceinline__ void publish_row(uint4* __restrict__ newr, uint32_t* __restrict__ bm_cur, const PeerOut& peers,
+                                            uint32_t row, uint32_t sub, uint4 acc, bool write, bool changed) {
+  if (write) newr[(uint64_t)row * 4 + sub] = acc;
+  if (changed && sub == 0) atomicOr(bm_cur + (row >> 5), 1u << (row & 31));
+  for (int p = 0; p < peers.n; p++) {
+    if (write) peers.newr[p][(uint64_t)row * 4 + sub] = acc;
+    if (changed && sub == 0) atomicOr_system(peers.bmc[p] + (row >> 5), 1u << (row & 31));
+  }
+}
+
 __device__ __forceinline__ bool bm_test(const uint32_t* __restrict__ bm, uint32_t v) {
   return (__ldg(bm + (v >> 5)) >> (v & 31)) & 1u;
 }
@@ -166,7 +180,7 @@ template <bool FRONTIER>
 __global__ void __launch_bounds__(256) k_pull_quad(uint64_t row_begin, uint64_t row_end,
     const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col, uint32_t col_base,
     const uint4* __restrict__ oldr, uint4* __restrict__ newr,
-    const uint32_t* __restrict__ bm_prev, uint32_t* __restrict__ bm_cur) {
+    const uint32_t* __restrict__ bm_prev, uint32_t* __restrict__ bm_cur, const PeerOut peers) {
   const uint64_t gt = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const uint32_t sub = threadIdx.x & 3;
   const uint32_t lane = threadIdx.x & 31;
@@ -176,17 +190,20 @@ __global__ void __launch_bounds__(256) k_pull_quad(uint64_t row_begin, uint64_t 
   const uint32_t e0 = row_ptr[row] - col_base, e1 = row_ptr[row + 1] - col_base;
   const uint4 own = oldr[row * 4 + sub];
   uint4 acc = own;
+  // lane `sub` fetches source index e+sub (one 16-B request per quad per 4 edges, prefetched one step ahead)
+  // and the quad shares the four indices by shuffle; an out-of-range or (FRONTIER) unchanged source is
+  // redirected to the row itself, which is a no-op under max and hits L1.
+  const unsigned qmask = 0xFu << (lane & ~3u);
+  const uint32_t self = (uint32_t)row;
+  uint32_t nxt = (e0 + sub < e1) ? ld_stream_u32(col + e0 + sub) : self;
   for (uint32_t e = e0; e < e1; e += 4) {
-    uint32_t i0 = col[e];
-    uint32_t i1 = (e + 1 < e1) ? col[e + 1] : i0;
-    uint32_t i2 = (e + 2 < e1) ? col[e + 2] : i0;
-    uint32_t i3 = (e + 3 < e1) ? col[e + 3] : i0;
-    if (FRONTIER) {  // an unchanged source is a no-op: redirect it to our own (cached) row
-      i0 = bm_test(bm_prev, i0) ? i0 : (uint32_t)row;
-      i1 = bm_test(bm_prev, i1) ? i1 : (uint32_t)row;
-      i2 = bm_test(bm_prev, i2) ? i2 : (uint32_t)row;
-      i3 = bm_test(bm_prev, i3) ? i3 : (uint32_t)row;
-    }
+    uint32_t mine = nxt;
+    nxt = (e + 4 + sub < e1) ? ld_stream_u32(col + e + 4 + sub) : self;
+    if (FRONTIER) mine = bm_test(bm_prev, mine) ? mine : self;
+    const uint32_t i0 = __shfl_sync(qmask, mine, 0, 4);
+    const uint32_t i1 = __shfl_sync(qmask, mine, 1, 4);
+    const uint32_t i2 = __shfl_sync(qmask, mine, 2, 4);
+    const uint32_t i3 = __shfl_sync(qmask, mine, 3, 4);
     const uint4 v0 = oldr[(uint64_t)i0 * 4 + sub];
     const uint4 v1 = oldr[(uint64_t)i1 * 4 + sub];
     const uint4 v2 = oldr[(uint64_t)i2 * 4 + sub];
@@ -196,8 +213,7 @@ __global__ void __launch_bounds__(256) k_pull_quad(uint64_t row_begin, uint64_t 
   const unsigned ball = __ballot_sync(0xffffffffu, ne_u4(acc, own));
   const bool changed = ((ball >> (lane & ~3u)) & 0xFu) != 0u;
   if (!live) return;
-  if (changed || bm_test(bm_prev, (uint32_t)row)) newr[row * 4 + sub] = acc;
-  if (changed && sub == 0) atomicOr(bm_cur + (row >> 5), 1u << (row & 31));
+  publish_row(newr, bm_cur, peers, (uint32_t)row, sub, acc, changed || bm_test(bm_prev, (uint32_t)row), changed);
 }
 
 // ---- pull, long rows: one warp per <=CHUNK_EDGES work item ---------------------------------------------
@@ -206,7 +222,7 @@ __global__ void __launch_bounds__(256) k_pull_warp(uint64_t n_items, uint64_t fi
     const uint32_t* __restrict__ item_row, const uint32_t* __restrict__ item_start, uint32_t warp_row_begin,
     const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col, uint32_t col_base,
     const uint4* __restrict__ oldr, uint4* __restrict__ newr, uint4* __restrict__ partial,
-    const uint32_t* __restrict__ bm_prev, uint32_t* __restrict__ bm_cur) {
+    const uint32_t* __restrict__ bm_prev, uint32_t* __restrict__ bm_cur, const PeerOut peers) {
   const uint64_t item = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   if (item >= n_items) return;  // whole warp exits together
   const uint32_t lane = threadIdx.x & 31, sub = lane & 3, q = lane >> 2;
@@ -249,16 +265,13 @@ __global__ void __launch_bounds__(256) k_pull_warp(uint64_t n_items, uint64_t fi
   acc = vmax_u8x16(acc, own);
   const unsigned ball = __ballot_sync(0xffffffffu, ne_u4(acc, own));
   const bool changed = (ball & 0xFu) != 0u;
-  if (q == 0) {
-    if (changed || bm_test(bm_prev, row)) newr[(uint64_t)row * 4 + sub] = acc;
-    if (changed && sub == 0) atomicOr(bm_cur + (row >> 5), 1u << (row & 31));
-  }
+  if (q == 0) publish_row(newr, bm_cur, peers, row, sub, acc, changed || bm_test(bm_prev, row), changed);
 }
 
 // rows spanning several work items: one warp reduces the parked partials
 __global__ void __launch_bounds__(256) k_pull_merge(uint64_t n_rows, const uint32_t* __restrict__ item_start,
     uint32_t warp_row_begin, const uint4* __restrict__ partial, const uint4* __restrict__ oldr,
-    uint4* __restrict__ newr, const uint32_t* __restrict__ bm_prev, uint32_t* __restrict__ bm_cur) {
+    uint4* __restrict__ newr, const uint32_t* __restrict__ bm_prev, uint32_t* __restrict__ bm_cur, const PeerOut peers) {
   const uint64_t r = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   if (r >= n_rows) return;
   const uint32_t lane = threadIdx.x & 31, sub = lane & 3, q = lane >> 2;
@@ -277,10 +290,7 @@ __global__ void __launch_bounds__(256) k_pull_merge(uint64_t n_rows, const uint3
   acc = vmax_u8x16(acc, own);
   const unsigned ball = __ballot_sync(0xffffffffu, ne_u4(acc, own));
   const bool changed = (ball & 0xFu) != 0u;
-  if (q == 0) {
-    if (changed || bm_test(bm_prev, row)) newr[(uint64_t)row * 4 + sub] = acc;
-    if (changed && sub == 0) atomicOr(bm_cur + (row >> 5), 1u << (row & 31));
-  }
+  if (q == 0) publish_row(newr, bm_cur, peers, row, sub, acc, changed || bm_test(bm_prev, row), changed);
 }
 
 // ---- push from a small frontier (update_changed_counters, harmonic.rs:75-114) --------------------------
@@ -464,6 +474,8 @@ int hb_reset(sb200_graph* g) {
 template <bool FRONTIER>
 static int launch_pull(sb200_graph* g, const uint4* oldr, uint4* newr, const uint32_t* bmp, uint32_t* bmc) {
   cudaStream_t s = g->stream;
+  PeerOut po; po.n = 0;
+  if (g->p2p) { po.n = g->n_peers; for (int p = 0; p < g->n_peers; p++) { po.newr[p] = (uint4*)g->peer_regs[g->cur ^ 1][p]; po.bmc[p] = (uint32_t*)g->peer_bm[g->bcur ^ 1][p]; } }
   const int FW = FRONTIER ? sb200_graph::F_PULL_WARP_FRONT : sb200_graph::F_PULL_WARP_DENSE;
   const int FQ = FRONTIER ? sb200_graph::F_PULL_QUAD_FRONT : sb200_graph::F_PULL_QUAD_DENSE;
   const double per_edge = FRONTIER ? 4.0 : 68.0;  // col index (+ the 64-B gather when every source is read)
@@ -471,14 +483,14 @@ static int launch_pull(sb200_graph* g, const uint4* oldr, uint4* newr, const uin
     PROF_BEGIN(g, FW);
     SB_LAUNCH(k_pull_warp<FRONTIER>, div_up(g->n_items * 32, 256), 256, 0, s, g->n_items, g->n_multi_items,
               g->item_row.p, g->item_start.p, (uint32_t)g->warp_row_begin, g->row_ptr.p, g->col.p, g->col_base, oldr, newr,
-              g->partial.p, bmp, bmc);
+              g->partial.p, bmp, bmc, po);
     SB_CHECK_LAUNCH();
     PROF_END(g, FW, per_edge * (double)g->E_warp + 68.0 * (double)(g->warp_row_end - g->warp_row_begin - g->n_multi_rows));
   }
   if (g->n_multi_rows) {
     PROF_BEGIN(g, sb200_graph::F_PULL_MERGE);
     SB_LAUNCH(k_pull_merge, div_up(g->n_multi_rows * 32, 256), 256, 0, s, g->n_multi_rows, g->item_start.p,
-              (uint32_t)g->warp_row_begin, g->partial.p, oldr, newr, bmp, bmc);
+              (uint32_t)g->warp_row_begin, g->partial.p, oldr, newr, bmp, bmc, po);
     SB_CHECK_LAUNCH();
     PROF_END(g, sb200_graph::F_PULL_MERGE, 64.0 * (double)g->n_multi_items + 68.0 * (double)g->n_multi_rows);
   }
@@ -486,7 +498,7 @@ static int launch_pull(sb200_graph* g, const uint4* oldr, uint4* newr, const uin
   if (nq) {
     PROF_BEGIN(g, FQ);
     SB_LAUNCH(k_pull_quad<FRONTIER>, div_up(nq * 4, 256), 256, 0, s, g->quad_row_begin, g->quad_row_end, g->row_ptr.p,
-              g->col.p, g->col_base, oldr, newr, bmp, bmc);
+              g->col.p, g->col_base, oldr, newr, bmp, bmc, po);
     SB_CHECK_LAUNCH();
     PROF_END(g, FQ, per_edge * (double)g->E_quad + 68.0 * (double)nq);
   }
@@ -546,7 +558,9 @@ int hb_step(sb200_graph* g, sb200_iter_stats* st) {
   }
   if (force_mode >= 0 && (force_mode < 2 || (g->has_fwd && g->world == 1))) mode = force_mode;
   SB_CUDA(cudaEventRecord(g->ev0, s));
-  SB_CUDA(cudaMemsetAsync(bmc, 0, (words + 1) * 4, s));
+  // peers write their changed bits straight into this rank's bitmap, so with the fused exchange it is cleared
+  // at the END of the previous step (before the inter-step barrier), never at the start of this one
+  if (!g->p2p) SB_CUDA(cudaMemsetAsync(bmc, 0, (words + 1) * 4, s));
   SB_CUDA(cudaMemsetAsync(g->counters.p, 0, 8 * sizeof(unsigned long long), s));
   if (mode == 0) SB_TRY(launch_pull<false>(g, oldr, newr, bmp, bmc));
   else if (mode == 1) SB_TRY(launch_pull<true>(g, oldr, newr, bmp, bmc));
@@ -560,6 +574,7 @@ int hb_step(sb200_graph* g, sb200_iter_stats* st) {
     SB_CHECK_LAUNCH();
     PROF_END(g, sb200_graph::F_FINALIZE, 0.25 * (double)nrows);  // 2 bitmap bits/row; + 112 B per changed row below
   }
+  if (g->p2p) SB_CUDA(cudaMemsetAsync((void*)bmp, 0, (words + 1) * 4, s));  // next step's `cur` bitmap
   SB_CUDA(cudaMemcpyAsync(g->h_counters, g->counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   SB_CUDA(cudaEventRecord(g->ev1, s));
   SB_CUDA(cudaStreamSynchronize(s));

@@ -123,7 +123,8 @@ class DeviceGraph:
         check(self._L.sb200_graph_create(*(p[0] for p in ptrs), graph.n_edges, skipped_rel, device, rank,
                                          world_size, C.byref(self._h)))
         self._keep = None
-        self.world_size, self.rank = world_size, rank
+        self.world_size, self.rank, self.device = world_size, rank, device
+        self.p2p = False
 
     def info(self):
         gi = GraphInfo()
@@ -206,6 +207,31 @@ class DeviceGraph:
         check(self._L.sb200_hyperball_exchange_ptrs(self._h, C.byref(regs), C.byref(rb), C.byref(fr), C.byref(fb)))
         return regs.value, rb.value, fr.value, fb.value
 
+    def exchange_tensors(self):
+        """(registers uint8 [N*64], changed bitmap int32 [ceil(N/32)]) as zero-copy torch views of HBM."""
+        import torch
+        regs, rb, fr, fb = self.exchange_ptrs()
+        dev = torch.device("cuda", self.device)
+        torch.cuda.synchronize(dev)
+        return _as_tensor(regs, rb, torch.uint8, dev), _as_tensor(fr, fb, torch.int32, dev)
+
+    def enable_p2p(self, group=None):
+        """Fused exchange: swap CUDA IPC handles with every other rank and let the pull kernels store produced rows
+        straight into the peers' replicas over NVLink (sb200_hyperball_ipc_*)."""
+        import torch.distributed as dist
+        mine = (C.c_uint8 * 256)()
+        check(self._L.sb200_hyperball_ipc_export(self._h, mine))
+        allh = [None] * self.world_size
+        dist.all_gather_object(allh, bytes(mine), group=group)
+        for r, h in enumerate(allh):
+            if r == self.rank:
+                continue
+            buf = (C.c_uint8 * 256).from_buffer_copy(h)
+            check(self._L.sb200_hyperball_ipc_import(self._h, buf))
+        check(self._L.sb200_hyperball_p2p_enable(self._h, 1))
+        dist.barrier(group=group)
+        self.p2p = True
+
     def exchange_done(self, global_n_changed):
         check(self._L.sb200_hyperball_exchange_done(self._h, int(global_n_changed)))
 
@@ -263,48 +289,72 @@ class HarmonicCentrality:
         return len(self.values) == 0
 
 
+def run_sharded_loop(engine, world_size, group=None, max_iters=0):
+    """The AMPC round loop (crates/core/src/ampc/coordinator.rs:151-213 driving the six CentralityMappers,
+    entrypoint/ampc/harmonic_centrality/mapper.rs:38-45) for one rank, with torch.distributed as transport.
+
+    `engine` owns this rank's shard: `step()` runs one HyperBall iteration over its destination rows,
+    `exchange_tensors()` exposes the full register array and changed bitmap as torch tensors,
+    `row_ranges()` gives every rank's row range.  After each step every owner broadcasts its rows (the DHT
+    `HyperLogLog64Upsert` max-merge has a single writer per row, so it is an all-gather) and its bitmap words
+    (SaveBloom/UpdateBloom), and the changed counts are summed (Meta.round_had_changes)."""
+    import torch
+    import torch.distributed as dist
+    ranges = engine.row_ranges()
+    stats = []
+    t = 0
+    fused = bool(getattr(engine, "p2p", False))
+    if fused:
+        dist.barrier(group=group)  # every replica must be (re)initialised before a peer may write into it
+    while True:
+        st = engine.step()
+        if fused:
+            # rows and changed bits already sit in every replica; the all-reduce is the inter-step barrier
+            dev = torch.device("cuda", engine.device)
+            cnt = torch.tensor([st["n_changed"]], dtype=torch.int64, device=dev)
+            dist.all_reduce(cnt, group=group)
+            total = int(cnt.item())
+            engine.exchange_done(total)
+            st["n_changed_global"] = total
+            stats.append(st)
+            t += 1
+            if total == 0 or (max_iters and t >= max_iters):
+                return t, stats
+            continue
+        regs, fr = engine.exchange_tensors()
+        cnt = torch.tensor([st["n_changed"]], dtype=torch.int64, device=regs.device)
+        works = []
+        for r in range(world_size):
+            b, e = ranges[r], ranges[r + 1]
+            if e > b:
+                src = _global_rank(group, r)
+                works.append(dist.broadcast(regs[b * 64:e * 64], src=src, group=group, async_op=True))
+                works.append(dist.broadcast(fr[b // 32:(e + 31) // 32], src=src, group=group, async_op=True))
+        works.append(dist.all_reduce(cnt, group=group, async_op=True))
+        for w in works:
+            w.wait()
+        if regs.is_cuda:
+            torch.cuda.current_stream(regs.device).synchronize()
+        total = int(cnt.item())
+        engine.exchange_done(total)
+        st["n_changed_global"] = total
+        stats.append(st)
+        t += 1
+        if total == 0 or (max_iters and t >= max_iters):
+            return t, stats
+
+
 class ShardedHarmonicCentrality:
-    """The distributed job (coordinator.rs:122-135, mapper.rs:38-45) with torch.distributed as the
-    transport: every rank holds the full counter array, owns a destination-row range of the CSR and
-    after each iteration all-gathers the owned register rows (the DHT `HyperLogLog64Upsert` max-merge
-    has a single writer per row, so it degenerates to an all-gather), the changed bitmap
-    (SaveBloom/UpdateBloom) and sums the changed count (Meta.round_had_changes)."""
+    """The distributed job (coordinator.rs:122-135): one process per GPU; every rank holds the full counter
+    array, owns a destination-row range of the CSR, and runs `run_sharded_loop`."""
 
     @staticmethod
-    def calculate(graph, device, rank, world_size, max_iters=0, group=None):
-        import torch
-        import torch.distributed as dist
+    def calculate(graph, device, rank, world_size, max_iters=0, group=None, p2p=False):
         dg = DeviceGraph(graph, device=device, rank=rank, world_size=world_size)
         try:
-            ranges = dg.row_ranges()
-            stats = []
-            t = 0
-            dev = torch.device("cuda", device)
-            while True:
-                st = dg.step()
-                regs_ptr, regs_bytes, fr_ptr, fr_bytes = dg.exchange_ptrs()
-                regs = _as_tensor(regs_ptr, regs_bytes, torch.uint8, dev)
-                fr = _as_tensor(fr_ptr, fr_bytes, torch.int32, dev)
-                torch.cuda.current_stream(dev).synchronize()
-                cnt = torch.tensor([st["n_changed"]], dtype=torch.int64, device=dev)
-                works = []
-                for r in range(world_size):
-                    b, e = ranges[r], ranges[r + 1]
-                    if e > b:
-                        works.append(dist.broadcast(regs[b * 64:e * 64], src=_global_rank(group, r), group=group, async_op=True))
-                        wb, we = b // 32, (e + 31) // 32
-                        works.append(dist.broadcast(fr[wb:we], src=_global_rank(group, r), group=group, async_op=True))
-                works.append(dist.all_reduce(cnt, group=group, async_op=True))
-                for w in works:
-                    w.wait()
-                torch.cuda.current_stream(dev).synchronize()
-                total = int(cnt.item())
-                dg.exchange_done(total)
-                st["n_changed_global"] = total
-                stats.append(st)
-                t += 1
-                if total == 0 or (max_iters and t >= max_iters):
-                    break
+            if p2p and world_size > 1:
+                dg.enable_p2p(group)
+            t, stats = run_sharded_loop(dg, world_size, group, max_iters)
             lo, hi, c = dg.result()
             info = dg.info()
             return HarmonicCentrality(lo, hi, c, info["n_nodes"], t, stats, info)

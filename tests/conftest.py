@@ -21,6 +21,14 @@ def _has_gpu():
 
 
 def pytest_collection_modifyitems(config, items):
+    # a wedged kernel must not eat the GPU budget: every GPU test gets a hard per-test timeout
+    try:
+        import pytest_timeout  # noqa: F401
+        for item in items:
+            if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                item.add_marker(pytest.mark.timeout(300))
+    except ImportError:
+        pass
     if _has_gpu():
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")

@@ -1,0 +1,54 @@
+"""Two-GPU parity of the sharded HyperBall path (NCCL): every rank owns a destination-row range, results
+concatenated over ranks must equal the single-process oracle bit for bit.  Skipped with fewer than 2 GPUs."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, q, p2p):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from stract_b200 import synth
+        from stract_b200.webgraph import ShardedHarmonicCentrality, Webgraph
+        d = synth.rmat_graph(30_000, 400_000, seed=42)
+        g = Webgraph.from_arrays(d["from_lo"], d["from_hi"], d["to_lo"], d["to_hi"], d["rel_flags"])
+        r = ShardedHarmonicCentrality.calculate(g, rank, rank, world, p2p=p2p)
+        q.put((rank, r.ids_lo, r.ids_hi, r.values, r.iterations, r.info["row_begin"], r.info["row_end"]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("p2p", [False, True])
+def test_two_gpu_sharded_matches_oracle(p2p):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from oracle import hyperball_faithful
+    from stract_b200 import synth
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, p2p)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=600) for _ in range(2)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+    d = synth.rmat_graph(30_000, 400_000, seed=42)
+    ref = hyperball_faithful(d["from_lo"], d["from_hi"], d["to_lo"], d["to_hi"], d["rel_flags"])
+    assert res[0][4] == res[1][4] == ref["iters"]
+    lo = np.concatenate([r[1] for r in res]); hi = np.concatenate([r[2] for r in res]); c = np.concatenate([r[3] for r in res])
+    key = hi.astype(object) * (1 << 64) + lo.astype(object)
+    order = np.argsort(key)
+    assert np.array_equal(lo[order], ref["ids_lo"]) and np.array_equal(hi[order], ref["ids_hi"])
+    assert np.array_equal(c[order], ref["centrality"])
