@@ -233,6 +233,9 @@ __device__ __forceinline__ uint32_t lower_bound128(const uint32_t* a, uint32_t x
   uint32_t start = 0;
 #pragma unroll
   for (uint32_t len = 64; len >= 1; len >>= 1) if (a[start + len - 1] < x) start += len;
+  // the 7 halving steps count at most 127 smaller elements (the reference may assume target <= last element,
+  // we may not): one more probe makes the result 128 when every element is smaller
+  if (a[start] < x) start++;
   return start;
 }
 
