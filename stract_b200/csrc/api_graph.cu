@@ -114,6 +114,8 @@ int sb200_hyperball_run(sb200_graph* g, uint32_t max_iters, uint32_t* iters_done
   SB_CUDA(cudaEventRecord(g->ev_run0, g->stream));
   // calculate_centrality loop, harmonic.rs:237-280: stop after the first iteration without changes
   while (g->has_changes && (max_iters == 0 || g->t < max_iters)) {
+    // registers only grow and are bounded, so the loop always ends; the cap only guards against a broken build
+    if (g->t >= 100000) SB_FAIL(SB200_ESTATE, "HyperBall did not converge within 100000 iterations");
     sb200_iter_stats st;
     SB_TRY(hb_step(g, &st));
     if (per_iter && n < cap) per_iter[n] = st;

@@ -23,7 +23,9 @@
 #include "common.cuh"
 #include "../../include/stract_b200_bm25.h"
 
+#include <cub/cub.cuh>
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 namespace sb200 {
@@ -50,10 +52,15 @@ struct sb200_segment {
   sb200::DevBuf<uint16_t> b_bits;
   std::vector<uint32_t> h_df;  // host copy (query planning: Intersection sorts by size_hint)
   // per-batch scratch (grown on demand)
-  sb200::DevBuf<uint32_t> q_terms, q_nterms, o_docs, o_n;
+  sb200::DevBuf<uint32_t> q_terms, q_nterms, o_docs, o_n, q_orig;
   sb200::DevBuf<float> q_weights, q_cache, o_scores;
   sb200::DevBuf<double> o_totals, q_coeffs;
   sb200::DevBuf<unsigned long long> counters;
+  // 16-byte aligned copy of every term's block region (blocks are multiples of 16 bytes) for LDG.128 unpacking
+  sb200::DevBuf<uint4> a_post;
+  sb200::DevBuf<uint64_t> t_aoff;           // per term, in uint4 units
+  sb200::DevBuf<uint64_t> g_khi;            // per-query candidate buffers of the warp kernel
+  sb200::DevBuf<uint32_t> g_klo;
 };
 
 namespace sb200 {
@@ -228,6 +235,29 @@ __device__ void decode_next(const SegView& S, Smem& M, int s) {
   __syncthreads();
 }
 
+// advance term slot s to the first full block (>= its cursor) whose last doc is >= L; all threads call it
+__device__ void dir_skip(const SegView& S, Smem& M, int s, uint32_t L) {
+  __syncthreads();
+  const TermState& t = M.st[s];
+  const uint32_t first = t.first, nfull = t.nfull, tid = threadIdx.x;
+  uint32_t j = nfull;
+  for (uint32_t base = t.cur_blk; base < nfull; base += NT) {
+    const uint32_t idx = base + tid;
+    const bool pred = idx < nfull && __ldg(S.b_last + first + idx) >= L;
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if ((tid & 31) == 0) M.misc[tid >> 5] = m ? base + (tid & ~31u) + (uint32_t)__ffs(m) - 1u : 0xFFFFFFFFu;
+    __syncthreads();
+    const uint32_t best = min(min(M.misc[0], M.misc[1]), min(M.misc[2], M.misc[3]));
+    __syncthreads();
+    if (best != 0xFFFFFFFFu) { j = best; break; }
+  }
+  if (tid == 0) {
+    TermState& w = M.st[s];
+    if (j > w.cur_blk) { w.cur_blk = j; w.prev_last = S.b_last[first + j - 1]; }
+  }
+  __syncthreads();
+}
+
 // first index in the sorted 128-entry block with value >= x (branchless, block_search.rs:23-34)
 __device__ __forceinline__ uint32_t lower_bound128(const uint32_t* a, uint32_t x) {
   uint32_t start = 0;
@@ -262,6 +292,7 @@ __device__ void sort_keys_desc(Smem& M, uint32_t cap) {
 struct Params {
   SegView S;
   const uint32_t* q_terms; const uint32_t* q_nterms; const float* q_weights; const float* cache;
+  const uint32_t* q_orig;   // slot -> caller's query index (slots are ordered by decreasing work)
   uint32_t n_terms_max, k, cap;
   // path B
   float k1p1; double coeff_text; const double* sig; uint32_t n_cols; const double* coeffs; uint32_t max_docs;
@@ -288,6 +319,7 @@ __global__ void __launch_bounds__(NT) k_topk(const Params P) {
   }
   const SegView& S = P.S;
   const uint32_t q = blockIdx.x;
+  const uint32_t oq = P.q_orig ? P.q_orig[q] : q;
   const uint32_t T = P.q_nterms[q];
   const uint32_t tid = threadIdx.x;
   uint32_t* s_count = M.misc + 8;     // entries in the key buffer
@@ -319,60 +351,37 @@ __global__ void __launch_bounds__(NT) k_topk(const Params P) {
 
   while (!stop_all) {
     if (budget-- == 0) { if (tid == 0) atomicAdd(P.counters + 2, 1ull); break; }
-    // (1) refill exhausted blocks
+    // (1) refill exhausted blocks.  AND: a match is >= every term's head, so before decoding the next block of a
+    // term we jump over every block whose last doc is below L = max head of the other terms, using the block
+    // directory (the skip-list seek of Intersection::advance, intersection.rs:95-125 / skip.rs:243-254).
     for (uint32_t s = 0; s < T; s++) {
       const TermState& t = M.st[s];
       if (!t.done && t.pos >= t.len) {
+        if (MODE == 0 && T > 1) {
+          uint32_t L = 0;
+          for (uint32_t x = 0; x < T; x++) { const TermState& u = M.st[x]; if (x != s && !u.done && u.pos < u.len) L = max(L, M.docs[x * 128 + u.pos]); }
+          if (L > 0 && t.cur_blk < t.nfull) dir_skip(S, M, s, L);
+        }
         const bool more = (t.cur_blk < t.nfull) || (t.cur_blk == t.nfull && !t.tail_done && (t.df & 127u));
         if (more) { decode_next(S, M, s); my_blocks++; }
         else { __syncthreads(); if (tid == 0) M.st[s].done = 1; __syncthreads(); }
       }
     }
-    // (1b) AND: block-level leapfrog.  A match is >= every term's head, so with L = max head any block whose
-    // last doc is < L is dead: jump over it (and its successors) through the directory without decoding, the
-    // way Intersection::advance seeks the skip lists (intersection.rs:95-125, skip.rs:243-254).
+    // (1b) AND: blocks already decoded but entirely below L are dead, and so are the leading docs below L
     if (MODE == 0 && T > 1) {
       bool alive = true; uint32_t L = 0;
       for (uint32_t s = 0; s < T; s++) { const TermState& t = M.st[s]; if (t.done) alive = false; else L = max(L, M.docs[s * 128 + t.pos]); }
       if (alive) {
-        int victim = -1;
-        for (uint32_t s = 0; s < T; s++) if (M.st[s].last_doc < L) { victim = (int)s; break; }
-        if (victim >= 0) {
-          __syncthreads();
-          const TermState& t = M.st[victim];
-          const uint32_t first = t.first, nfull = t.nfull;
-          uint32_t j = nfull;
-          for (uint32_t base = t.cur_blk; base < nfull; base += NT) {
-            const uint32_t idx = base + tid;
-            const bool pred = idx < nfull && __ldg(S.b_last + first + idx) >= L;
-            const unsigned m = __ballot_sync(0xffffffffu, pred);
-            if ((tid & 31) == 0) M.misc[tid >> 5] = m ? base + (tid & ~31u) + (uint32_t)__ffs(m) - 1u : 0xFFFFFFFFu;
-            __syncthreads();
-            const uint32_t best = min(min(M.misc[0], M.misc[1]), min(M.misc[2], M.misc[3]));
-            __syncthreads();
-            if (best != 0xFFFFFFFFu) { j = best; break; }
-          }
-          if (tid == 0) {
-            TermState& w = M.st[victim];
-            if (j > w.cur_blk || w.cur_blk > nfull) { w.cur_blk = max(j, w.cur_blk); }
-            w.prev_last = (w.cur_blk > 0 && w.cur_blk <= nfull) ? S.b_last[first + w.cur_blk - 1] : w.prev_last;
-            w.pos = 0; w.len = 0;
-          }
-          __syncthreads();
-          continue;  // refill decodes the target block (or marks the term exhausted)
-        }
-        // all current blocks reach L: drop their docs below L
+        bool dead = false;
+        for (uint32_t s = 0; s < T; s++) if (M.st[s].last_doc < L) dead = true;
         __syncthreads();
         if (tid < T) {
-          const uint32_t p = lower_bound128(M.docs + tid * 128, L);
-          s_rhi[tid] = (p > M.st[tid].pos) ? 1u : 0u;
-          if (p > M.st[tid].pos) M.st[tid].pos = min(p, M.st[tid].len);
+          TermState& w = M.st[tid];
+          if (w.last_doc < L) { w.pos = 0; w.len = 0; }  // refill (with directory skip) next pass
+          else { const uint32_t p = lower_bound128(M.docs + tid * 128, L); if (p > w.pos) w.pos = min(p, w.len); }
         }
         __syncthreads();
-        bool moved = false;
-        for (uint32_t s = 0; s < T; s++) moved |= (s_rhi[s] != 0);
-        __syncthreads();
-        if (moved) continue;  // heads rose: L may have risen too
+        if (dead) continue;
       }
     }
     // (2) the round's bound
@@ -523,11 +532,11 @@ __global__ void __launch_bounds__(NT) k_topk(const Params P) {
   sort_keys_desc(M, P.cap);
   const uint32_t n = min(*s_count, P.k);
   for (uint32_t i = tid; i < n; i += NT) {
-    P.o_docs[(size_t)q * P.k + i] = ~M.klo[i];
-    if (MODE == 2) P.o_totals[(size_t)q * P.k + i] = unord_f64(M.khi[i]);
-    else P.o_scores[(size_t)q * P.k + i] = unord_f32((uint32_t)(M.khi[i] >> 32));
+    P.o_docs[(size_t)oq * P.k + i] = ~M.klo[i];
+    if (MODE == 2) P.o_totals[(size_t)oq * P.k + i] = unord_f64(M.khi[i]);
+    else P.o_scores[(size_t)oq * P.k + i] = unord_f32((uint32_t)(M.khi[i] >> 32));
   }
-  if (tid == 0) P.o_n[q] = n;
+  if (tid == 0) P.o_n[oq] = n;
   for (int o = 16; o; o >>= 1) { my_docs += __shfl_down_sync(0xffffffffu, my_docs, o); }
   if ((tid & 31) == 0 && my_docs) atomicAdd(P.counters + 0, my_docs);
   if (tid == 0 && my_blocks) atomicAdd(P.counters + 1, my_blocks);
@@ -560,6 +569,24 @@ static int launch_topk(const Params& P, uint32_t n_queries, cudaStream_t s) {
 template <class T>
 static int ensure(DevBuf<T>& b, size_t n) { if (b.n < n) return b.alloc(n + (n >> 2) + 16); return SB200_OK; }
 
+}  // namespace sb200
+#include "bm25_warp.cuh"
+namespace sb200 {
+
+template <int MODE>
+static int launch_topk_warp(const WParams& P, cudaStream_t s) {
+  const size_t per_warp = (size_t)P.n_terms_max * 128 * 8 + sizeof(WTerm) * P.n_terms_max + 32 * 4;
+  const size_t sm = 1024 + WQ * per_warp;
+  static size_t configured[3] = {0, 0, 0};
+  if (sm > 48 * 1024 && configured[MODE] < sm) {
+    SB_CUDA(cudaFuncSetAttribute(k_topk_warp<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    configured[MODE] = sm;
+  }
+  SB_LAUNCH(k_topk_warp<MODE>, div_up(P.n_queries, WQ), WQ * 32, sm, s, P);
+  SB_CHECK_LAUNCH();
+  return SB200_OK;
+}
+
 static int run_batch(sb200_segment* g, const sb200_bm25_batch* b, int mode, const sb200_signal_batch* sb, uint32_t* docs,
                      float* scores, double* totals, uint32_t* n_out, sb200_bm25_stats* stats) {
   cudaStream_t s = g->stream;
@@ -572,7 +599,19 @@ static int run_batch(sb200_segment* g, const sb200_bm25_batch* b, int mode, cons
   std::vector<uint32_t> terms((size_t)nq * nt), nterms(nq);
   std::vector<float> weights((size_t)nq * nt);
   unsigned long long postings = 0;
-  for (uint32_t q = 0; q < nq; q++) {
+  // longest-processing-time-first: one warp walks a whole query, so the batch finishes when its largest query
+  // does; slots are ordered by decreasing posting count and results go back to the caller's index (q_orig)
+  std::vector<uint32_t> order(nq);
+  {
+    std::vector<uint64_t> work(nq, 0);
+    for (uint32_t q = 0; q < nq; q++) {
+      order[q] = q;
+      for (uint32_t t = 0; t < nt; t++) { const uint32_t ord = b->term_ords[(size_t)q * nt + t]; if (ord != SB200_NO_TERM && ord < g->n_terms) work[q] += g->h_df[ord]; }
+    }
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t bb) { return work[a] > work[bb]; });
+  }
+  for (uint32_t slot = 0; slot < nq; slot++) {
+    const uint32_t q = order[slot];
     uint32_t idx[MAXT]; uint32_t c = 0;
     for (uint32_t t = 0; t < nt; t++) {
       const uint32_t ord = b->term_ords[(size_t)q * nt + t];
@@ -582,17 +621,18 @@ static int run_batch(sb200_segment* g, const sb200_bm25_batch* b, int mode, cons
     }
     if (mode == SB200_MODE_AND) std::stable_sort(idx, idx + c, [&](uint32_t a, uint32_t bb) { return g->h_df[b->term_ords[(size_t)q * nt + a]] < g->h_df[b->term_ords[(size_t)q * nt + bb]]; });
     for (uint32_t i = 0; i < c; i++) {
-      terms[(size_t)q * nt + i] = b->term_ords[(size_t)q * nt + idx[i]];
-      weights[(size_t)q * nt + i] = b->weights[(size_t)q * nt + idx[i]];
-      postings += g->h_df[terms[(size_t)q * nt + i]];
+      terms[(size_t)slot * nt + i] = b->term_ords[(size_t)q * nt + idx[i]];
+      weights[(size_t)slot * nt + i] = b->weights[(size_t)q * nt + idx[i]];
+      postings += g->h_df[terms[(size_t)slot * nt + i]];
     }
-    nterms[q] = c;
+    nterms[slot] = c;
   }
   SB_TRY(ensure(g->q_terms, (size_t)nq * nt)); SB_TRY(ensure(g->q_weights, (size_t)nq * nt)); SB_TRY(ensure(g->q_nterms, nq));
   SB_TRY(ensure(g->q_cache, 256)); SB_TRY(ensure(g->o_docs, (size_t)nq * k)); SB_TRY(ensure(g->o_n, nq));
   if (totals) SB_TRY(ensure(g->o_totals, (size_t)nq * k)); else SB_TRY(ensure(g->o_scores, (size_t)nq * k));
-  SB_TRY(ensure(g->counters, 4));
+  SB_TRY(ensure(g->counters, 4)); SB_TRY(ensure(g->q_orig, nq));
   SB_CUDA(cudaEventRecord(g->ev0, s));
+  SB_CUDA(cudaMemcpyAsync(g->q_orig.p, order.data(), (size_t)nq * 4, cudaMemcpyHostToDevice, s));
   SB_CUDA(cudaMemcpyAsync(g->q_terms.p, terms.data(), terms.size() * 4, cudaMemcpyHostToDevice, s));
   SB_CUDA(cudaMemcpyAsync(g->q_weights.p, weights.data(), weights.size() * 4, cudaMemcpyHostToDevice, s));
   SB_CUDA(cudaMemcpyAsync(g->q_nterms.p, nterms.data(), nterms.size() * 4, cudaMemcpyHostToDevice, s));
@@ -603,7 +643,7 @@ static int run_batch(sb200_segment* g, const sb200_bm25_batch* b, int mode, cons
   P.S.p32 = (const uint32_t*)g->postings.p; P.S.postings_len = g->postings_len; P.S.fieldnorm = g->fieldnorm.p; P.S.max_doc = g->max_doc;
   P.S.t_data_off = g->t_data_off.p; P.S.t_end_off = g->t_end_off.p; P.S.t_df = g->t_df.p; P.S.t_first = g->t_first.p;
   P.S.b_last = g->b_last.p; P.S.b_off = g->b_off.p; P.S.b_bits = g->b_bits.p; P.S.record = g->record;
-  P.q_terms = g->q_terms.p; P.q_nterms = g->q_nterms.p; P.q_weights = g->q_weights.p; P.cache = g->q_cache.p;
+  P.q_terms = g->q_terms.p; P.q_nterms = g->q_nterms.p; P.q_weights = g->q_weights.p; P.cache = g->q_cache.p; P.q_orig = g->q_orig.p;
   P.n_terms_max = nt; P.k = k;
   uint32_t cap = 1024; while (cap < k + nt * 128u) cap <<= 1;
   P.cap = cap;
@@ -619,10 +659,28 @@ static int run_batch(sb200_segment* g, const sb200_bm25_batch* b, int mode, cons
       SB_CUDA(cudaMemcpyAsync(g->q_coeffs.p, sb->coeffs, sb->signals->n_cols * 8, cudaMemcpyDefault, s));
       P.sig = sb->signals->rows.p; P.n_cols = sb->signals->n_cols; P.coeffs = g->q_coeffs.p;
     }
-    SB_TRY(launch_topk<2>(P, nq, s));
-  } else if (mode == SB200_MODE_AND) SB_TRY(launch_topk<0>(P, nq, s));
-  else if (mode == SB200_MODE_OR) SB_TRY(launch_topk<1>(P, nq, s));
-  else SB_FAIL(SB200_EINVAL, "mode %d", mode);
+  }
+  if (!sb && mode != SB200_MODE_AND && mode != SB200_MODE_OR) SB_FAIL(SB200_EINVAL, "mode %d", mode);
+  const int kmode = sb ? 2 : mode;
+  static const bool use_cta_kernel = getenv("SB200_BM25_CTA") != nullptr;  // the first-generation CTA-per-query kernel
+  if (use_cta_kernel) {
+    if (kmode == 2) SB_TRY(launch_topk<2>(P, nq, s));
+    else if (kmode == 0) SB_TRY(launch_topk<0>(P, nq, s));
+    else SB_TRY(launch_topk<1>(P, nq, s));
+  } else {
+    SB_TRY(ensure(g->g_khi, (size_t)nq * cap)); SB_TRY(ensure(g->g_klo, (size_t)nq * cap));
+    WParams W;
+    memset(&W, 0, sizeof(W));
+    W.S = P.S; W.a128 = g->a_post.p; W.t_aoff = g->t_aoff.p;
+    W.q_terms = P.q_terms; W.q_nterms = P.q_nterms; W.q_weights = P.q_weights; W.cache = P.cache; W.q_orig = P.q_orig;
+    W.n_queries = nq; W.n_terms_max = nt; W.k = k; W.cap = cap;
+    W.k1p1 = P.k1p1; W.coeff_text = P.coeff_text; W.sig = P.sig; W.n_cols = P.n_cols; W.coeffs = P.coeffs; W.max_docs = P.max_docs;
+    W.g_khi = g->g_khi.p; W.g_klo = g->g_klo.p;
+    W.o_docs = P.o_docs; W.o_scores = P.o_scores; W.o_totals = P.o_totals; W.o_n = P.o_n; W.counters = P.counters;
+    if (kmode == 2) SB_TRY(launch_topk_warp<2>(W, s));
+    else if (kmode == 0) SB_TRY(launch_topk_warp<0>(W, s));
+    else SB_TRY(launch_topk_warp<1>(W, s));
+  }
   SB_CUDA(cudaEventRecord(g->evk1, s));
   SB_CUDA(cudaMemcpyAsync(docs, g->o_docs.p, (size_t)nq * k * 4, cudaMemcpyDefault, s));
   if (totals) SB_CUDA(cudaMemcpyAsync(totals, g->o_totals.p, (size_t)nq * k * 8, cudaMemcpyDefault, s));
@@ -699,9 +757,32 @@ int sb200_segment_create(const uint8_t* postings_file, uint64_t postings_len, co
     }
     int h_err = 0;
     SB_CUDA(cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    SB_CUDA(cudaEventRecord(g->ev1, s));
     SB_CUDA(cudaStreamSynchronize(s));
     if (h_err) SB_FAIL(SB200_EFORMAT, "malformed postings (code %d): term range outside the file, skip length != blocks x %d, or bit width > 32", h_err, g->stride);
+    // aligned copy of the block regions: per-term size (uint4 units) -> exclusive scan -> realigning copy
+    SB_TRY(g->t_aoff.alloc(n_terms + 1));
+    uint64_t total_units = 0;
+    if (n_terms) {
+      DevBuf<uint64_t> units; SB_TRY(units.alloc(n_terms + 1));
+      SB_CUDA(cudaMemsetAsync(units.p + n_terms, 0, 8, s));
+      SB_LAUNCH(k_block_units, div_up(n_terms, 256), 256, 0, s, g->t_first.p, g->t_df.p, g->b_off.p, n_terms, units.p);
+      SB_CHECK_LAUNCH();
+      size_t need = 0;
+      SB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, units.p, g->t_aoff.p, (int64_t)(n_terms + 1), s));
+      DevBuf<uint8_t> tmp; SB_TRY(tmp.alloc(need + 256));
+      SB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, need, units.p, g->t_aoff.p, (int64_t)(n_terms + 1), s));
+      g_launches.fetch_add(2, std::memory_order_relaxed);
+      SB_CUDA(cudaMemcpyAsync(&total_units, g->t_aoff.p + n_terms, 8, cudaMemcpyDeviceToHost, s));
+      SB_CUDA(cudaStreamSynchronize(s));
+    }
+    SB_TRY(g->a_post.alloc(total_units + 4));
+    if (n_terms && total_units) {
+      SB_LAUNCH(k_align_blocks, div_up((uint64_t)n_terms * 32, 256), 256, 0, s, (const uint32_t*)g->postings.p, g->t_data_off.p,
+                g->t_first.p, g->t_df.p, g->b_off.p, g->t_aoff.p, n_terms, (uint32_t*)g->a_post.p);
+      SB_CHECK_LAUNCH();
+    }
+    SB_CUDA(cudaEventRecord(g->ev1, s));
+    SB_CUDA(cudaStreamSynchronize(s));
     float ms = 0; cudaEventElapsedTime(&ms, g->ev0, g->ev1); g->stage_ms = ms;
     return SB200_OK;
   };

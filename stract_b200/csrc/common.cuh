@@ -92,8 +92,22 @@ bool is_device_ptr(const void* p);
 static inline unsigned div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
 
 // ---- device helpers --------------------------------------------------------------------------
+// Byte-wise unsigned max of 4 packed bytes, valid when every byte is < 128 -- which holds for HyperLogLog<64>
+// registers (rho <= 65, hyperloglog.rs:4385-4396).  sm_100a has no SIMD byte max (`__vmaxu4` is emulated with
+// ~10 LOP3/SHF/PRMT/IADD; ncu showed the pull kernels issue-bound on exactly that), so use 3 instructions:
+//   d = a + 0x80808080 - b   no carry/borrow crosses a byte (a_i + 0x80 <= 0xFF and >= 0x80 > b_i); MSB_i = (a_i >= b_i)
+//   m = PRMT sign-replicate  0xFF where a_i >= b_i, else 0x00
+//   r = (a & m) | (b & ~m)   one LOP3
+__device__ __forceinline__ uint32_t bmax4_7bit(uint32_t a, uint32_t b) {
+  const uint32_t d = a + 0x80808080u - b;
+  uint32_t m;
+  // generic-mode PRMT: a selector nibble with its msb set replicates the SIGN of the selected byte over the byte
+  // (the `__byte_perm` intrinsic masks that bit off, hence the inline PTX)
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m) : "r"(d), "r"(0u), "r"(0xba98u));
+  return (a & m) | (b & ~m);
+}
 __device__ __forceinline__ uint4 vmax_u8x16(uint4 a, uint4 b) {
-  return make_uint4(__vmaxu4(a.x, b.x), __vmaxu4(a.y, b.y), __vmaxu4(a.z, b.z), __vmaxu4(a.w, b.w));
+  return make_uint4(bmax4_7bit(a.x, b.x), bmax4_7bit(a.y, b.y), bmax4_7bit(a.z, b.z), bmax4_7bit(a.w, b.w));
 }
 __device__ __forceinline__ bool ne_u4(uint4 a, uint4 b) {
   return ((a.x ^ b.x) | (a.y ^ b.y) | (a.z ^ b.z) | (a.w ^ b.w)) != 0u;

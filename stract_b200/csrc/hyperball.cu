@@ -177,7 +177,7 @@ __device__ __forceinline__ bool bm_test(const uint32_t* __restrict__ bm, uint32_
 
 // ---- pull, short rows: 4 lanes per destination row ----------------------------------------------------
 template <bool FRONTIER>
-__global__ void __launch_bounds__(256) k_pull_quad(uint64_t row_begin, uint64_t row_end,
+__global__ void __launch_bounds__(256, 7) k_pull_quad(uint64_t row_begin, uint64_t row_end,
     const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col, uint32_t col_base,
     const uint4* __restrict__ oldr, uint4* __restrict__ newr,
     const uint32_t* __restrict__ bm_prev, uint32_t* __restrict__ bm_cur, const PeerOut peers) {
@@ -218,7 +218,9 @@ __global__ void __launch_bounds__(256) k_pull_quad(uint64_t row_begin, uint64_t 
 
 // ---- pull, long rows: one warp per <=CHUNK_EDGES work item ---------------------------------------------
 template <bool FRONTIER>
-__global__ void __launch_bounds__(256) k_pull_warp(uint64_t n_items, uint64_t first_multi_free_item,
+// 8 CTAs/SM (<= 32 registers): at full scale the gathers are DRAM-latency bound and the kernel's speed tracks the
+// number of resident warps (36 registers = 7 CTAs measured 11 % slower than 32 registers = 8 CTAs)
+__global__ void __launch_bounds__(256, 8) k_pull_warp(uint64_t n_items, uint64_t first_multi_free_item,
     const uint32_t* __restrict__ item_row, const uint32_t* __restrict__ item_start, uint32_t warp_row_begin,
     const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col, uint32_t col_base,
     const uint4* __restrict__ oldr, uint4* __restrict__ newr, uint4* __restrict__ partial,
@@ -232,22 +234,21 @@ __global__ void __launch_bounds__(256) k_pull_warp(uint64_t n_items, uint64_t fi
   const uint32_t e0 = rs + chunk * (uint32_t)CHUNK_EDGES;
   const uint32_t e1 = min(e0 + (uint32_t)CHUNK_EDGES, re);
   uint4 acc = make_uint4(0, 0, 0, 0);
-  const uint32_t NONE = 0xFFFFFFFFu;
-  uint32_t nxt = (e0 + lane < e1) ? ld_stream_u32(col + e0 + lane) : NONE;
+  // out-of-range lanes and (FRONTIER) unchanged sources are redirected to the row itself: merging one's own row
+  // is a no-op under max and hits L1, so the gather loop is branch-free
+  uint32_t nxt = (e0 + lane < e1) ? ld_stream_u32(col + e0 + lane) : row;
   for (uint32_t base = e0; base < e1; base += 32) {
     uint32_t mine = nxt;
-    nxt = (base + 32 + lane < e1) ? ld_stream_u32(col + base + 32 + lane) : NONE;
-    if (FRONTIER && mine != NONE && !bm_test(bm_prev, mine)) mine = NONE;
+    nxt = (base + 32 + lane < e1) ? ld_stream_u32(col + base + 32 + lane) : row;
+    if (FRONTIER) mine = bm_test(bm_prev, mine) ? mine : row;
     const uint32_t i0 = __shfl_sync(0xffffffffu, mine, q);
     const uint32_t i1 = __shfl_sync(0xffffffffu, mine, q + 8);
     const uint32_t i2 = __shfl_sync(0xffffffffu, mine, q + 16);
     const uint32_t i3 = __shfl_sync(0xffffffffu, mine, q + 24);
-    const uint4 zero = make_uint4(0, 0, 0, 0);
-    uint4 v0 = zero, v1 = zero, v2 = zero, v3 = zero;
-    if (i0 != NONE) v0 = oldr[(uint64_t)i0 * 4 + sub];
-    if (i1 != NONE) v1 = oldr[(uint64_t)i1 * 4 + sub];
-    if (i2 != NONE) v2 = oldr[(uint64_t)i2 * 4 + sub];
-    if (i3 != NONE) v3 = oldr[(uint64_t)i3 * 4 + sub];
+    const uint4 v0 = oldr[(uint64_t)i0 * 4 + sub];
+    const uint4 v1 = oldr[(uint64_t)i1 * 4 + sub];
+    const uint4 v2 = oldr[(uint64_t)i2 * 4 + sub];
+    const uint4 v3 = oldr[(uint64_t)i3 * 4 + sub];
     acc = vmax_u8x16(vmax_u8x16(acc, v0), vmax_u8x16(vmax_u8x16(v1, v2), v3));
   }
 #pragma unroll
@@ -332,11 +333,11 @@ __global__ void __launch_bounds__(256) k_push(const uint32_t* __restrict__ list,
       const uint32_t mine = old32[(uint64_t)u * 16 + l];
       uint32_t* addr = new32 + (uint64_t)v * 16 + l;
       uint32_t cur = *addr;
-      uint32_t m = __vmaxu4(cur, mine);
+      uint32_t m = bmax4_7bit(cur, mine);
       while (m != cur) {
         const uint32_t prev = atomicCAS(addr, cur, m);
         if (prev == cur) { changed = true; break; }
-        cur = prev; m = __vmaxu4(cur, mine);
+        cur = prev; m = bmax4_7bit(cur, mine);
       }
     }
     const unsigned ball = __ballot_sync(0xffffffffu, changed);
