@@ -302,8 +302,15 @@ def main():
         nl = torch.tensor([kernel_launch_count() - launches_t0], device=dev, dtype=torch.int64)
         dist.all_reduce(nl)
         value = E * tot_iters / (ms_total * 1e-3)
+        # one extra untimed run for the per-rank, per-iteration device times (load balance evidence)
+        dg.reset()
+        _, st_last = run_sharded_loop(dg, world)
+        mine = {"rank": rank, "rows": [info["row_begin"], info["row_end"]], "edges_local": info["n_edges_local"],
+                "iter_ms": [round(s["ms"], 3) for s in st_last], "modes": [s["mode"] for s in st_last]}
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
         result.update(value=value, ms_per_step=ms_total / args.steps, iters=tot_iters // args.steps, E=E, info=info,
-                      clocks=clocks, roofline=None, launches=int(nl.item()), kernels=[], per_iter=[])
+                      clocks=clocks, roofline=None, launches=int(nl.item()), kernels=[], per_iter=allr)
         dg.close()
 
     # ---- e2e: the C-ABI call sequence from HOST buffers (rank 0 only drives it at N=1) ----------

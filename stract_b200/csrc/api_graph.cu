@@ -103,7 +103,7 @@ int sb200_hyperball_set_policy(sb200_graph* g, double dense_frac, double push_di
   return SB200_OK;
 }
 
-int sb200_hyperball_reset(sb200_graph* g) { SB_ENTER(g); return hb_reset(g); }
+int sb200_hyperball_reset(sb200_graph* g) { SB_ENTER(g); g->reuse++; return hb_reset(g); }
 
 int sb200_hyperball_step(sb200_graph* g, sb200_iter_stats* stats) { SB_ENTER(g); return hb_step(g, stats); }
 

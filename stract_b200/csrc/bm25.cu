@@ -30,6 +30,7 @@
 
 namespace sb200 {
 uint32_t fieldnorm_value(uint8_t id);
+struct MergeJob { uint32_t first_slot, n_slots, out_slot, _pad; };
 }
 
 struct sb200_signals {
@@ -61,6 +62,8 @@ struct sb200_segment {
   sb200::DevBuf<uint64_t> t_aoff;           // per term, in uint4 units
   sb200::DevBuf<uint64_t> g_khi;            // per-query candidate buffers of the warp kernel
   sb200::DevBuf<uint32_t> g_klo;
+  sb200::DevBuf<uint32_t> q_items;          // item -> (query slot, lo, hi, output slot), SoA
+  sb200::DevBuf<sb200::MergeJob> q_jobs;
 };
 
 namespace sb200 {
@@ -582,7 +585,7 @@ static int launch_topk_warp(const WParams& P, cudaStream_t s) {
     SB_CUDA(cudaFuncSetAttribute(k_topk_warp<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     configured[MODE] = sm;
   }
-  SB_LAUNCH(k_topk_warp<MODE>, div_up(P.n_queries, WQ), WQ * 32, sm, s, P);
+  SB_LAUNCH(k_topk_warp<MODE>, div_up(P.n_items, WQ), WQ * 32, sm, s, P);
   SB_CHECK_LAUNCH();
   return SB200_OK;
 }
@@ -627,12 +630,47 @@ static int run_batch(sb200_segment* g, const sb200_bm25_batch* b, int mode, cons
     }
     nterms[slot] = c;
   }
+  // work items: queries much larger than the average are cut into doc ranges (<= 16, W*k <= 16384 for the merge)
+  std::vector<uint32_t> it_q, it_lo, it_hi, it_out;
+  std::vector<MergeJob> jobs;
+  uint32_t extra = 0, capm = 0;
+  {
+    const bool can_split = !(sb && sb->max_docs) && getenv("SB200_BM25_CTA") == nullptr && getenv("SB200_BM25_NOSPLIT") == nullptr;
+    const uint64_t target = std::max<uint64_t>(32768, postings / std::max<uint32_t>(nq, 1));
+    const uint32_t wmax = std::max<uint32_t>(1, std::min<uint32_t>(16, 16384 / k));
+    it_q.reserve(nq + 64); it_lo.reserve(nq + 64); it_hi.reserve(nq + 64); it_out.reserve(nq + 64);
+    for (uint32_t slot = 0; slot < nq; slot++) {
+      uint64_t work = 0;
+      for (uint32_t i = 0; i < nterms[slot]; i++) work += g->h_df[terms[(size_t)slot * nt + i]];
+      uint32_t W = can_split ? (uint32_t)std::min<uint64_t>(wmax, (work + target - 1) / target) : 1;
+      if (W < 1) W = 1;
+      if (W == 1) { it_q.push_back(slot); it_lo.push_back(0); it_hi.push_back(0xFFFFFFFFu); it_out.push_back(order[slot]); continue; }
+      MergeJob j; j.first_slot = nq + extra; j.n_slots = W; j.out_slot = order[slot]; j._pad = 0;
+      jobs.push_back(j);
+      for (uint32_t c = 0; c < W; c++) {
+        it_q.push_back(slot);
+        it_lo.push_back((uint32_t)((uint64_t)g->max_doc * c / W));
+        it_hi.push_back(c + 1 == W ? 0xFFFFFFFFu : (uint32_t)((uint64_t)g->max_doc * (c + 1) / W));
+        it_out.push_back(nq + extra + c);
+      }
+      extra += W;
+    }
+    if (!jobs.empty()) { capm = 1024; while (capm < wmax * k) capm <<= 1; }
+  }
+  const uint32_t n_items = (uint32_t)it_q.size();
+  const size_t n_slots_out = (size_t)nq + extra;
   SB_TRY(ensure(g->q_terms, (size_t)nq * nt)); SB_TRY(ensure(g->q_weights, (size_t)nq * nt)); SB_TRY(ensure(g->q_nterms, nq));
-  SB_TRY(ensure(g->q_cache, 256)); SB_TRY(ensure(g->o_docs, (size_t)nq * k)); SB_TRY(ensure(g->o_n, nq));
-  if (totals) SB_TRY(ensure(g->o_totals, (size_t)nq * k)); else SB_TRY(ensure(g->o_scores, (size_t)nq * k));
+  SB_TRY(ensure(g->q_cache, 256)); SB_TRY(ensure(g->o_docs, n_slots_out * k)); SB_TRY(ensure(g->o_n, n_slots_out));
+  if (totals) SB_TRY(ensure(g->o_totals, n_slots_out * k)); else SB_TRY(ensure(g->o_scores, n_slots_out * k));
   SB_TRY(ensure(g->counters, 4)); SB_TRY(ensure(g->q_orig, nq));
+  SB_TRY(ensure(g->q_items, (size_t)4 * n_items)); SB_TRY(ensure(g->q_jobs, jobs.size() + 1));
   SB_CUDA(cudaEventRecord(g->ev0, s));
   SB_CUDA(cudaMemcpyAsync(g->q_orig.p, order.data(), (size_t)nq * 4, cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(g->q_items.p, it_q.data(), (size_t)n_items * 4, cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(g->q_items.p + n_items, it_lo.data(), (size_t)n_items * 4, cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(g->q_items.p + 2 * (size_t)n_items, it_hi.data(), (size_t)n_items * 4, cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(g->q_items.p + 3 * (size_t)n_items, it_out.data(), (size_t)n_items * 4, cudaMemcpyHostToDevice, s));
+  if (!jobs.empty()) SB_CUDA(cudaMemcpyAsync(g->q_jobs.p, jobs.data(), jobs.size() * sizeof(MergeJob), cudaMemcpyHostToDevice, s));
   SB_CUDA(cudaMemcpyAsync(g->q_terms.p, terms.data(), terms.size() * 4, cudaMemcpyHostToDevice, s));
   SB_CUDA(cudaMemcpyAsync(g->q_weights.p, weights.data(), weights.size() * 4, cudaMemcpyHostToDevice, s));
   SB_CUDA(cudaMemcpyAsync(g->q_nterms.p, nterms.data(), nterms.size() * 4, cudaMemcpyHostToDevice, s));
@@ -668,18 +706,28 @@ static int run_batch(sb200_segment* g, const sb200_bm25_batch* b, int mode, cons
     else if (kmode == 0) SB_TRY(launch_topk<0>(P, nq, s));
     else SB_TRY(launch_topk<1>(P, nq, s));
   } else {
-    SB_TRY(ensure(g->g_khi, (size_t)nq * cap)); SB_TRY(ensure(g->g_klo, (size_t)nq * cap));
+    SB_TRY(ensure(g->g_khi, (size_t)n_items * cap)); SB_TRY(ensure(g->g_klo, (size_t)n_items * cap));
     WParams W;
     memset(&W, 0, sizeof(W));
     W.S = P.S; W.a128 = g->a_post.p; W.t_aoff = g->t_aoff.p;
     W.q_terms = P.q_terms; W.q_nterms = P.q_nterms; W.q_weights = P.q_weights; W.cache = P.cache; W.q_orig = P.q_orig;
     W.n_queries = nq; W.n_terms_max = nt; W.k = k; W.cap = cap;
+    W.n_items = n_items; W.item_q = g->q_items.p; W.item_lo = g->q_items.p + n_items; W.item_hi = g->q_items.p + 2 * (size_t)n_items; W.item_out = g->q_items.p + 3 * (size_t)n_items;
     W.k1p1 = P.k1p1; W.coeff_text = P.coeff_text; W.sig = P.sig; W.n_cols = P.n_cols; W.coeffs = P.coeffs; W.max_docs = P.max_docs;
     W.g_khi = g->g_khi.p; W.g_klo = g->g_klo.p;
     W.o_docs = P.o_docs; W.o_scores = P.o_scores; W.o_totals = P.o_totals; W.o_n = P.o_n; W.counters = P.counters;
     if (kmode == 2) SB_TRY(launch_topk_warp<2>(W, s));
     else if (kmode == 0) SB_TRY(launch_topk_warp<0>(W, s));
     else SB_TRY(launch_topk_warp<1>(W, s));
+    if (!jobs.empty()) {
+      const size_t msm = (size_t)capm * 12;
+      static size_t mconf[3] = {0, 0, 0};
+      if (kmode == 2) { if (msm > 48 * 1024 && mconf[2] < msm) { SB_CUDA(cudaFuncSetAttribute(k_merge_topk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm)); mconf[2] = msm; }
+                        SB_LAUNCH(k_merge_topk<2>, (unsigned)jobs.size(), 256, msm, s, g->q_jobs.p, k, capm, P.o_docs, P.o_scores, P.o_totals, P.o_n); }
+      else { if (msm > 48 * 1024 && mconf[0] < msm) { SB_CUDA(cudaFuncSetAttribute(k_merge_topk<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm)); mconf[0] = msm; }
+             SB_LAUNCH(k_merge_topk<0>, (unsigned)jobs.size(), 256, msm, s, g->q_jobs.p, k, capm, P.o_docs, P.o_scores, P.o_totals, P.o_n); }
+      SB_CHECK_LAUNCH();
+    }
   }
   SB_CUDA(cudaEventRecord(g->evk1, s));
   SB_CUDA(cudaMemcpyAsync(docs, g->o_docs.p, (size_t)nq * k * 4, cudaMemcpyDefault, s));

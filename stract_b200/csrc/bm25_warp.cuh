@@ -36,6 +36,8 @@ struct WParams {
   const uint32_t* q_terms; const uint32_t* q_nterms; const float* q_weights; const float* cache;
   const uint32_t* q_orig;   // slot -> caller's query index (slots are ordered by decreasing work)
   uint32_t n_queries, n_terms_max, k, cap;
+  // work items: (query slot, doc range, output slot); null item_q = one item per query over the whole doc space
+  uint32_t n_items; const uint32_t* item_q; const uint32_t* item_lo; const uint32_t* item_hi; const uint32_t* item_out;
   float k1p1; double coeff_text; const double* sig; uint32_t n_cols; const double* coeffs; uint32_t max_docs;
   uint64_t* g_khi; uint32_t* g_klo;   // [n_queries][cap] candidate buffers
   uint32_t* o_docs; float* o_scores; double* o_totals; uint32_t* o_n; unsigned long long* counters;
@@ -155,6 +157,16 @@ __device__ void w_sort_keys_desc(uint64_t* khi, uint32_t* klo, uint32_t cap, uin
   __syncwarp();
 }
 
+// sorts the first `count` candidates: only the next power of two is touched (zero keys pad it), the buffer is
+// never initialised as a whole -- most AND queries hold a few dozen candidates in a 2048-entry buffer
+__device__ __forceinline__ void w_sort_prefix_desc(uint64_t* khi, uint32_t* klo, uint32_t count, uint32_t cap, uint32_t lane) {
+  uint32_t n2 = 2; while (n2 < count) n2 <<= 1;
+  if (n2 > cap) n2 = cap;
+  __syncwarp();
+  for (uint32_t i = count + lane; i < n2; i += 32) { khi[i] = 0; klo[i] = 0; }
+  w_sort_keys_desc(khi, klo, n2, lane);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(WQ * 32) k_topk_warp(const WParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -173,13 +185,16 @@ __global__ void __launch_bounds__(WQ * 32) k_topk_warp(const WParams P) {
   uint32_t* s_rhi = misc + 14;     // [MAXT]
   for (uint32_t i = threadIdx.x; i < 256; i += WQ * 32) cache[i] = P.cache[i];
   __syncthreads();  // the only block barrier: the shared norm cache
-  const uint32_t q = blockIdx.x * WQ + warp;
-  if (q >= P.n_queries) return;
+  // one warp = one work item = (query slot, doc range [lo, hi)); large queries are cut into several items so the
+  // batch is not bounded by its largest query, their partial top-k lists are merged by k_merge_topk
+  const uint32_t item = blockIdx.x * WQ + warp;
+  if (item >= P.n_items) return;
   const SegView& S = P.S;
-  const uint32_t oq = P.q_orig ? P.q_orig[q] : q;
+  const uint32_t q = P.item_q ? P.item_q[item] : item;
+  const uint32_t lo_doc = P.item_q ? P.item_lo[item] : 0u, hi_doc = P.item_q ? P.item_hi[item] : 0xFFFFFFFFu;
+  const uint32_t oq = P.item_q ? P.item_out[item] : (P.q_orig ? P.q_orig[q] : q);   // output slot
   const uint32_t T = P.q_nterms[q];
-  uint64_t* khi = P.g_khi + (size_t)q * P.cap; uint32_t* klo = P.g_klo + (size_t)q * P.cap;
-  for (uint32_t i = lane; i < P.cap; i += 32) { khi[i] = 0; klo[i] = 0; }
+  uint64_t* khi = P.g_khi + (size_t)item * P.cap; uint32_t* klo = P.g_klo + (size_t)item * P.cap;
   if (lane < TM) {
     WTerm& t = st[lane];
     t.done = 1; t.len = 0; t.pos = 0; t.df = 0; t.nfull = 0; t.cur_blk = 0; t.tail_done = 0; t.last_doc = 0; t.prev_last = 0;
@@ -199,6 +214,9 @@ __global__ void __launch_bounds__(WQ * 32) k_topk_warp(const WParams P) {
   unsigned long long budget = 64;
   for (uint32_t s = 0; s < T; s++) budget += 4ull * (st[s].nfull + 2);
   bool watchdog = false;
+  if (lo_doc > 0)  // start every cursor at the first block that can hold a doc >= lo
+    for (uint32_t s = 0; s < T; s++) if (!st[s].done && st[s].nfull) w_dir_skip(P, st, s, lo_doc, lane);
+  const bool ranged = lo_doc > 0 || hi_doc != 0xFFFFFFFFu;
 
   while (T > 0) {
     if (budget-- == 0) { watchdog = true; break; }
@@ -215,6 +233,22 @@ __global__ void __launch_bounds__(WQ * 32) k_topk_warp(const WParams P) {
         if (more) { w_decode_next(P, st, docs, tfs, s, lane); my_blocks++; }
         else { __syncwarp(); if (lane == 0) st[s].done = 1; __syncwarp(); }
       }
+    }
+    // (1a) clamp to this item's doc range: drop docs below lo, retire a term once its head reaches hi
+    if (ranged) {
+      __syncwarp();
+      if (lane < T) {
+        WTerm& w = st[lane];
+        if (!w.done && w.pos < w.len) {
+          const uint32_t p = lower_bound128(docs + lane * 128, lo_doc);
+          if (p > w.pos) w.pos = min(p, w.len);
+          if (w.pos < w.len && docs[lane * 128 + w.pos] >= hi_doc) w.done = 1;
+        }
+      }
+      __syncwarp();
+      bool again = false;
+      for (uint32_t s = 0; s < T; s++) if (!st[s].done && st[s].pos >= st[s].len) again = true;
+      if (again) continue;  // a block entirely below lo: refill
     }
     // (1b) AND: decoded blocks entirely below L = max head are dead; so are leading docs below L
     if (MODE == 0 && T > 1) {
@@ -237,6 +271,7 @@ __global__ void __launch_bounds__(WQ * 32) k_topk_warp(const WParams P) {
     uint32_t bound = 0xFFFFFFFFu; bool any = false, all = true;
     for (uint32_t s = 0; s < T; s++) { const WTerm& t = st[s]; if (!t.done) { bound = min(bound, t.last_doc); any = true; } else all = false; }
     if (!any || (MODE == 0 && !all)) break;
+    if (ranged && bound >= hi_doc) bound = hi_doc - 1u;
     // (3) ranges
     if (lane < T) {
       const WTerm& t = st[lane];
@@ -253,12 +288,11 @@ __global__ void __launch_bounds__(WQ * 32) k_topk_warp(const WParams P) {
     __syncwarp();
     const uint32_t R = s_rstart[T];
     if (*s_count + R > P.cap) {
-      w_sort_keys_desc(khi, klo, P.cap, lane);
+      w_sort_prefix_desc(khi, klo, *s_count, P.cap, lane);
       const uint32_t c = min(*s_count, P.k);
       if (c == P.k) { thr_on = true; thr_hi = khi[P.k - 1]; thr_lo = klo[P.k - 1]; }
       __syncwarp();
       if (lane == 0) *s_count = c;
-      for (uint32_t i = P.k + lane; i < P.cap; i += 32) { khi[i] = 0; klo[i] = 0; }
       __syncwarp();
     }
     uint32_t cutoff = 0xFFFFFFFFu; bool last_round = false;
@@ -311,7 +345,7 @@ __global__ void __launch_bounds__(WQ * 32) k_topk_warp(const WParams P) {
           pi[u] = i; pj[u] = st[i].pos + (e - s_rstart[i]); pd[u] = docs[i * 128 + pj[u]];
           pv[u] = pd[u] <= cutoff;
           if (pv[u]) {
-            pf[u] = S.fieldnorm[pd[u]];
+            if (MODE != 0) pf[u] = S.fieldnorm[pd[u]];   // AND: almost every entry fails the membership test, fetch later
             if (sig4) { const double2* r = (const double2*)(P.sig + (size_t)pd[u] * 4); ps0[u] = __ldg(r); ps1[u] = __ldg(r + 1); }
           }
         }
@@ -319,7 +353,8 @@ __global__ void __launch_bounds__(WQ * 32) k_topk_warp(const WParams P) {
 #pragma unroll
     for (int u = 0; u < U; u++) {
       if (!pv[u]) continue;
-      const uint32_t i = pi[u], j = pj[u], d = pd[u], fid = pf[u];
+      const uint32_t i = pi[u], j = pj[u], d = pd[u];
+      uint32_t fid = pf[u];
       uint32_t tf[MAXT];
       bool ok = true;
 #pragma unroll
@@ -337,6 +372,7 @@ __global__ void __launch_bounds__(WQ * 32) k_topk_warp(const WParams P) {
       }
       if (!ok) continue;
       my_docs++;
+      if (MODE == 0) fid = S.fieldnorm[d];
       const float norm = cache[fid];
       uint64_t kh;
       if (MODE == 2) {
@@ -388,7 +424,7 @@ __global__ void __launch_bounds__(WQ * 32) k_topk_warp(const WParams P) {
   }
   __threadfence_block();
   __syncwarp();
-  w_sort_keys_desc(khi, klo, P.cap, lane);
+  w_sort_prefix_desc(khi, klo, *s_count, P.cap, lane);
   const uint32_t n = min(*s_count, P.k);
   for (uint32_t i = lane; i < n; i += 32) {
     P.o_docs[(size_t)oq * P.k + i] = ~klo[i];
@@ -402,6 +438,51 @@ __global__ void __launch_bounds__(WQ * 32) k_topk_warp(const WParams P) {
     if (my_blocks) atomicAdd(P.counters + 1, my_blocks);
     if (watchdog) atomicAdd(P.counters + 2, 1ull);
   }
+}
+
+// Merge of the partial top-k lists of a query that was cut into several doc-range items (TopCollector::merge_fruits,
+// tantivy/src/collector/top_collector.rs:109-129, is the same operation across segments): one CTA per such query,
+// all candidates (<= W*k <= 16384) sorted in shared memory with the same (score desc, doc asc) keys.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_merge_topk(const MergeJob* __restrict__ jobs, uint32_t k, uint32_t capm,
+                                                    uint32_t* o_docs, float* o_scores, double* o_totals, uint32_t* o_n) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* khi = (uint64_t*)smem_raw;
+  uint32_t* klo = (uint32_t*)(khi + capm);
+  const MergeJob job = jobs[blockIdx.x];
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t i = tid; i < capm; i += 256) { khi[i] = 0; klo[i] = 0; }
+  __syncthreads();
+  uint32_t base = 0;
+  for (uint32_t s = 0; s < job.n_slots; s++) {
+    const uint32_t slot = job.first_slot + s, n = o_n[slot];
+    for (uint32_t i = tid; i < n; i += 256) {
+      const uint32_t d = o_docs[(size_t)slot * k + i];
+      khi[base + i] = (MODE == 2) ? ord_f64(o_totals[(size_t)slot * k + i]) : ((uint64_t)ord_f32(o_scores[(size_t)slot * k + i]) << 32);
+      klo[base + i] = ~d;
+    }
+    base += n;
+  }
+  for (uint32_t size = 2; size <= capm; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (uint32_t i = tid; i < (capm >> 1); i += 256) {
+        const uint32_t lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const uint64_t ah = khi[lo], bh = khi[hi]; const uint32_t al = klo[lo], bl = klo[hi];
+        const bool swap = desc ? key_gt(bh, bl, ah, al) : key_gt(ah, al, bh, bl);
+        if (swap) { khi[lo] = bh; klo[lo] = bl; khi[hi] = ah; klo[hi] = al; }
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t n = min(base, k);
+  for (uint32_t i = tid; i < n; i += 256) {
+    o_docs[(size_t)job.out_slot * k + i] = ~klo[i];
+    if (MODE == 2) o_totals[(size_t)job.out_slot * k + i] = unord_f64(khi[i]);
+    else o_scores[(size_t)job.out_slot * k + i] = unord_f32((uint32_t)(khi[i] >> 32));
+  }
+  if (tid == 0) o_n[job.out_slot] = n;
 }
 
 // copies every term's block region into a 16-byte aligned buffer (one warp per term, byte realignment by funnel shift)

@@ -27,6 +27,7 @@ struct sb200_graph {
   uint64_t row_begin = 0, row_end = 0;  // owned rows (internal order)
   uint64_t n_pos = 0;                   // rows [0, n_pos) have in-degree > 0 (globally)
   bool has_fwd = false;
+  int reuse = 0;  // explicit resets: the source-major CSR (push branch) is only built once a handle is reused
   double stage_ms = 0;
 
   sb200::DevBuf<uint64_t> id_lo, id_hi;
@@ -88,6 +89,8 @@ namespace sb200 {
 constexpr int QUAD_MAX_DEG = 32;   // rows up to this in-degree: 4 lanes per row
 constexpr int CHUNK_EDGES = 1024;  // longer rows are cut into warp-sized work items of this many edges
 
+// source-major CSR from the resident destination-major one (lazy: see sb200_graph::reuse)
+int build_fwd_csr(sb200_graph* g);
 int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi, const uint64_t* to_lo,
                 const uint64_t* to_hi, const uint64_t* rel, uint64_t n_edges, uint64_t mask);
 }  // namespace sb200

@@ -175,15 +175,24 @@ __global__ void k_class_bounds(const uint32_t* __restrict__ deg, uint64_t n, uin
   if (d > t2 && !(nx > t2)) out[2] = i + 1;
 }
 // first row whose row_ptr >= target (rows are edge-balanced between ranks), 32-row aligned
+// Rank boundaries by estimated iteration time rather than raw edge count (measured on B200: the warp-per-item
+// kernel moves ~6.0 TB/s of algorithmic bytes, the quad-per-row kernel ~4.1 TB/s, and every row with in-edges
+// costs ~200 B of row/finalize traffic): cost(row) = 68*E_before + 34*E_quad_before + 200*min(row, n_pos).
+__device__ __forceinline__ double split_cost(const uint32_t* row_ptr, uint64_t row, uint64_t n_warp, uint64_t n_pos) {
+  const double e = (double)row_ptr[row];
+  const double eq = row > n_warp ? e - (double)row_ptr[n_warp] : 0.0;
+  return 68.0 * e + 34.0 * eq + 200.0 * (double)(row < n_pos ? row : n_pos);
+}
 __global__ void k_find_splits(const uint32_t* __restrict__ row_ptr, uint64_t n, uint64_t E, int world,
-                              unsigned long long* out) {
+                              const unsigned long long* __restrict__ cls /* [0]=n_pos [1]=n_warp */, unsigned long long* out) {
   int r = threadIdx.x;
   if (r > world) return;
   if (r == 0) { out[0] = 0; return; }
   if (r == world) { out[r] = n; return; }
-  uint64_t target = (E * (uint64_t)r) / (uint64_t)world;
+  const uint64_t n_pos = cls[0], n_warp = cls[1];
+  const double target = split_cost(row_ptr, n, n_warp, n_pos) * (double)r / (double)world;
   uint64_t lo = 0, hi = n;
-  while (lo < hi) { uint64_t mid = (lo + hi) / 2; if (row_ptr[mid] < target) lo = mid + 1; else hi = mid; }
+  while (lo < hi) { uint64_t mid = (lo + hi) / 2; if (split_cost(row_ptr, mid, n_warp, n_pos) < target) lo = mid + 1; else hi = mid; }
   out[r] = (lo / 32) * 32;
 }
 __global__ void k_row_chunks(const uint32_t* __restrict__ row_ptr, uint64_t row0, uint64_t nrows, int chunk,
@@ -211,6 +220,33 @@ int copy_in(void* dst, const void* src, size_t bytes, cudaStream_t s) {
   if (bytes == 0) return SB200_OK;
   SB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s));
   return SB200_OK;
+}
+
+// (src<<32 | dst) key of every edge of the resident destination-major CSR: short rows one thread per row, long
+// rows one warp per work item
+__global__ void k_fwd_keys_rows(uint64_t row_begin, uint64_t row_end, const uint32_t* __restrict__ row_ptr,
+                                const uint32_t* __restrict__ col, uint64_t* keys) {
+  const uint64_t row = row_begin + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (row >= row_end) return;
+  for (uint32_t e = row_ptr[row]; e < row_ptr[row + 1]; e++) keys[e] = ((uint64_t)col[e] << 32) | (uint32_t)row;
+}
+__global__ void k_fwd_keys_items(uint64_t n_items, const uint32_t* __restrict__ item_row, const uint32_t* __restrict__ item_start,
+                                 uint32_t warp_row_begin, const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col,
+                                 int chunk, uint64_t* keys) {
+  const uint64_t item = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  if (item >= n_items) return;
+  const uint32_t lane = threadIdx.x & 31, row = item_row[item];
+  const uint32_t c = (uint32_t)item - item_start[row - warp_row_begin];
+  const uint32_t e0 = row_ptr[row] + c * (uint32_t)chunk, e1 = min(e0 + (uint32_t)chunk, row_ptr[row + 1]);
+  for (uint32_t e = e0 + lane; e < e1; e += 32) keys[e] = ((uint64_t)col[e] << 32) | row;
+}
+// CSR offsets from keys sorted by their high word: ptr[r] = first index whose row >= r (no atomics)
+__global__ void k_offsets_from_sorted(const uint64_t* __restrict__ keys, uint64_t n, uint64_t n_rows, uint32_t* ptr) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i > n) return;
+  const uint64_t r = (i < n) ? (keys[i] >> 32) : n_rows;
+  const uint64_t rp = (i == 0) ? 0 : (keys[i - 1] >> 32) + 1;
+  for (uint64_t x = rp; x <= r && x <= n_rows; x++) ptr[x] = (uint32_t)i;
 }
 
 template <class K, class V>
@@ -409,7 +445,7 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
     SB_CUDA(cudaStreamSynchronize(s));
   }
   DevBuf<unsigned long long> splits; SB_TRY(splits.alloc(g->world + 1));
-  SB_LAUNCH(k_find_splits, 1, 128, 0, s, g->row_ptr.p, N, E, g->world, splits.p); SB_CHECK_LAUNCH();
+  SB_LAUNCH(k_find_splits, 1, 128, 0, s, g->row_ptr.p, N, E, g->world, ctr.p, splits.p); SB_CHECK_LAUNCH();
   std::vector<unsigned long long> h_splits(g->world + 1);
   SB_CUDA(cudaMemcpyAsync(h_ctr, ctr.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   SB_CUDA(cudaMemcpyAsync(h_splits.data(), splits.p, (g->world + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -436,8 +472,10 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
     SB_TRY(sort_keys<uint64_t>(tmp, a, c, E, 0, 32 + nb, s));
     SB_LAUNCH(k_lo32, div_up(E, TPB), TPB, 0, s, a, E, col_full.p); SB_CHECK_LAUNCH();
     pt.mark("3c remap + sort (fwd CSR)");
-    // source-major CSR (single-rank handles only: the push branch needs every out-edge)
-    if (g->world == 1) {
+    // source-major CSR (single-rank handles only: the push branch needs every out-edge).  It costs a third sort
+    // (~0.2 s at 1e9 edges) and saves ~10 ms per run, so by default it is built lazily by build_fwd_csr() the first
+    // time a REUSED handle meets a small frontier; SB200_EAGER_FWD=1 builds it here.
+    if (g->world == 1 && getenv("SB200_EAGER_FWD") != nullptr) {
       uint64_t* other = c;  // scratch half of the last sort
       SB_LAUNCH(k_remap, div_up(E, TPB), TPB, 0, s, b, E, g->inv.p, a, true); SB_CHECK_LAUNCH();
       SB_TRY(sort_keys<uint64_t>(tmp, a, other, E, 0, 32 + nb, s));
@@ -513,6 +551,35 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
   SB_CUDA(cudaStreamSynchronize(s));
   float ms = 0; cudaEventElapsedTime(&ms, g->ev0, g->ev1);
   g->stage_ms = ms;
+  return SB200_OK;
+}
+
+int build_fwd_csr(sb200_graph* g) {
+  if (g->has_fwd || g->world != 1) return SB200_OK;
+  cudaStream_t s = g->stream;
+  const uint64_t N = g->N, E = g->E_kept;
+  const int TPB = 256;
+  SB_TRY(g->fwd_ptr.alloc(N + 1));
+  if (E == 0) { SB_CUDA(cudaMemsetAsync(g->fwd_ptr.p, 0, (N + 1) * 4, s)); g->has_fwd = true; return SB200_OK; }
+  DevBuf<uint64_t> ka, kb; SB_TRY(ka.alloc(E)); SB_TRY(kb.alloc(E));
+  if (g->n_items) {
+    SB_LAUNCH(k_fwd_keys_items, div_up(g->n_items * 32, TPB), TPB, 0, s, g->n_items, g->item_row.p, g->item_start.p,
+              (uint32_t)g->warp_row_begin, g->row_ptr.p, g->col.p, CHUNK_EDGES, ka.p);
+    SB_CHECK_LAUNCH();
+  }
+  if (g->quad_row_end > g->quad_row_begin) {
+    SB_LAUNCH(k_fwd_keys_rows, div_up(g->quad_row_end - g->quad_row_begin, TPB), TPB, 0, s, g->quad_row_begin, g->quad_row_end,
+              g->row_ptr.p, g->col.p, ka.p);
+    SB_CHECK_LAUNCH();
+  }
+  uint64_t *a = ka.p, *b = kb.p;
+  SB_TRY(sort_keys<uint64_t>(g->cub_tmp, a, b, E, 0, 32 + bits_for(N), s));
+  SB_TRY(g->fwd_dst.alloc(E));
+  SB_LAUNCH(k_lo32, div_up(E, TPB), TPB, 0, s, a, E, g->fwd_dst.p); SB_CHECK_LAUNCH();
+  SB_LAUNCH(k_offsets_from_sorted, div_up(E + 1, TPB), TPB, 0, s, a, E, N, g->fwd_ptr.p); SB_CHECK_LAUNCH();
+  SB_CUDA(cudaStreamSynchronize(s));
+  g->cub_tmp.release();
+  g->has_fwd = true;
   return SB200_OK;
 }
 

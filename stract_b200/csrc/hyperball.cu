@@ -536,6 +536,19 @@ static int run_push(sb200_graph* g, const uint4* oldr, uint4* newr, const uint32
   return SB200_OK;
 }
 
+// out-edges of the nodes in a changed bitmap (needed once, right after the lazy source-major CSR build)
+__global__ void k_frontier_out_edges(const uint32_t* __restrict__ bm, uint64_t words, const uint32_t* __restrict__ fwd_ptr,
+                                     unsigned long long* counter) {
+  const uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  unsigned long long acc = 0;
+  if (w < words) {
+    uint32_t m = bm[w];
+    while (m) { const int b = __ffs(m) - 1; m &= m - 1; const uint64_t v = w * 32 + b; acc += fwd_ptr[v + 1] - fwd_ptr[v]; }
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(counter, acc);
+}
+
 int hb_step(sb200_graph* g, sb200_iter_stats* st) {
   cudaStream_t s = g->stream;
   const uint64_t N = g->N, words = (N + 31) / 32;
@@ -550,10 +563,26 @@ int hb_step(sb200_graph* g, sb200_iter_stats* st) {
   int mode;
   const double E = (double)std::max<uint64_t>(g->E_kept, 1);
   if (g->world == 1) {
-    const double fe = (double)g->frontier_edges_prev;
-    if (fe >= dense_frac * E) mode = 0;
-    else if (g->has_fwd && fe * push_div <= E) mode = 2;
-    else mode = 1;
+    // the source-major CSR is built lazily: when a reused handle (or a pinned push policy) first meets a frontier
+    // of < N/64 nodes.  A handle that computes one centrality and is dropped never pays for it.
+    if (!g->has_fwd && ((g->reuse > 0 && g->t > 0 && (double)g->n_changed_prev * 64.0 <= (double)N) || force_mode == 2)) {
+      SB_TRY(build_fwd_csr(g));
+      SB_CUDA(cudaMemsetAsync(g->counters.p + 4, 0, sizeof(unsigned long long), s));
+      SB_LAUNCH(k_frontier_out_edges, div_up(words, 256), 256, 0, s, bmp, words, g->fwd_ptr.p, g->counters.p + 4);
+      SB_CHECK_LAUNCH();
+      unsigned long long fe0 = 0;
+      SB_CUDA(cudaMemcpyAsync(&fe0, g->counters.p + 4, sizeof(fe0), cudaMemcpyDeviceToHost, s));
+      SB_CUDA(cudaStreamSynchronize(s));
+      g->frontier_edges_prev = fe0;
+    }
+    if (g->has_fwd) {
+      const double fe = (double)g->frontier_edges_prev;
+      if (fe >= dense_frac * E) mode = 0;
+      else if (fe * push_div <= E) mode = 2;
+      else mode = 1;
+    } else {
+      mode = ((double)g->n_changed_prev >= 0.75 * (double)N) ? 0 : 1;
+    }
   } else {
     mode = ((double)g->n_changed_prev >= 0.25 * (double)N) ? 0 : 1;
   }
