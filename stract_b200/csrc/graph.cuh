@@ -16,7 +16,7 @@
 
 namespace sb200 {
 constexpr int MAX_PEERS = 15;
-struct PeerOut { uint4* newr[MAX_PEERS]; uint32_t* bmc[MAX_PEERS]; int n; };
+struct PeerOut { uint4* newr[MAX_PEERS]; uint32_t* bmc[MAX_PEERS]; int n; uint32_t world, rank; };
 }
 
 struct sb200_graph {

@@ -161,6 +161,10 @@ __global__ void k_bm_fill(uint32_t* bm, uint64_t N, uint64_t words) {
 // other rank's replica of it (one writer per row, so plain 16-B stores; the changed bit goes through a
 // system-scope atomic OR).  This replaces the per-iteration all-gather: the transfer of a row overlaps the
 // gathers of the rows still being computed, and rows that did not change never cross the link.
+// sharded handles: destination rows are owned in interleaved blocks of 32 (block b -> rank b % world)
+__device__ __forceinline__ bool owned_row(const PeerOut& o, uint32_t row) {
+  return o.world <= 1u || ((row >> 5) % o.world) == o.rank;
+}
 __device__ __forceinline__ void publish_row(uint4* __restrict__ newr, uint32_t* __restrict__ bm_cur, const PeerOut& peers,
                                             uint32_t row, uint32_t sub, uint4 acc, bool write, bool changed) {
   if (write) newr[(uint64_t)row * 4 + sub] = acc;
@@ -185,9 +189,11 @@ __global__ void __launch_bounds__(256, 7) k_pull_quad(uint64_t row_begin, uint64
   const uint32_t sub = threadIdx.x & 3;
   const uint32_t lane = threadIdx.x & 31;
   uint64_t row = row_begin + (gt >> 2);
-  const bool live = row < row_end;
+  bool live = row < row_end;
   if (!live) row = row_end - 1;  // keep the warp converged; results of dead quads are discarded
-  const uint32_t e0 = row_ptr[row] - col_base, e1 = row_ptr[row + 1] - col_base;
+  live = live && owned_row(peers, (uint32_t)row);
+  if (__ballot_sync(0xffffffffu, live) == 0u) return;  // none of this warp's rows belongs to this rank
+  const uint32_t e0 = live ? row_ptr[row] - col_base : 0u, e1 = live ? row_ptr[row + 1] - col_base : 0u;
   const uint4 own = oldr[row * 4 + sub];
   uint4 acc = own;
   // lane `sub` fetches source index e+sub (one 16-B request per quad per 4 edges, prefetched one step ahead)
@@ -229,6 +235,7 @@ __global__ void __launch_bounds__(256, 8) k_pull_warp(uint64_t n_items, uint64_t
   if (item >= n_items) return;  // whole warp exits together
   const uint32_t lane = threadIdx.x & 31, sub = lane & 3, q = lane >> 2;
   const uint32_t row = item_row[item];
+  if (!owned_row(peers, row)) return;  // sharded: another rank owns this row (warp-uniform)
   const uint32_t chunk = (uint32_t)item - item_start[row - warp_row_begin];
   const uint32_t rs = row_ptr[row] - col_base, re = row_ptr[row + 1] - col_base;
   const uint32_t e0 = rs + chunk * (uint32_t)CHUNK_EDGES;
@@ -277,6 +284,7 @@ __global__ void __launch_bounds__(256) k_pull_merge(uint64_t n_rows, const uint3
   if (r >= n_rows) return;
   const uint32_t lane = threadIdx.x & 31, sub = lane & 3, q = lane >> 2;
   const uint32_t row = warp_row_begin + (uint32_t)r;
+  if (!owned_row(peers, row)) return;
   const uint32_t i0 = item_start[r], i1 = item_start[r + 1];
   uint4 acc = make_uint4(0, 0, 0, 0);
   for (uint32_t it = i0 + q; it < i1; it += 8) acc = vmax_u8x16(acc, partial[(uint64_t)it * 4 + sub]);
@@ -350,7 +358,8 @@ __global__ void __launch_bounds__(256) k_push(const uint32_t* __restrict__ list,
 __global__ void __launch_bounds__(256) k_finalize(uint64_t row_begin, uint64_t row_end,
     const uint4* __restrict__ newr, const uint32_t* __restrict__ bm_prev, const uint32_t* __restrict__ bm_cur,
     uint64_t* __restrict__ size_cache, double* __restrict__ ksum, double* __restrict__ kerr,
-    const uint32_t* __restrict__ fwd_ptr, double t_plus_1, unsigned long long* counters) {
+    const uint32_t* __restrict__ fwd_ptr, double t_plus_1, unsigned long long* counters, const uint32_t own_world,
+    const uint32_t own_rank) {
   __shared__ HllTables tab;
   __shared__ unsigned long long s_cnt[2];
   for (int i = threadIdx.x; i < (int)(sizeof(HllTables) / 8); i += blockDim.x) ((double*)&tab)[i] = ((const double*)&c_tab)[i];
@@ -358,7 +367,7 @@ __global__ void __launch_bounds__(256) k_finalize(uint64_t row_begin, uint64_t r
   __syncthreads();
   const uint64_t v = row_begin + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   unsigned long long my_changed = 0, my_out = 0;
-  if (v < row_end) {
+  if (v < row_end && (own_world <= 1 || ((v >> 5) % own_world) == own_rank)) {
     const bool bc = bm_test(bm_cur, (uint32_t)v), bp = bm_test(bm_prev, (uint32_t)v);
     if (bc || bp) {
       double s = ksum[v], e = kerr[v];
@@ -394,12 +403,14 @@ __global__ void __launch_bounds__(256) k_finalize(uint64_t row_begin, uint64_t r
 
 // ---- result / debug gathers ------------------------------------------------------------------------------
 __global__ void k_result_flags(const uint32_t* __restrict__ inv, const double* __restrict__ ksum, uint64_t N,
-                               uint64_t row_begin, uint64_t row_end, double norm, uint32_t* flag, double* val) {
+                               uint64_t row_begin, uint64_t row_end, double norm, uint32_t* flag, double* val,
+                               const uint32_t own_world, const uint32_t own_rank) {
   uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (r >= N) return;
   const uint32_t v = inv[r];
   double c = ksum[v];
-  const bool keep = (c > 0.0) && v >= row_begin && v < row_end;  // normalize_centralities harmonic.rs:178-195
+  const bool keep = (c > 0.0) && v >= row_begin && v < row_end &&  // normalize_centralities harmonic.rs:178-195
+                    (own_world <= 1 || ((v >> 5) % own_world) == own_rank);
   c = __ddiv_rn(c, norm);
   if (isinf(c) || isnan(c)) c = 0.0;
   flag[r] = keep ? 1u : 0u;
@@ -475,7 +486,7 @@ int hb_reset(sb200_graph* g) {
 template <bool FRONTIER>
 static int launch_pull(sb200_graph* g, const uint4* oldr, uint4* newr, const uint32_t* bmp, uint32_t* bmc) {
   cudaStream_t s = g->stream;
-  PeerOut po; po.n = 0;
+  PeerOut po; po.n = 0; po.world = (uint32_t)g->world; po.rank = (uint32_t)g->rank;
   if (g->p2p) { po.n = g->n_peers; for (int p = 0; p < g->n_peers; p++) { po.newr[p] = (uint4*)g->peer_regs[g->cur ^ 1][p]; po.bmc[p] = (uint32_t*)g->peer_bm[g->bcur ^ 1][p]; } }
   const int FW = FRONTIER ? sb200_graph::F_PULL_WARP_FRONT : sb200_graph::F_PULL_WARP_DENSE;
   const int FQ = FRONTIER ? sb200_graph::F_PULL_QUAD_FRONT : sb200_graph::F_PULL_QUAD_DENSE;
@@ -600,7 +611,7 @@ int hb_step(sb200_graph* g, sb200_iter_stats* st) {
     PROF_BEGIN(g, sb200_graph::F_FINALIZE);
     SB_LAUNCH(k_finalize, div_up(nrows, 256), 256, 0, s, g->row_begin, g->row_end, newr, bmp, bmc, g->size_cache.p,
               g->kahan_sum.p, g->kahan_err.p, g->has_fwd ? g->fwd_ptr.p : (const uint32_t*)nullptr, (double)(g->t + 1),
-              g->counters.p);
+              g->counters.p, (uint32_t)g->world, (uint32_t)g->rank);
     SB_CHECK_LAUNCH();
     PROF_END(g, sb200_graph::F_FINALIZE, 0.25 * (double)nrows);  // 2 bitmap bits/row; + 112 B per changed row below
   }
@@ -641,7 +652,8 @@ int hb_result(sb200_graph* g, uint64_t* id_lo, uint64_t* id_hi, double* cent, ui
   SB_TRY(flag.alloc(N + 1)); SB_TRY(pos.alloc(N + 1)); SB_TRY(val.alloc(N));
   SB_CUDA(cudaMemsetAsync(flag.p + N, 0, 4, s));
   const double norm = (double)(N - 1);
-  SB_LAUNCH(k_result_flags, div_up(N, 256), 256, 0, s, g->inv.p, g->kahan_sum.p, N, g->row_begin, g->row_end, norm, flag.p, val.p);
+  SB_LAUNCH(k_result_flags, div_up(N, 256), 256, 0, s, g->inv.p, g->kahan_sum.p, N, g->row_begin, g->row_end, norm, flag.p, val.p,
+            (uint32_t)g->world, (uint32_t)g->rank);
   SB_CHECK_LAUNCH();
   size_t need = 0;
   SB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, flag.p, pos.p, (int64_t)(N + 1), s));

@@ -323,13 +323,12 @@ def run_sharded_loop(engine, world_size, group=None, max_iters=0):
             continue
         regs, fr = engine.exchange_tensors()
         cnt = torch.tensor([st["n_changed"]], dtype=torch.int64, device=regs.device)
-        works = []
-        for r in range(world_size):
-            b, e = ranges[r], ranges[r + 1]
-            if e > b:
-                src = _global_rank(group, r)
-                works.append(dist.broadcast(regs[b * 64:e * 64], src=src, group=group, async_op=True))
-                works.append(dist.broadcast(fr[b // 32:(e + 31) // 32], src=src, group=group, async_op=True))
+        # Rows are owned in interleaved 32-row blocks, so the merge is the DHT's own operator: elementwise byte
+        # max over all replicas (`HyperLogLog64Upsert`, ampc/dht/upsert.rs:66-83; registers only grow, a non-owner's
+        # copy of a row is an older, smaller-or-equal state).  Each 32-bit bitmap word has a single owner too.
+        fr8 = fr.view(torch.uint8)
+        works = [dist.all_reduce(regs, op=dist.ReduceOp.MAX, group=group, async_op=True),
+                 dist.all_reduce(fr8, op=dist.ReduceOp.MAX, group=group, async_op=True)]
         works.append(dist.all_reduce(cnt, group=group, async_op=True))
         for w in works:
             w.wait()

@@ -1,5 +1,5 @@
-"""world_size-2 `gloo` test of the multi-rank host logic (stract_b200.webgraph.run_sharded_loop): row-range
-ownership, per-owner broadcast of register rows and changed-bitmap words, changed-count all-reduce and the
+"""world_size-2 `gloo` test of the multi-rank host logic (stract_b200.webgraph.run_sharded_loop): interleaved
+row ownership, byte-max all-reduce of the register replicas and changed bitmaps, changed-count all-reduce and the
 termination rule.  The per-rank compute engine is a numpy stand-in (tests only); on the GPU box the same
 loop drives the CUDA DeviceGraph (tests/test_sharded_gpu.py)."""
 import os
@@ -38,10 +38,9 @@ class NumpyShard:
                 continue
             edges.append((a, b_))
         self.edges = np.array(edges, np.int64).reshape(-1, 2)
-        # 32-aligned row ranges
-        cuts = [0] + [min(n, ((n * (r + 1) // world) // 32) * 32) for r in range(world - 1)] + [n]
-        self.ranges = cuts
-        self.b, self.e = cuts[rank], cuts[rank + 1]
+        # interleaved ownership: 32-row block b belongs to rank b % world (as in the CUDA library)
+        self.ranges = [0] * world + [n]
+        self.own = ((np.arange(n) >> 5) % world) == rank
         self.regs = torch.from_numpy(self.orc.registers().reshape(-1).copy())
         self.front = torch.zeros((n + 31) // 32, dtype=torch.int32)
         self.changed_prev = np.ones(n, bool)
@@ -52,16 +51,16 @@ class NumpyShard:
     def step(self):
         old = self.regs.numpy().reshape(self.n, 64).copy()
         new = old.copy()
-        m = self.changed_prev[self.edges[:, 0]] & (self.edges[:, 1] >= self.b) & (self.edges[:, 1] < self.e)
+        m = self.changed_prev[self.edges[:, 0]] & self.own[self.edges[:, 1]]
         src, dst = self.edges[m, 0], self.edges[m, 1]
         np.maximum.at(new, dst, old[src])
         ch = (new != old).any(1)
-        self.regs.numpy().reshape(self.n, 64)[self.b:self.e] = new[self.b:self.e]
+        self.regs.numpy().reshape(self.n, 64)[self.own] = new[self.own]
         bits = np.zeros(((self.n + 31) // 32) * 32, np.uint8)
-        bits[:self.n][self.b:self.e] = ch[self.b:self.e]
+        bits[:self.n][self.own] = ch[self.own]
         words = np.packbits(bits.reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).reshape(-1).astype(np.int64)
         self.front.copy_(torch.from_numpy(words.astype(np.uint32).view(np.int32)))
-        return {"n_changed": int(ch[self.b:self.e].sum())}
+        return {"n_changed": int(ch[self.own].sum())}
 
     def exchange_tensors(self):
         return self.regs, self.front
