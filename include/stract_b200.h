@@ -61,10 +61,10 @@ typedef struct sb200_graph sb200_graph;
  * The library relabels u128 ids to dense u32 indices, builds a destination-major CSR (and a
  * source-major one for small frontiers) in HBM and keeps 2 x N x 64 B of HyperLogLog registers.
  *
- * Sharding (reference: one CentralityJob{shard} per worker, mapper.rs:356-369): rank `rank`
- * of `world_size` owns the destination rows [rank*N/world, (rank+1)*N/world) balanced by edge
- * count and keeps only their in-edges; every rank must be given the SAME full edge stream
- * (or use sb200_graph_create with world_size=1 for a single GPU). */
+ * Sharding (reference: one CentralityJob{shard} per worker, mapper.rs:356-369): with world_size > 1
+ * every rank must be given the SAME full edge stream; it keeps the full CSR and register array and
+ * OWNS the destination rows of every world_size-th 32-row block of the internal (degree-sorted)
+ * order (row block b -> rank b % world_size), so all ranks hold an equal share of every degree class. */
 #define SB200_SKIPPED_REL_DEFAULT 0x6FED00ull /* bits 8,10,11,13-19,21,22 */
 
 SB200_API int sb200_graph_create(const uint64_t* from_lo, const uint64_t* from_hi, const uint64_t* to_lo,
@@ -135,16 +135,15 @@ SB200_API int sb200_hyperball_registers(sb200_graph* g, uint64_t first, uint64_t
 SB200_API int sb200_hyperball_kahan(sb200_graph* g, uint64_t first, uint64_t count, double* sum, double* err);
 SB200_API int sb200_graph_node_ids(sb200_graph* g, uint64_t first, uint64_t count, uint64_t* id_lo, uint64_t* id_hi);
 
-/* Multi-GPU exchange hooks (the DHT upsert `HyperLogLog64Upsert` = elementwise max,
- * crates/core/src/ampc/dht/upsert.rs:66-83, degenerates to an all-gather because every
- * destination row has exactly one owner).  Device pointers, valid until the next step:
- *   regs      : the full N x 64 B "current" register array in INTERNAL row order; rows
- *               [row_begin,row_end) were just produced by this rank; the caller all-gathers
- *               them in place (e.g. ncclAllGather / torch.distributed.all_gather_into_tensor
- *               over the per-rank row ranges given by sb200_graph_row_ranges).
- *   frontier  : N-bit changed bitmap (32-bit words), this rank's rows only set by this rank;
- *               the caller OR-reduces / all-gathers it word-aligned the same way.
- * row ranges are aligned to 32 rows so bitmap words never straddle ranks. */
+/* Multi-GPU exchange hooks, collective variant.  The DHT upsert `HyperLogLog64Upsert` is an
+ * elementwise max (crates/core/src/ampc/dht/upsert.rs:66-83); registers only grow and every row has one
+ * owner, so after a step the caller merges the replicas with exactly that operator:
+ *   regs      : the full N x 64 B "current" register array (device pointer, valid until the next step):
+ *               ncclAllReduce(ncclUint8, ncclMax) in place (torch: all_reduce(op=MAX) on a uint8 view);
+ *   frontier  : N-bit changed bitmap; each 32-bit word has a single owner (ownership is in 32-row blocks)
+ *               and non-owners hold 0, so the same byte-wise max all-reduce yields the union;
+ * then sums the per-rank changed counts and calls sb200_hyperball_exchange_done.
+ * sb200_graph_row_ranges is kept for ABI compatibility and returns [0, ..., 0, N] for interleaved handles. */
 SB200_API int sb200_hyperball_exchange_ptrs(sb200_graph* g, void** regs, uint64_t* regs_bytes,
                                   void** frontier_words, uint64_t* frontier_bytes);
 SB200_API int sb200_graph_row_ranges(sb200_graph* g, uint64_t* begins /* world_size+1 */);

@@ -6,6 +6,7 @@
 namespace sb200 {
 static thread_local char t_err[1024] = "";
 std::atomic<uint64_t> g_launches{0};
+thread_local cudaStream_t t_pool_stream = nullptr;
 void set_error(const char* fmt, ...) {
   va_list ap; va_start(ap, fmt);
   vsnprintf(t_err, sizeof(t_err), fmt, ap);
@@ -57,7 +58,19 @@ int sb200_graph_create(const uint64_t* from_lo, const uint64_t* from_hi, const u
     SB_CUDA(cudaEventCreate(&g->ev0)); SB_CUDA(cudaEventCreate(&g->ev1));
     SB_CUDA(cudaEventCreate(&g->ev_run0)); SB_CUDA(cudaEventCreate(&g->ev_run1));
     for (int f = 0; f < sb200_graph::F_COUNT; f++) { SB_CUDA(cudaEventCreate(&g->prof_ev[f][0])); SB_CUDA(cudaEventCreate(&g->prof_ev[f][1])); }
-    SB_TRY(stage_graph(g, from_lo, from_hi, to_lo, to_hi, rel_flags, n_edges, skipped_rel_mask));
+    {
+      // staging temporaries and the CSR come from the stream-ordered pool (kept warm across creates);
+      // the register arrays / bitmaps below stay plain cudaMalloc because they are exported through CUDA IPC
+      static bool pool_ready[64] = {false};
+      if (device < 64 && !pool_ready[device]) {
+        cudaMemPool_t pool; uint64_t keep = ~0ull;
+        SB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        SB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        pool_ready[device] = true;
+      }
+      PoolScope scope(getenv("SB200_NO_POOL") ? nullptr : g->stream);
+      SB_TRY(stage_graph(g, from_lo, from_hi, to_lo, to_hi, rel_flags, n_edges, skipped_rel_mask));
+    }
     g->cub_tmp.release();
     SB_TRY(hb_alloc_state(g));
     SB_TRY(hb_reset(g));
@@ -188,7 +201,7 @@ int sb200_hyperball_exchange_ptrs(sb200_graph* g, void** regs, uint64_t* regs_by
 }
 int sb200_graph_row_ranges(sb200_graph* g, uint64_t* begins) {
   if (!g || !begins) SB_FAIL(SB200_EINVAL, "NULL argument");
-  for (int r = 0; r <= g->world; r++) begins[r] = g->range_begins[r];
+  for (int r = 0; r <= g->world; r++) begins[r] = (g->world > 1) ? (r == g->world ? g->N : 0) : g->range_begins[r];
   return SB200_OK;
 }
 // ---- fused exchange over NVLink peer memory (CUDA IPC between the per-GPU processes) ----------------------

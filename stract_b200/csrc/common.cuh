@@ -51,31 +51,44 @@ struct Err {
 
 #define SB_CHECK_LAUNCH() SB_CUDA(cudaGetLastError())
 
-// RAII device buffer (cudaMalloc); move-only
+extern thread_local cudaStream_t t_pool_stream;
+struct PoolScope {
+  cudaStream_t prev;
+  explicit PoolScope(cudaStream_t s) : prev(t_pool_stream) { t_pool_stream = s; }
+  ~PoolScope() { t_pool_stream = prev; }
+};
+
+// RAII device buffer (cudaMalloc or, inside a PoolScope, cudaMallocAsync); move-only
 template <class T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  cudaStream_t pool_stream = nullptr;  // non-null: stream-ordered allocation (cudaMallocAsync) on that stream
   DevBuf() {}
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), pool_stream(o.pool_stream) { o.p = nullptr; o.n = 0; o.pool_stream = nullptr; }
   DevBuf& operator=(DevBuf&& o) noexcept {
-    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    if (this != &o) { release(); p = o.p; n = o.n; pool_stream = o.pool_stream; o.p = nullptr; o.n = 0; o.pool_stream = nullptr; }
     return *this;
   }
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
-    p = nullptr; n = 0;
+    if (p) { if (pool_stream) cudaFreeAsync(p, pool_stream); else cudaFree(p); }
+    p = nullptr; n = 0; pool_stream = nullptr;
   }
+  // Inside a PoolScope the buffer comes from the device's stream-ordered memory pool: the staging pipeline
+  // allocates and frees tens of GB of temporaries per graph, and cudaMalloc/cudaFree of such sizes cost up to
+  // ~150 ms apiece (measured as noise in the per-phase staging times); pooled memory is recycled across creates.
   int alloc(size_t count) {
     release();
     if (count == 0) { n = 0; return SB200_OK; }
-    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    cudaError_t e;
+    if (t_pool_stream) { e = cudaMallocAsync((void**)&p, count * sizeof(T), t_pool_stream); pool_stream = t_pool_stream; }
+    else e = cudaMalloc((void**)&p, count * sizeof(T));
     if (e != cudaSuccess) {
-      p = nullptr;
-      set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+      p = nullptr; pool_stream = nullptr;
+      set_error("device allocation of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
       cudaGetLastError();
       return SB200_ENOMEM;
     }

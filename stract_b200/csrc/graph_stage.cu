@@ -72,6 +72,50 @@ __global__ void k_insert_nodes(const uint64_t* __restrict__ flo, const uint64_t*
   }
 }
 
+// inserts one endpoint and returns the table slot that holds it (0xFFFFFFFF for the all-ones id / on overflow)
+__device__ __forceinline__ uint32_t insert_slot(ulonglong2* table, uint64_t mask, uint64_t lo, uint64_t hi,
+                                                unsigned long long* count, unsigned long long max_count, int* flags) {
+  if (lo == EMPTY64 && hi == EMPTY64) { flags[1] = 1; return 0xFFFFFFFFu; }
+  const u128 key = ((u128)hi << 64) | lo;
+  uint64_t slot = hash128(lo, hi) & mask;
+  for (uint64_t probe = 0;; probe++) {
+    const ulonglong2 cur = table[slot];
+    if (cur.x == lo && cur.y == hi) return (uint32_t)slot;
+    if (cur.x == EMPTY64 || cur.y == EMPTY64) {
+      const u128 old = cas128((u128*)&table[slot], ~(u128)0, key);
+      if (old == ~(u128)0) {
+        const unsigned long long c = atomicAdd(count, 1ull);
+        if (c + 1 > max_count) flags[0] = 1;
+        return (uint32_t)slot;
+      }
+      if (old == key) return (uint32_t)slot;
+    }
+    slot = (slot + 1) & mask;
+    if (probe > mask) { flags[0] = 1; return 0xFFFFFFFFu; }
+  }
+}
+__global__ void k_insert_edges(const uint64_t* __restrict__ flo, const uint64_t* __restrict__ fhi,
+                               const uint64_t* __restrict__ tlo, const uint64_t* __restrict__ thi,
+                               const uint64_t* __restrict__ rel, uint64_t n, uint64_t skip_mask, ulonglong2* table,
+                               uint64_t mask, unsigned long long* count, unsigned long long max_count, int* flags,
+                               uint32_t* slot_from, uint32_t* slot_to, uint8_t* skip) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    if (*(volatile int*)flags) return;  // table overflow: the host grows it and replays the stream
+    slot_from[i] = insert_slot(table, mask, flo[i], fhi[i], count, max_count, flags);
+    slot_to[i] = insert_slot(table, mask, tlo[i], thi[i], count, max_count, flags);
+    skip[i] = (rel[i] & skip_mask) != 0;
+  }
+}
+__global__ void k_map_slots(const uint32_t* __restrict__ slot_from, const uint32_t* __restrict__ slot_to, uint64_t n,
+                            const uint32_t* __restrict__ slot_val, uint32_t max_rank, uint64_t* keys) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t sf = slot_from[i], st = slot_to[i];
+  const uint32_t rf = sf == 0xFFFFFFFFu ? max_rank : slot_val[sf];
+  const uint32_t rt = st == 0xFFFFFFFFu ? max_rank : slot_val[st];
+  keys[i] = ((uint64_t)rt << 32) | rf;
+}
+
 __device__ __forceinline__ uint32_t lookup_rank(const ulonglong2* __restrict__ table,
                                                 const uint32_t* __restrict__ slot_val, uint64_t mask,
                                                 uint64_t lo, uint64_t hi, uint32_t max_rank) {
@@ -320,23 +364,34 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
   PhaseTimer pt(s);
   pt.mark("0 copy-in");
 
-  // ---- 0. bring the SoA edge stream into HBM (no copy if the caller already has it there) ----
-  DevBuf<uint64_t> in_copy[5];
+  // ---- 0+1a. stream the SoA edge stream through HBM in chunks: while chunk c+1 crosses PCIe on the copy stream,
+  //            the endpoints of chunk c are inserted into the node hash set and their table slots recorded.
+  //            Only 9 B/edge (two u32 slots + the skip flag) stay resident instead of the 40 B/edge input.
   const uint64_t* src[5] = {from_lo, from_hi, to_lo, to_hi, rel};
-  const uint64_t* d[5];
+  bool host_in[5];
   for (int a = 0; a < 5; a++) {
-    if (n_edges == 0) { d[a] = nullptr; continue; }
-    if (!src[a]) SB_FAIL(SB200_EINVAL, "edge array %d is NULL", a);
-    if (is_device_ptr(src[a])) d[a] = src[a];
-    else { SB_TRY(in_copy[a].alloc(n_edges)); SB_TRY(copy_in(in_copy[a].p, src[a], n_edges * 8, s)); d[a] = in_copy[a].p; }
+    if (n_edges && !src[a]) SB_FAIL(SB200_EINVAL, "edge array %d is NULL", a);
+    host_in[a] = n_edges ? !is_device_ptr(src[a]) : false;
   }
+  const uint64_t CHUNK = 1ull << 25;
+  const uint64_t n_chunks = (n_edges + CHUNK - 1) / CHUNK;
+  DevBuf<uint64_t> stg[2][5];
+  for (int a = 0; a < 5; a++) if (host_in[a]) for (int bsel = 0; bsel < 2; bsel++) SB_TRY(stg[bsel][a].alloc(std::min<uint64_t>(CHUNK, n_edges)));
+  struct Pipe {
+    cudaStream_t cs = nullptr; cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+    ~Pipe() { for (int i = 0; i < 2; i++) { if (copied[i]) cudaEventDestroy(copied[i]); if (consumed[i]) cudaEventDestroy(consumed[i]); } if (cs) cudaStreamDestroy(cs); }
+  } pipe;
+  SB_CUDA(cudaStreamSynchronize(s));  // the staging buffers may be stream-ordered allocations of `s`; the copy stream uses them
+  SB_CUDA(cudaStreamCreateWithFlags(&pipe.cs, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) { SB_CUDA(cudaEventCreateWithFlags(&pipe.copied[i], cudaEventDisableTiming)); SB_CUDA(cudaEventCreateWithFlags(&pipe.consumed[i], cudaEventDisableTiming)); }
 
   DevBuf<unsigned long long> ctr; SB_TRY(ctr.alloc(8));
   DevBuf<int> flags; SB_TRY(flags.alloc(2));
   unsigned long long h_ctr[8]; int h_flags[2];
   DevBuf<uint8_t>& tmp = g->cub_tmp;
+  DevBuf<uint32_t> slot_from, slot_to; SB_TRY(slot_from.alloc(n_edges)); SB_TRY(slot_to.alloc(n_edges));
+  DevBuf<uint8_t> skip_a, skip_b; SB_TRY(skip_a.alloc(n_edges)); SB_TRY(skip_b.alloc(n_edges));
 
-  pt.mark("1a hash insert");
   // ---- 1. node dictionary ---------------------------------------------------------------------
   DevBuf<ulonglong2> table;
   uint64_t cap = 1ull << 12;
@@ -347,19 +402,35 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
     SB_CUDA(cudaMemsetAsync(table.p, 0xFF, cap * sizeof(ulonglong2), s));
     SB_CUDA(cudaMemsetAsync(ctr.p, 0, 8 * sizeof(unsigned long long), s));
     SB_CUDA(cudaMemsetAsync(flags.p, 0, 2 * sizeof(int), s));
-    if (n_edges) {
-      unsigned grid = (unsigned)std::min<uint64_t>(div_up(2 * n_edges, TPB), 148u * 32u);
-      SB_LAUNCH(k_insert_nodes, grid, TPB, 0, s, d[0], d[1], d[2], d[3], n_edges, table.p, cap - 1, ctr.p,
-                (unsigned long long)(cap / 2), flags.p);
+    for (uint64_t c = 0; c < n_chunks; c++) {
+      const int bsel = (int)(c & 1);
+      const uint64_t off = c * CHUNK, cnt = std::min<uint64_t>(CHUNK, n_edges - off);
+      const uint64_t* ptr[5];
+      bool any_host = false;
+      for (int a = 0; a < 5; a++) {
+        if (host_in[a]) {
+          if (!any_host) SB_CUDA(cudaStreamWaitEvent(pipe.cs, pipe.consumed[bsel], 0));  // staging buffer free again
+          any_host = true;
+          SB_CUDA(cudaMemcpyAsync(stg[bsel][a].p, src[a] + off, cnt * 8, cudaMemcpyHostToDevice, pipe.cs));
+          ptr[a] = stg[bsel][a].p;
+        } else ptr[a] = src[a] + off;
+      }
+      if (any_host) { SB_CUDA(cudaEventRecord(pipe.copied[bsel], pipe.cs)); SB_CUDA(cudaStreamWaitEvent(s, pipe.copied[bsel], 0)); }
+      const unsigned grid = (unsigned)std::min<uint64_t>(div_up(cnt, TPB), 148u * 32u);
+      SB_LAUNCH(k_insert_edges, grid, TPB, 0, s, ptr[0], ptr[1], ptr[2], ptr[3], ptr[4], cnt, skip_mask, table.p, cap - 1, ctr.p,
+                (unsigned long long)(cap / 2), flags.p, slot_from.p + off, slot_to.p + off, skip_a.p + off);
       SB_CHECK_LAUNCH();
+      if (any_host) SB_CUDA(cudaEventRecord(pipe.consumed[bsel], s));
     }
     SB_CUDA(cudaMemcpyAsync(h_ctr, ctr.p, sizeof(h_ctr), cudaMemcpyDeviceToHost, s));
     SB_CUDA(cudaMemcpyAsync(h_flags, flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, s));
     SB_CUDA(cudaStreamSynchronize(s));
+    SB_CUDA(cudaStreamSynchronize(pipe.cs));
     if (!h_flags[0]) { n_keys = h_ctr[0]; has_max = h_flags[1] != 0; break; }
     cap <<= 2;  // load factor exceeded 1/2: grow and redo (still linear overall)
-    if (cap > (1ull << 34)) SB_FAIL(SB200_ENOMEM, "node hash set would exceed 2^34 slots");
+    if (cap > (1ull << 32)) SB_FAIL(SB200_ENOMEM, "node hash set would exceed 2^32 slots");
   }
+  for (int a = 0; a < 5; a++) for (int bsel = 0; bsel < 2; bsel++) stg[bsel][a].release();
   pt.mark("1b compact+sort ids");
   const uint64_t N = n_keys + (has_max ? 1 : 0);
   g->N = N;
@@ -404,12 +475,12 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
   pt.mark("2a map edges");
   // ---- 2. edges -> (to_rank<<32|from_rank), stable sort, unique_by first-wins, drop skipped ----
   DevBuf<uint64_t> keys_a, keys_b; SB_TRY(keys_a.alloc(n_edges)); SB_TRY(keys_b.alloc(n_edges));
-  DevBuf<uint8_t> skip_a, skip_b; SB_TRY(skip_a.alloc(n_edges)); SB_TRY(skip_b.alloc(n_edges));
-  SB_LAUNCH(k_map_edges, div_up(n_edges, TPB), TPB, 0, s, d[0], d[1], d[2], d[3], d[4], n_edges, skip_mask, table.p,
-            slot_val.p, cap - 1, (uint32_t)(N - 1), keys_a.p, skip_a.p);
-  SB_CHECK_LAUNCH();
+  if (n_edges) {
+    SB_LAUNCH(k_map_slots, div_up(n_edges, TPB), TPB, 0, s, slot_from.p, slot_to.p, n_edges, slot_val.p, (uint32_t)(N - 1), keys_a.p);
+    SB_CHECK_LAUNCH();
+  }
   SB_CUDA(cudaStreamSynchronize(s));
-  for (int a = 0; a < 5; a++) in_copy[a].release();
+  slot_from.release(); slot_to.release();
   table.release(); slot_val.release();
 
   pt.mark("2b sort pairs + select");

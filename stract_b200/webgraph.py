@@ -168,7 +168,7 @@ class DeviceGraph:
         ln = C.c_uint64(0)
         check(self._L.sb200_hyperball_result(self._h, None, None, None, 0, C.byref(ln)))
         k = ln.value
-        lo = np.zeros(k, np.uint64); hi = np.zeros(k, np.uint64); c = np.zeros(k, np.float64)
+        lo = np.empty(k, np.uint64); hi = np.empty(k, np.uint64); c = np.empty(k, np.float64)
         if k:
             check(self._L.sb200_hyperball_result(self._h, lo.ctypes.data, hi.ctypes.data, c.ctypes.data, k, C.byref(ln)))
         return lo, hi, c
