@@ -255,8 +255,20 @@ def main():
         roofline = None
         if dom:
             ach = dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9
+            # DRAM bytes per launch come from the committed `ncu --set full` capture of this kernel and only
+            # apply when the workload is the one that was captured; otherwise null
+            traffic, traffic_src = None, None
+            try:
+                with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as fh:
+                    cap = json.load(fh)
+                if cap["config"]["nodes"] == args.nodes and cap["config"]["edges"] == args.edges and "pull_warp" in dom["name"]:
+                    traffic = cap["k_pull_warp<dense>"]["dram_bytes_per_launch"]
+                    traffic_src = cap["source"]
+            except (OSError, KeyError, ValueError):
+                pass
             roofline = {"bound": "hbm", "kernel": dom["name"], "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                        "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                        "peak_source": peak_src,
                         "launches": dom["launches"], "avg_launch_ms": dom["ms"] / dom["launches"],
                         "alg_bytes_per_launch": dom["alg_bytes"] / dom["launches"]}
         result.update(value=value, ms_per_step=ms_total / args.steps, iters=iters, E=E, info=info, clocks=clocks,
