@@ -19,6 +19,7 @@ import numpy as np
 
 from . import _lib_bm25 as B
 from ._lib import check, lib
+from ._hostmem import host_out
 
 K1 = np.float32(1.2)
 B_ = np.float32(0.75)
@@ -224,19 +225,13 @@ class TopDocs:
         nq, nt = term_ords.shape
         if weights is None:  # Bm25Weight::for_terms with the segment's own statistics (bm25.rs:98-134)
             df = segment.doc_freq[np.minimum(term_ords, segment.n_terms - 1)]
-            uniq = {}
-            weights = np.zeros((nq, nt), np.float32)
-            for q in range(nq):
-                for t in range(nt):
-                    d = int(df[q, t])
-                    w = uniq.get(d)
-                    if w is None:
-                        w = uniq[d] = np.float32(idf(d, segment.max_doc) * (np.float32(1.0) + K1))
-                    weights[q, t] = w
+            uniq, inv = np.unique(df, return_inverse=True)  # one scalar idf per distinct doc_freq
+            w_u = np.array([np.float32(idf(int(d), segment.max_doc) * (np.float32(1.0) + K1)) for d in uniq], np.float32)
+            weights = w_u[inv].reshape(nq, nt)
         weights = np.ascontiguousarray(weights, np.float32)
         cache = compute_tf_cache(segment.average_fieldnorm)
         k = self.limit
-        docs = np.zeros((nq, k), np.uint32); scores = np.zeros((nq, k), np.float32); n_out = np.zeros(nq, np.uint32)
+        docs = host_out((nq, k), np.uint32); scores = host_out((nq, k), np.float32); n_out = np.zeros(nq, np.uint32)
         b = B.Bm25Batch(nq, nt, _p(term_ords), _p(weights), _p(cache), mode, k)
         st = B.Bm25Stats()
         check(segment._L.sb200_bm25_topk_batch(segment._h, C.byref(b), _p(docs), _p(scores), _p(n_out), C.byref(st)))
@@ -268,17 +263,11 @@ class SignalComputer:
         term_ords = np.ascontiguousarray(term_ords, np.uint32)
         nq, nt = term_ords.shape
         df = seg.doc_freq[np.minimum(term_ords, seg.n_terms - 1)]
-        uniq = {}
-        weights = np.zeros((nq, nt), np.float32)
-        for q in range(nq):
-            for t in range(nt):
-                d = int(df[q, t])
-                w = uniq.get(d)
-                if w is None:
-                    w = uniq[d] = idf(d, seg.max_doc)
-                weights[q, t] = w
+        uniq, inv = np.unique(df, return_inverse=True)  # one scalar idf per distinct doc_freq
+        w_u = np.array([idf(int(d), seg.max_doc) for d in uniq], np.float32)
+        weights = np.ascontiguousarray(w_u[inv].reshape(nq, nt))
         cache = compute_tf_cache(seg.average_fieldnorm, self.k1, self.b)
-        docs = np.zeros((nq, k), np.uint32); totals = np.zeros((nq, k), np.float64); n_out = np.zeros(nq, np.uint32)
+        docs = host_out((nq, k), np.uint32); totals = host_out((nq, k), np.float64); n_out = np.zeros(nq, np.uint32)
         sb = B.SignalBatch()
         sb.q = B.Bm25Batch(nq, nt, _p(term_ords), _p(weights), _p(cache), MODE_OR, k)
         sb.k1 = float(self.k1); sb.coeff_text = self.coeff_text

@@ -72,7 +72,12 @@ int sb200_graph_create(const uint64_t* from_lo, const uint64_t* from_hi, const u
       SB_TRY(stage_graph(g, from_lo, from_hi, to_lo, to_hi, rel_flags, n_edges, skipped_rel_mask));
     }
     g->cub_tmp.release();
-    SB_TRY(hb_alloc_state(g));
+    {
+      // a single-rank handle never exports its arrays, so they can come from the warm pool too (saves the
+      // cudaMalloc/cudaFree of ~4.5 GB per create/destroy at C2 size); sharded handles need IPC-exportable memory
+      PoolScope scope((world_size == 1 && !getenv("SB200_NO_POOL")) ? g->stream : nullptr);
+      SB_TRY(hb_alloc_state(g));
+    }
     SB_TRY(hb_reset(g));
     return SB200_OK;
   };

@@ -29,6 +29,7 @@
 //     reference's "+= 0.0" (it is idempotent after one application, so skipping the other N-1 zero
 //     adds is bit-exact).
 // Roofline: HBM.  Algorithmic bytes per iteration: 68 B x E_active + 132 B x N_written + 40 B x N_changed.
+#include <chrono>
 #include "graph.cuh"
 #include "../../include/sb200_hll_tables.h"
 
@@ -664,6 +665,8 @@ int hb_result(sb200_graph* g, uint64_t* id_lo, uint64_t* id_hi, double* cent, ui
   cudaStream_t s = g->stream;
   const uint64_t N = g->N;
   if (N == 0) { *len = 0; return SB200_OK; }
+  PoolScope scope(getenv("SB200_NO_POOL") ? nullptr : s);  // temporaries from the stream-ordered pool, freed on `s`
+  const auto tp0 = std::chrono::steady_clock::now();
   DevBuf<uint32_t> flag, pos; DevBuf<double> val;
   SB_TRY(flag.alloc(N + 1)); SB_TRY(pos.alloc(N + 1)); SB_TRY(val.alloc(N));
   SB_CUDA(cudaMemsetAsync(flag.p + N, 0, 4, s));
@@ -679,6 +682,9 @@ int hb_result(sb200_graph* g, uint64_t* id_lo, uint64_t* id_hi, double* cent, ui
   uint32_t total = 0;
   SB_CUDA(cudaMemcpyAsync(&total, pos.p + N, 4, cudaMemcpyDeviceToHost, s));
   SB_CUDA(cudaStreamSynchronize(s));
+  const bool timing = getenv("SB200_RESULT_TIMING") != nullptr;
+  const auto tp1 = std::chrono::steady_clock::now();
+  if (timing) fprintf(stderr, "[sb200 result] flags+scan %.2f ms\n", std::chrono::duration<double, std::milli>(tp1 - tp0).count());
   *len = total;
   if (!cent) return SB200_OK;
   const uint64_t k = std::min<uint64_t>(total, cap);
@@ -691,6 +697,8 @@ int hb_result(sb200_graph* g, uint64_t* id_lo, uint64_t* id_hi, double* cent, ui
   SB_CUDA(cudaMemcpyAsync(id_hi, ohi.p, k * 8, cudaMemcpyDefault, s));
   SB_CUDA(cudaMemcpyAsync(cent, oc.p, k * 8, cudaMemcpyDefault, s));
   SB_CUDA(cudaStreamSynchronize(s));
+  if (timing) fprintf(stderr, "[sb200 result] scatter+d2h of %llu rows %.2f ms\n", (unsigned long long)k,
+                      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp1).count());
   return SB200_OK;
 }
 

@@ -18,6 +18,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import GraphInfo, IterStats, check, lib
+from ._hostmem import host_out
 
 
 class RelFlags:
@@ -165,13 +166,19 @@ class DeviceGraph:
                 for i in range(n.value)]
 
     def result(self):
+        # one call with capacity = node count (an upper bound on the nodes with centrality > 0) instead of a
+        # count-only call followed by a second pass; big outputs land in page-locked memory (_hostmem.py)
+        import time
+        n = self.info()["n_nodes"]
         ln = C.c_uint64(0)
-        check(self._L.sb200_hyperball_result(self._h, None, None, None, 0, C.byref(ln)))
+        t0 = time.perf_counter()
+        lo = host_out(n, np.uint64); hi = host_out(n, np.uint64); c = host_out(n, np.float64)
+        t1 = time.perf_counter()
+        if n:
+            check(self._L.sb200_hyperball_result(self._h, lo.ctypes.data, hi.ctypes.data, c.ctypes.data, n, C.byref(ln)))
+        self.result_wall_ms = {"host_alloc": (t1 - t0) * 1e3, "call": (time.perf_counter() - t1) * 1e3}
         k = ln.value
-        lo = np.empty(k, np.uint64); hi = np.empty(k, np.uint64); c = np.empty(k, np.float64)
-        if k:
-            check(self._L.sb200_hyperball_result(self._h, lo.ctypes.data, hi.ctypes.data, c.ctypes.data, k, C.byref(ln)))
-        return lo, hi, c
+        return lo[:k], hi[:k], c[:k]
 
     def registers(self, first=0, count=None):
         n = self.info()["n_nodes"]
@@ -258,14 +265,23 @@ class HarmonicCentrality:
 
     @classmethod
     def calculate(cls, graph, device=0, max_iters=0):
+        import time
+        t0 = time.perf_counter()
         dg = DeviceGraph(graph, device=device)
         try:
+            t1 = time.perf_counter()
             iters, stats = dg.run(max_iters)
+            t2 = time.perf_counter()
             lo, hi, c = dg.result()
+            t3 = time.perf_counter()
             info = dg.info()
-            return cls(lo, hi, c, info["n_nodes"], iters, stats, info)
         finally:
             dg.close()
+        t4 = time.perf_counter()
+        # host wall clock of the four C-ABI phases (every call returns synchronised)
+        info["wall_ms"] = {"create": (t1 - t0) * 1e3, "run": (t2 - t1) * 1e3, "result": (t3 - t2) * 1e3,
+                           "destroy": (t4 - t3) * 1e3, **{"result_" + k: v for k, v in dg.result_wall_ms.items()}}
+        return cls(lo, hi, c, info["n_nodes"], iters, stats, info)
 
     def _m(self):
         if self._map is None:
