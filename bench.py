@@ -174,7 +174,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-bm25", action="store_true")
-    ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL broadcast exchange instead of the fused peer-memory stores")
+    ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL byte-max all-reduce exchange instead of the fused peer-memory stores")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "symm", "multicast"],
+                    help="multi-GPU fused exchange transport: CUDA IPC peer mappings (default), torch symmetric memory "
+                         "unicast, or NVSwitch multicast stores")
     ap.add_argument("--cpu-nodes", type=int, default=1_000_000)
     ap.add_argument("--cpu-edges", type=int, default=20_000_000)
     ap.add_argument("--ref-nodes", type=int, default=50_000)
@@ -284,8 +287,12 @@ def main():
         # (device ms of the step kernels) + exchange wall time => use wall clock around the loop
         from stract_b200.webgraph import DeviceGraph as _DG
         dg = _DG(graph, device=local_rank, rank=rank, world_size=world)
-        if not args.no_p2p:
+        exchange_kind = "nccl"
+        if args.exchange in ("symm", "multicast"):
+            exchange_kind = "symmetric-memory " + dg.enable_symmetric(multicast=(args.exchange == "multicast"))
+        elif not args.no_p2p:
             dg.enable_p2p()
+            exchange_kind = "p2p"
         info = dg.info()
         E = info["n_edges_kept"]
         ranges = dg.row_ranges()
@@ -321,6 +328,7 @@ def main():
                 "iter_ms": [round(s["ms"], 3) for s in st_last], "modes": [s["mode"] for s in st_last]}
         allr = [None] * world
         dist.all_gather_object(allr, mine)
+        result.update(exchange_kind=exchange_kind)
         result.update(value=value, ms_per_step=ms_total / args.steps, iters=tot_iters // args.steps, E=E, info=info,
                       clocks=clocks, roofline=None, launches=int(nl.item()), kernels=[], per_iter=allr)
         dg.close()
@@ -391,7 +399,9 @@ def main():
                            "kept_edges": result["E"], "n_nodes": result["info"]["n_nodes"],
                            "iterations_per_step": result["iters"],
                            "l2_policy": "inputs >> L2: 2 x 3.2 GB register arrays + 4 GB CSR per iteration",
-                           "parallelism": "1 GPU" if world == 1 else (f"destination-row partition x{world}, " + ("NCCL broadcast of owned register rows per iteration" if args.no_p2p else "fused exchange: pull kernels store produced rows into all peers' replicas over NVLink (CUDA IPC), NCCL all-reduce of the changed count as barrier")),
+                           "parallelism": "1 GPU" if world == 1 else (f"destination-row partition x{world}, " + {"nccl": "NCCL byte-max all-reduce of the register replicas per iteration",
+                                                                                                    "p2p": "fused exchange: pull kernels store produced rows into all peers' replicas over NVLink (CUDA IPC), NCCL all-reduce of the changed count as barrier"}.get(
+                               result.get("exchange_kind", "p2p"), "fused exchange over " + str(result.get("exchange_kind")) + " stores, NCCL all-reduce of the changed count as barrier")),
                            "hbm_bytes": result["info"]["hbm_bytes"], "gen_s": round(gen_s, 2),
                            "stage_ms": result["info"]["stage_ms"]},
                 "clocks": result["clocks"], "gpu_launches": result["launches"], "roofline": result["roofline"],

@@ -149,14 +149,32 @@ SB200_API int sb200_hyperball_exchange_ptrs(sb200_graph* g, void** regs, uint64_
 SB200_API int sb200_graph_row_ranges(sb200_graph* g, uint64_t* begins /* world_size+1 */);
 /* Fused exchange (one process per GPU on one NVLink/NVSwitch box): every rank exports CUDA IPC handles of its two
  * register arrays and two bitmaps, imports those of all other ranks (any order) and enables p2p.  From then on
- * sb200_hyperball_step stores every produced row, and ORs every changed bit, directly into the peers' replicas from
- * inside the pull kernels (st.global / atom.or.sys on peer pointers), so no all-gather is needed: between steps the
- * caller only needs a barrier plus the sum of the per-rank changed counts (one small all-reduce does both), then
- * sb200_hyperball_exchange_done.  A barrier is also required after create/reset before the first step. */
+ * sb200_hyperball_step stores every produced row directly into the peers' replicas from inside the pull kernels
+ * (st.global on peer pointers) and copies its owned changed-bitmap words to them, so no all-gather is needed:
+ * between steps the caller only needs a barrier plus the sum of the per-rank changed counts (one small all-reduce
+ * does both), then sb200_hyperball_exchange_done.  A barrier is also required after create/reset before the
+ * first step. */
 #define SB200_IPC_HANDLE_BYTES 64
 SB200_API int sb200_hyperball_ipc_export(sb200_graph* g, uint8_t* out /* 4 * SB200_IPC_HANDLE_BYTES */);
 SB200_API int sb200_hyperball_ipc_import(sb200_graph* g, const uint8_t* handles /* one peer's 4 handles */);
 SB200_API int sb200_hyperball_p2p_enable(sb200_graph* g, int on);
+
+/* The same fused exchange over caller-owned memory, addressed directly instead of through CUDA IPC.  Meant for
+ * "symmetric" memory that is bound to an NVSwitch multicast object on every rank (cuMemCreate +
+ * cuMulticastBindMem; torch.distributed._symmetric_memory does exactly that):
+ *   1. sb200_hyperball_state_bytes  -> sizes of one register array / one bitmap for this graph;
+ *   2. the caller allocates 2 + 2 such buffers (register arrays 64-byte aligned) and hands their LOCAL mappings to
+ *      sb200_hyperball_bind_state right after create: the handle drops its own arrays, uses these (never frees
+ *      them; they must outlive the handle) and re-initialises the HyperBall state;
+ *   3. sb200_hyperball_set_publish_targets names where produced rows / bitmap words are stored in addition to the
+ *      local replica: either world_size-1 unicast peer mappings, or ONE multicast mapping (n_targets = 1) -- a store
+ *      to a multicast address is replicated by the switch into every rank's replica, so a produced row leaves the
+ *      GPU once instead of world_size-1 times.  n_targets = 0 switches the fused exchange off.
+ * Inter-step protocol as above (barrier + changed-count all-reduce, then sb200_hyperball_exchange_done). */
+SB200_API int sb200_hyperball_state_bytes(sb200_graph* g, uint64_t* regs_bytes, uint64_t* bitmap_bytes);
+SB200_API int sb200_hyperball_bind_state(sb200_graph* g, void* regs0, void* regs1, void* bitmap0, void* bitmap1);
+SB200_API int sb200_hyperball_set_publish_targets(sb200_graph* g, int n_targets, const uint64_t* regs0,
+                                                  const uint64_t* regs1, const uint64_t* bitmap0, const uint64_t* bitmap1);
 
 /* after the exchange: tell the library the global changed count so every rank picks the same mode */
 SB200_API int sb200_hyperball_exchange_done(sb200_graph* g, uint64_t global_n_changed);

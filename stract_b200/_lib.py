@@ -69,6 +69,9 @@ def lib():
     f("sb200_hyperball_ipc_export", i32, vp, vp)
     f("sb200_hyperball_ipc_import", i32, vp, vp)
     f("sb200_hyperball_p2p_enable", i32, vp, i32)
+    f("sb200_hyperball_state_bytes", i32, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
+    f("sb200_hyperball_bind_state", i32, vp, vp, vp, vp, vp)
+    f("sb200_hyperball_set_publish_targets", i32, vp, i32, vp, vp, vp, vp)
     try:
         from . import _lib_bm25
         _lib_bm25.proto(L, f)

@@ -1,6 +1,7 @@
 // api_graph.cu -- C ABI of path 1 (see include/stract_b200.h) + process-wide error/launch accounting.
 #include "graph.cuh"
 
+#include <algorithm>
 #include <vector>
 
 namespace sb200 {
@@ -91,7 +92,7 @@ void sb200_graph_destroy(sb200_graph* g) {
   if (!g) return;
   cudaSetDevice(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);
-  for (int p = 0; p < g->n_peers; p++) for (int i = 0; i < 2; i++) {
+  if (g->peers_ipc) for (int p = 0; p < g->n_peers; p++) for (int i = 0; i < 2; i++) {
     if (g->peer_regs[i][p]) cudaIpcCloseMemHandle(g->peer_regs[i][p]);
     if (g->peer_bm[i][p]) cudaIpcCloseMemHandle(g->peer_bm[i][p]);
   }
@@ -225,6 +226,7 @@ int sb200_hyperball_ipc_export(sb200_graph* g, uint8_t* out /* 4 x 64 bytes */) 
 int sb200_hyperball_ipc_import(sb200_graph* g, const uint8_t* handles) {
   SB_ENTER(g);
   if (!handles) SB_FAIL(SB200_EINVAL, "handles is NULL");
+  if (!g->peers_ipc) SB_FAIL(SB200_ESTATE, "publish targets were set by address; IPC import cannot be mixed in");
   if (g->n_peers >= sb200::MAX_PEERS) SB_FAIL(SB200_ERANGE, "more than %d peers", sb200::MAX_PEERS);
   void* opened[4];
   for (int i = 0; i < 4; i++) {
@@ -241,6 +243,49 @@ int sb200_hyperball_p2p_enable(sb200_graph* g, int on) {
   SB_ENTER(g);
   if (on && g->n_peers != g->world - 1) SB_FAIL(SB200_ESTATE, "imported %d peers, world_size-1 = %d", g->n_peers, g->world - 1);
   g->p2p = on != 0;
+  return SB200_OK;
+}
+
+// ---- caller-owned state + publish targets by address (symmetric / multicast memory) -----------------------
+int sb200_hyperball_state_bytes(sb200_graph* g, uint64_t* regs_bytes, uint64_t* bitmap_bytes) {
+  if (!g) SB_FAIL(SB200_EINVAL, "NULL graph handle");
+  if (regs_bytes) *regs_bytes = std::max<uint64_t>(g->N, 1) * 64;
+  if (bitmap_bytes) *bitmap_bytes = ((g->N + 31) / 32 + 1) * 4;
+  return SB200_OK;
+}
+int sb200_hyperball_bind_state(sb200_graph* g, void* regs0, void* regs1, void* bitmap0, void* bitmap1) {
+  SB_ENTER(g);
+  if (!regs0 || !regs1 || !bitmap0 || !bitmap1) SB_FAIL(SB200_EINVAL, "NULL state buffer");
+  if (regs0 == regs1 || bitmap0 == bitmap1) SB_FAIL(SB200_EINVAL, "the two register arrays / bitmaps must be distinct");
+  if (((uintptr_t)regs0 | (uintptr_t)regs1) & 63) SB_FAIL(SB200_EINVAL, "register arrays must be 64-byte aligned");
+  if (((uintptr_t)bitmap0 | (uintptr_t)bitmap1) & 3) SB_FAIL(SB200_EINVAL, "bitmaps must be 4-byte aligned");
+  void* all[4] = {regs0, regs1, bitmap0, bitmap1};
+  for (void* q : all) if (!is_device_ptr(q)) SB_FAIL(SB200_EINVAL, "state buffers must be device memory");
+  if (g->t != 0 || g->exchange_pending) SB_FAIL(SB200_ESTATE, "bind the state right after create/reset, before the first step");
+  if (g->n_peers) SB_FAIL(SB200_ESTATE, "bind the state before the publish targets are set");
+  SB_CUDA(cudaStreamSynchronize(g->stream));
+  const uint64_t rn = std::max<uint64_t>(g->N, 1) * 64, bn = (g->N + 31) / 32 + 1;
+  g->regs[0].adopt((uint8_t*)regs0, rn); g->regs[1].adopt((uint8_t*)regs1, rn);
+  g->bm[0].adopt((uint32_t*)bitmap0, bn); g->bm[1].adopt((uint32_t*)bitmap1, bn);
+  return hb_reset(g);
+}
+int sb200_hyperball_set_publish_targets(sb200_graph* g, int n_targets, const uint64_t* regs0, const uint64_t* regs1,
+                                        const uint64_t* bitmap0, const uint64_t* bitmap1) {
+  SB_ENTER(g);
+  if (n_targets < 0 || n_targets > sb200::MAX_PEERS) SB_FAIL(SB200_ERANGE, "n_targets %d not in [0,%d]", n_targets, sb200::MAX_PEERS);
+  if (n_targets && (!regs0 || !regs1 || !bitmap0 || !bitmap1)) SB_FAIL(SB200_EINVAL, "NULL target array");
+  if (g->n_peers && g->peers_ipc) SB_FAIL(SB200_ESTATE, "IPC peers were imported; targets by address cannot be mixed in");
+  if (g->exchange_pending) SB_FAIL(SB200_ESTATE, "an exchange is pending");
+  for (int p = 0; p < n_targets; p++) {
+    if (!regs0[p] || !regs1[p] || !bitmap0[p] || !bitmap1[p]) SB_FAIL(SB200_EINVAL, "target %d has a NULL address", p);
+    if ((regs0[p] | regs1[p]) & 15) SB_FAIL(SB200_EINVAL, "target %d: register arrays must be 16-byte aligned", p);
+  }
+  for (int p = 0; p < sb200::MAX_PEERS; p++) {
+    const bool on = p < n_targets;
+    g->peer_regs[0][p] = on ? (void*)(uintptr_t)regs0[p] : nullptr; g->peer_regs[1][p] = on ? (void*)(uintptr_t)regs1[p] : nullptr;
+    g->peer_bm[0][p] = on ? (void*)(uintptr_t)bitmap0[p] : nullptr; g->peer_bm[1][p] = on ? (void*)(uintptr_t)bitmap1[p] : nullptr;
+  }
+  g->n_peers = n_targets; g->peers_ipc = false; g->p2p = n_targets > 0;
   return SB200_OK;
 }
 

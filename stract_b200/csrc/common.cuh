@@ -64,19 +64,26 @@ struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
   cudaStream_t pool_stream = nullptr;  // non-null: stream-ordered allocation (cudaMallocAsync) on that stream
+  bool borrowed = false;               // caller-owned memory (sb200_hyperball_bind_state): never freed here
   DevBuf() {}
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), pool_stream(o.pool_stream) { o.p = nullptr; o.n = 0; o.pool_stream = nullptr; }
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), pool_stream(o.pool_stream), borrowed(o.borrowed) {
+    o.p = nullptr; o.n = 0; o.pool_stream = nullptr; o.borrowed = false;
+  }
   DevBuf& operator=(DevBuf&& o) noexcept {
-    if (this != &o) { release(); p = o.p; n = o.n; pool_stream = o.pool_stream; o.p = nullptr; o.n = 0; o.pool_stream = nullptr; }
+    if (this != &o) {
+      release(); p = o.p; n = o.n; pool_stream = o.pool_stream; borrowed = o.borrowed;
+      o.p = nullptr; o.n = 0; o.pool_stream = nullptr; o.borrowed = false;
+    }
     return *this;
   }
   ~DevBuf() { release(); }
   void release() {
-    if (p) { if (pool_stream) cudaFreeAsync(p, pool_stream); else cudaFree(p); }
-    p = nullptr; n = 0; pool_stream = nullptr;
+    if (p && !borrowed) { if (pool_stream) cudaFreeAsync(p, pool_stream); else cudaFree(p); }
+    p = nullptr; n = 0; pool_stream = nullptr; borrowed = false;
   }
+  void adopt(T* ptr, size_t count) { release(); p = ptr; n = count; borrowed = true; }
   // Inside a PoolScope the buffer comes from the device's stream-ordered memory pool: the staging pipeline
   // allocates and frees tens of GB of temporaries per graph, and cudaMalloc/cudaFree of such sizes cost up to
   // ~150 ms apiece (measured as noise in the per-phase staging times); pooled memory is recycled across creates.

@@ -65,6 +65,7 @@ struct sb200_graph {
   // fused multi-GPU exchange over peer memory (CUDA IPC): replicas of regs[2]/bm[2] on the other ranks
   int n_peers = 0;
   bool p2p = false;
+  bool peers_ipc = true;  // peer mappings came from cudaIpcOpenMemHandle (closed at destroy); false: caller-owned addresses
   void* peer_regs[2][sb200::MAX_PEERS] = {{nullptr}};
   void* peer_bm[2][sb200::MAX_PEERS] = {{nullptr}};
   double dense_frac = 0.35, push_div = 48.0;  // mode policy (see hb_step)

@@ -239,6 +239,37 @@ class DeviceGraph:
         dist.barrier(group=group)
         self.p2p = True
 
+    def enable_symmetric(self, group=None, multicast=True):
+        """Fused exchange over torch symmetric memory: the register arrays and bitmaps move into buffers that every
+        rank maps (and, on an NVSwitch box, that are bound to a multicast object).  With `multicast` and switch
+        support a produced row is stored once, to the multicast address, and the switch replicates it into every
+        replica; otherwise it is stored to each peer mapping like `enable_p2p` does.  Returns "multicast" or
+        "unicast".  The buffers are torch tensors owned by this object (plumbing; the stores are the library's)."""
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        grp = group if group is not None else dist.group.WORLD
+        rb, bb = C.c_uint64(0), C.c_uint64(0)
+        check(self._L.sb200_hyperball_state_bytes(self._h, C.byref(rb), C.byref(bb)))
+        dev = torch.device("cuda", self.device)
+        bufs = [symm.empty(rb.value, dtype=torch.uint8, device=dev), symm.empty(rb.value, dtype=torch.uint8, device=dev),
+                symm.empty(bb.value // 4, dtype=torch.int32, device=dev), symm.empty(bb.value // 4, dtype=torch.int32, device=dev)]
+        hdls = [symm.rendezvous(b, grp) for b in bufs]
+        torch.cuda.synchronize(dev)
+        check(self._L.sb200_hyperball_bind_state(self._h, *(b.data_ptr() for b in bufs)))
+        use_mc = bool(multicast) and all(int(getattr(h, "multicast_ptr", 0) or 0) != 0 for h in hdls)
+        if use_mc:
+            cols = [[int(h.multicast_ptr)] for h in hdls]
+        else:
+            cols = [[int(p) for r, p in enumerate(h.buffer_ptrs) if r != hdls[0].rank] for h in hdls]
+        n = len(cols[0])
+        arrs = [(C.c_uint64 * max(n, 1))(*c) for c in cols]
+        check(self._L.sb200_hyperball_set_publish_targets(self._h, n, *arrs))
+        self._symm = (bufs, hdls)  # keep the buffers alive for as long as the handle uses them
+        dist.barrier(group=group)
+        self.p2p = True
+        return "multicast" if use_mc else "unicast"
+
     def exchange_done(self, global_n_changed):
         check(self._L.sb200_hyperball_exchange_done(self._h, int(global_n_changed)))
 
@@ -246,6 +277,7 @@ class DeviceGraph:
         if self._h:
             self._L.sb200_graph_destroy(self._h)
             self._h = C.c_void_p()
+        self._symm = None
 
     def __del__(self):
         try:
@@ -364,11 +396,16 @@ class ShardedHarmonicCentrality:
     array, owns a destination-row range of the CSR, and runs `run_sharded_loop`."""
 
     @staticmethod
-    def calculate(graph, device, rank, world_size, max_iters=0, group=None, p2p=False):
+    def calculate(graph, device, rank, world_size, max_iters=0, group=None, p2p=False, exchange=None):
+        """exchange: None/"nccl" = byte-max all-reduce, "p2p" (or p2p=True) = fused stores over CUDA IPC peer
+        mappings, "symm" / "multicast" = fused stores over torch symmetric memory (unicast / NVSwitch multicast)."""
         dg = DeviceGraph(graph, device=device, rank=rank, world_size=world_size)
         try:
-            if p2p and world_size > 1:
-                dg.enable_p2p(group)
+            if world_size > 1:
+                if exchange in ("symm", "multicast"):
+                    dg.exchange_kind = dg.enable_symmetric(group, multicast=(exchange == "multicast"))
+                elif p2p or exchange == "p2p":
+                    dg.enable_p2p(group)
             t, stats = run_sharded_loop(dg, world_size, group, max_iters)
             lo, hi, c = dg.result()
             info = dg.info()
