@@ -179,6 +179,16 @@ SB200_API int sb200_hyperball_set_publish_targets(sb200_graph* g, int n_targets,
 /* after the exchange: tell the library the global changed count so every rank picks the same mode */
 SB200_API int sb200_hyperball_exchange_done(sb200_graph* g, uint64_t global_n_changed);
 
+/* Device-memory arena diagnostics.  With SB200_ARENA=1 in the environment, staging temporaries, the CSR and the
+ * state of single-rank handles are sub-allocated from large slabs that are kept for the life of the process
+ * (deterministic, no driver call per allocation once warm) instead of the driver's stream-ordered pool.
+ * sb200_arena_trim returns empty slabs to the driver; sb200_arena_selftest runs the allocator's randomised
+ * invariant test over host memory (no GPU needed) and returns 0 on success. */
+SB200_API int sb200_arena_stats(int device, uint64_t* reserved_bytes, uint64_t* in_use_bytes, uint64_t* peak_bytes,
+                                uint64_t* n_slabs);
+SB200_API int sb200_arena_trim(int device);
+SB200_API int sb200_arena_selftest(uint64_t seed, uint32_t ops);
+
 /* ===========================================================================================
  * Path 2 -- BM25 posting-list scoring + top-k   (declared in stract_b200_bm25.h)
  * =========================================================================================== */

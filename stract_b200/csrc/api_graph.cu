@@ -103,8 +103,9 @@ void sb200_graph_destroy(sb200_graph* g) {
   if (g->ev_run1) cudaEventDestroy(g->ev_run1);
   for (int f = 0; f < sb200_graph::F_COUNT; f++) for (int k = 0; k < 2; k++) if (g->prof_ev[f][k]) cudaEventDestroy(g->prof_ev[f][k]);
   cudaStream_t s = g->stream;
+  const int dev = g->device;
   delete g;  // DevBuf destructors free HBM
-  if (s) cudaStreamDestroy(s);
+  if (s) { arena_retire_stream(dev, s); cudaStreamDestroy(s); }  // the stream is idle: its arena blocks are free for all
 }
 
 int sb200_graph_get_info(const sb200_graph* g, sb200_graph_info* info) {

@@ -52,6 +52,11 @@ struct Err {
 #define SB_CHECK_LAUNCH() SB_CUDA(cudaGetLastError())
 
 extern thread_local cudaStream_t t_pool_stream;
+// opt-in slab arena (arena.h / arena.cu, SB200_ARENA=1): replaces cudaMallocAsync inside a PoolScope
+bool arena_enabled();
+void* arena_alloc(size_t bytes, cudaStream_t stream, int* dev_out);
+void arena_free(void* p, cudaStream_t stream, int dev);
+void arena_retire_stream(int dev, cudaStream_t stream);
 struct PoolScope {
   cudaStream_t prev;
   explicit PoolScope(cudaStream_t s) : prev(t_pool_stream) { t_pool_stream = s; }
@@ -65,23 +70,28 @@ struct DevBuf {
   size_t n = 0;
   cudaStream_t pool_stream = nullptr;  // non-null: stream-ordered allocation (cudaMallocAsync) on that stream
   bool borrowed = false;               // caller-owned memory (sb200_hyperball_bind_state): never freed here
+  int arena_dev = -1;                  // >= 0: block of that device's slab arena, "freed on" pool_stream
   DevBuf() {}
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), pool_stream(o.pool_stream), borrowed(o.borrowed) {
-    o.p = nullptr; o.n = 0; o.pool_stream = nullptr; o.borrowed = false;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), pool_stream(o.pool_stream), borrowed(o.borrowed), arena_dev(o.arena_dev) {
+    o.p = nullptr; o.n = 0; o.pool_stream = nullptr; o.borrowed = false; o.arena_dev = -1;
   }
   DevBuf& operator=(DevBuf&& o) noexcept {
     if (this != &o) {
-      release(); p = o.p; n = o.n; pool_stream = o.pool_stream; borrowed = o.borrowed;
-      o.p = nullptr; o.n = 0; o.pool_stream = nullptr; o.borrowed = false;
+      release(); p = o.p; n = o.n; pool_stream = o.pool_stream; borrowed = o.borrowed; arena_dev = o.arena_dev;
+      o.p = nullptr; o.n = 0; o.pool_stream = nullptr; o.borrowed = false; o.arena_dev = -1;
     }
     return *this;
   }
   ~DevBuf() { release(); }
   void release() {
-    if (p && !borrowed) { if (pool_stream) cudaFreeAsync(p, pool_stream); else cudaFree(p); }
-    p = nullptr; n = 0; pool_stream = nullptr; borrowed = false;
+    if (p && !borrowed) {
+      if (arena_dev >= 0) arena_free(p, pool_stream, arena_dev);
+      else if (pool_stream) cudaFreeAsync(p, pool_stream);
+      else cudaFree(p);
+    }
+    p = nullptr; n = 0; pool_stream = nullptr; borrowed = false; arena_dev = -1;
   }
   void adopt(T* ptr, size_t count) { release(); p = ptr; n = count; borrowed = true; }
   // Inside a PoolScope the buffer comes from the device's stream-ordered memory pool: the staging pipeline
@@ -91,6 +101,9 @@ struct DevBuf {
     release();
     if (count == 0) { n = 0; return SB200_OK; }
     cudaError_t e;
+    if (t_pool_stream && arena_enabled() && (p = (T*)arena_alloc(count * sizeof(T), t_pool_stream, &arena_dev)) != nullptr) {
+      pool_stream = t_pool_stream; n = count; return SB200_OK;
+    }
     if (t_pool_stream) { e = cudaMallocAsync((void**)&p, count * sizeof(T), t_pool_stream); pool_stream = t_pool_stream; }
     else e = cudaMalloc((void**)&p, count * sizeof(T));
     if (e != cudaSuccess) {
