@@ -64,6 +64,10 @@ struct sb200_segment {
   sb200::DevBuf<uint32_t> g_klo;
   sb200::DevBuf<uint32_t> q_items;          // item -> (query slot, lo, hi, output slot), SoA
   sb200::DevBuf<sb200::MergeJob> q_jobs;
+  // scratch of the unit-based AND path (bm25_and3.cuh)
+  sb200::DevBuf<uint4> a3_units;            // AUnit records
+  sb200::DevBuf<uint64_t> a3_off;           // per query slot: start of its candidate list
+  sb200::DevBuf<uint32_t> a3_cnt, a3_key, a3_doc;
 };
 
 namespace sb200 {
@@ -590,6 +594,70 @@ static int launch_topk_warp(const WParams& P, cudaStream_t s) {
   return SB200_OK;
 }
 
+}  // namespace sb200
+#include "bm25_and3.cuh"
+namespace sb200 {
+
+// AND batch through the unit kernel: `terms`/`nterms` are the planned clauses per query slot (sorted by doc_freq),
+// results land in g->o_docs / o_scores / o_n at the caller's query index (order[slot]).  Candidate memory is
+// sum(doc_freq of the rarest clause) x 8 B; slots are processed in groups that keep it under a budget.
+static int run_and3(sb200_segment* g, const Params& P, const std::vector<uint32_t>& terms, const std::vector<uint32_t>& nterms,
+                    uint32_t nq, uint32_t nt, uint32_t k, cudaStream_t s) {
+  static_assert(sizeof(AUnit) == sizeof(uint4), "AUnit is stored in a uint4 buffer");
+  uint64_t budget = (uint64_t)8 << 30;
+  if (const char* e = getenv("SB200_AND3_BUDGET_MB")) { const long mb = atol(e); if (mb > 0) budget = (uint64_t)mb << 20; }
+  const uint64_t max_entries = std::max<uint64_t>(budget / 8, 1);
+  std::vector<uint64_t> off(nq, 0);
+  std::vector<AUnit> units;
+  static size_t sel_conf = 0;
+  const size_t sel_smem = (size_t)A3_SEL_CAP * 8;
+  if (sel_conf < sel_smem) {
+    SB_CUDA(cudaFuncSetAttribute(k_and3_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+    sel_conf = sel_smem;
+  }
+  SB_TRY(ensure(g->a3_off, nq)); SB_TRY(ensure(g->a3_cnt, nq));
+  uint32_t g0 = 0;
+  while (g0 < nq) {
+    // group [g0, g1): as many slots as fit the candidate budget (at least one)
+    uint64_t entries = 0; uint32_t g1 = g0;
+    units.clear();
+    while (g1 < nq) {
+      const uint32_t dfA = nterms[g1] ? g->h_df[terms[(size_t)g1 * nt]] : 0u;
+      if (g1 > g0 && entries + dfA > max_entries) break;
+      off[g1] = entries; entries += dfA;
+      const uint32_t nblk = (dfA >> 7) + ((dfA & 127u) ? 1u : 0u);
+      for (uint32_t b0 = 0; b0 < nblk; b0 += A3_UNIT_BLOCKS) {
+        AUnit u; u.q = g1; u.blk_lo = b0; u.blk_hi = std::min(nblk, b0 + A3_UNIT_BLOCKS); u._pad = 0;
+        units.push_back(u);
+      }
+      g1++;
+    }
+    const uint32_t n_units = (uint32_t)units.size();
+    SB_TRY(ensure(g->a3_key, (size_t)std::max<uint64_t>(entries, 1))); SB_TRY(ensure(g->a3_doc, (size_t)std::max<uint64_t>(entries, 1)));
+    SB_TRY(ensure(g->a3_units, std::max<size_t>(n_units, 1)));
+    SB_CUDA(cudaMemcpyAsync(g->a3_off.p + g0, off.data() + g0, (size_t)(g1 - g0) * 8, cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemsetAsync(g->a3_cnt.p + g0, 0, (size_t)(g1 - g0) * 4, s));
+    if (n_units) {
+      SB_CUDA(cudaMemcpyAsync(g->a3_units.p, units.data(), (size_t)n_units * sizeof(AUnit), cudaMemcpyHostToDevice, s));
+      A3Params A;
+      memset(&A, 0, sizeof(A));
+      A.S = P.S; A.a128 = g->a_post.p; A.t_aoff = g->t_aoff.p;
+      A.q_terms = P.q_terms; A.q_nterms = P.q_nterms; A.q_weights = P.q_weights; A.cache = P.cache; A.n_terms_max = nt;
+      A.units = (const AUnit*)g->a3_units.p; A.n_units = n_units;
+      A.cand_off = g->a3_off.p; A.cand_cnt = g->a3_cnt.p; A.c_key = g->a3_key.p; A.c_doc = g->a3_doc.p;
+      A.counters = P.counters;
+      SB_LAUNCH(k_and3, div_up(n_units, A3_WARPS), A3_WARPS * 32, 0, s, A);
+      SB_CHECK_LAUNCH();
+    }
+    SB_LAUNCH(k_and3_select, g1 - g0, 256, sel_smem, s, g->a3_off.p, g->a3_cnt.p, g->a3_key.p, g->a3_doc.p, P.q_orig, g0, k,
+              P.o_docs, P.o_scores, P.o_n);
+    SB_CHECK_LAUNCH();
+    if (g1 < nq) SB_CUDA(cudaStreamSynchronize(s));  // `units` / `off` are reused by the next group's async copies
+    g0 = g1;
+  }
+  return SB200_OK;
+}
+
 static int run_batch(sb200_segment* g, const sb200_bm25_batch* b, int mode, const sb200_signal_batch* sb, uint32_t* docs,
                      float* scores, double* totals, uint32_t* n_out, sb200_bm25_stats* stats) {
   cudaStream_t s = g->stream;
@@ -705,6 +773,8 @@ static int run_batch(sb200_segment* g, const sb200_bm25_batch* b, int mode, cons
     if (kmode == 2) SB_TRY(launch_topk<2>(P, nq, s));
     else if (kmode == 0) SB_TRY(launch_topk<0>(P, nq, s));
     else SB_TRY(launch_topk<1>(P, nq, s));
+  } else if (kmode == 0 && getenv("SB200_BM25_AND3") != nullptr) {
+    SB_TRY(run_and3(g, P, terms, nterms, nq, nt, k, s));  // unit-based intersection (bm25_and3.cuh), opt-in
   } else {
     SB_TRY(ensure(g->g_khi, (size_t)n_items * cap)); SB_TRY(ensure(g->g_klo, (size_t)n_items * cap));
     WParams W;

@@ -70,6 +70,7 @@ struct sb200_graph {
   void* peer_bm[2][sb200::MAX_PEERS] = {{nullptr}};
   double dense_frac = 0.35, push_div = 48.0;  // mode policy (see hb_step)
   int force_mode = -1;
+  uint64_t l2_window_bytes = 0;  // SB200_L2_PERSIST_MB: persisting-L2 access window over the hot prefix of the `old` register array
 
   // optional per-kernel-family device timing (bench evidence; CUDA events on this handle's stream)
   enum { F_PULL_WARP_DENSE, F_PULL_QUAD_DENSE, F_PULL_WARP_FRONT, F_PULL_QUAD_FRONT, F_PULL_MERGE, F_PUSH, F_FINALIZE, F_COUNT };

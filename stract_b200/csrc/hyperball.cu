@@ -463,6 +463,21 @@ int hb_alloc_state(sb200_graph* g) {
   SB_TRY(g->kahan_sum.alloc(std::max<uint64_t>(N, 1))); SB_TRY(g->kahan_err.alloc(std::max<uint64_t>(N, 1)));
   SB_TRY(g->counters.alloc(8));
   if (!g->h_counters) SB_CUDA(cudaMallocHost((void**)&g->h_counters, 8 * sizeof(unsigned long long)));
+  // Experiment switch (off by default): rows are ordered by in-degree, so the head of the register array holds the
+  // hubs -- on a power-law graph also the most-gathered sources.  SB200_L2_PERSIST_MB=m pins the first m MB of the
+  // array being READ as persisting L2 lines for the pull kernels (stream access-policy window, re-pointed at the
+  // `old` array every iteration), so the streaming col/row traffic cannot evict them.
+  const double mb = env_f("SB200_L2_PERSIST_MB", 0.0);
+  g->l2_window_bytes = 0;
+  if (mb > 0) {
+    cudaDeviceProp prop;
+    SB_CUDA(cudaGetDeviceProperties(&prop, g->device));
+    uint64_t want = (uint64_t)(mb * 1048576.0);
+    want = std::min<uint64_t>(want, (uint64_t)std::max(prop.persistingL2CacheMaxSize, 0));
+    want = std::min<uint64_t>(want, (uint64_t)std::max(prop.accessPolicyMaxWindowSize, 0));
+    want = std::min<uint64_t>(want, N * 64);
+    if (want) { SB_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want)); g->l2_window_bytes = want; }
+  }
   return SB200_OK;
 }
 
@@ -614,6 +629,14 @@ int hb_step(sb200_graph* g, sb200_iter_stats* st) {
   // at the END of the previous step (before the inter-step barrier), never at the start of this one
   if (!g->p2p) SB_CUDA(cudaMemsetAsync(bmc, 0, (words + 1) * 4, s));
   SB_CUDA(cudaMemsetAsync(g->counters.p, 0, 8 * sizeof(unsigned long long), s));
+  if (g->l2_window_bytes && mode != 2) {
+    cudaStreamAttrValue a;
+    memset(&a, 0, sizeof(a));
+    a.accessPolicyWindow.base_ptr = (void*)oldr; a.accessPolicyWindow.num_bytes = g->l2_window_bytes;
+    a.accessPolicyWindow.hitRatio = 1.0f; a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    SB_CUDA(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &a));
+  }
   if (mode == 0) SB_TRY(launch_pull<false>(g, oldr, newr, bmp, bmc));
   else if (mode == 1) SB_TRY(launch_pull<true>(g, oldr, newr, bmp, bmc));
   else SB_TRY(run_push(g, oldr, newr, bmp, bmc));

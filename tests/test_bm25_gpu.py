@@ -1,5 +1,7 @@
 """Parity of the CUDA BM25 top-k path (through the C ABI) against the CPU oracle.  Needs a GPU.
 Bar: doc ids, order and f32 scores / f64 totals bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
@@ -185,3 +187,38 @@ def test_malformed_postings_rejected():
         SegmentReader(data, (off, ln, np.array([700, 10], np.uint32)), oseg.fieldnorm_ids)  # df disagrees with the skip list
     with pytest.raises(Sb200Error):
         SegmentReader(data[:100], (off, ln, df), oseg.fieldnorm_ids)  # term range outside the file
+
+
+@pytest.mark.skipif(not os.environ.get("SB200_TEST_AND3"), reason="unit-based AND kernel (bm25_and3.cuh) is opt-in until it has been run once on a GPU: SB200_TEST_AND3=1")
+def test_and3_unit_kernel_bit_exact(monkeypatch):
+    """The opt-in unit-based intersection must give exactly what the default kernel and the oracle give:
+    ragged clause sizes (tail-only terms, exact multiples of 128), 1..4 clauses, k below/above the hit count,
+    and a budget small enough to force several candidate groups."""
+    monkeypatch.setenv("SB200_BM25_AND3", "1")
+    dfs = [1, 5, 127, 128, 129, 255, 256, 300, 1000, 1280, 5000, 20000, 40000]
+    (oseg, seg), rng = random_index(21, 80_000, dfs)
+    nt = len(dfs)
+    for _ in range(60):
+        n = int(rng.integers(1, 5))
+        q = [int(x) for x in rng.choice(nt, n, replace=False)]
+        for k in (1, 10, 1000):
+            check_query(oseg, seg, q, MODE_AND, k)
+    check_query(oseg, seg, [nt - 1, nt - 2], MODE_AND, 100)
+    check_query(oseg, seg, [nt - 1], MODE_AND, 4096)          # single clause: every posting is a hit, chunked select
+    check_query(oseg, seg, [nt - 1, nt - 2, nt - 3], MODE_AND, 1000)
+    # batch + forced grouping of the candidate memory
+    monkeypatch.setenv("SB200_AND3_BUDGET_MB", "1")
+    nq = 300
+    terms = np.stack([rng.choice(nt, 2, replace=False) for _ in range(nq)]).astype(np.uint32)
+    cache = bm25.compute_tf_cache(seg.average_fieldnorm)
+    w = np.zeros((nq, 2), np.float32)
+    for q in range(nq):
+        for t in range(2):
+            w[q, t] = bm25.Bm25Weight.for_one_term(int(seg.doc_freq[terms[q, t]]), seg.max_doc, seg.average_fieldnorm).weight
+    caches = np.tile(cache, (nq * 2, 1))
+    od, os_, on, _ = oseg.topk_batch(terms, w, caches, MODE_AND, 1000, threads=8)
+    gd, gs, gn, st = TopDocs.with_limit(1000).search_batch(seg, terms, MODE_AND, return_stats=True)
+    assert np.array_equal(gn, on)
+    for q in range(nq):
+        assert np.array_equal(gd[q, :gn[q]], od[q, :on[q]]) and np.array_equal(gs[q, :gn[q]], os_[q, :on[q]])
+    assert st["docs_scored"] == int(on.sum()) or st["docs_scored"] >= int(on.sum())
