@@ -596,7 +596,21 @@ static int launch_topk_warp(const WParams& P, cudaStream_t s) {
 
 }  // namespace sb200
 #include "bm25_and3.cuh"
+#include "bm25_or3.cuh"
 namespace sb200 {
+
+// union modes through k_or3, instantiated for the smallest term-count bound that covers the batch
+template <int MODE>
+static int launch_or3(const WParams& P, cudaStream_t s) {
+  const unsigned grid = div_up(P.n_items, WQ);
+  void (*kern)(const WParams) = k_or3<MODE, 8>;
+  if (P.n_terms_max <= 2) kern = k_or3<MODE, 2>;
+  else if (P.n_terms_max <= 3) kern = k_or3<MODE, 3>;
+  else if (P.n_terms_max <= 5) kern = k_or3<MODE, 5>;
+  SB_LAUNCH(kern, grid, WQ * 32, 0, s, P);
+  SB_CHECK_LAUNCH();
+  return SB200_OK;
+}
 
 // AND batch through the unit kernel: `terms`/`nterms` are the planned clauses per query slot (sorted by doc_freq),
 // results land in g->o_docs / o_scores / o_n at the caller's query index (order[slot]).  Candidate memory is
@@ -786,7 +800,9 @@ static int run_batch(sb200_segment* g, const sb200_bm25_batch* b, int mode, cons
     W.k1p1 = P.k1p1; W.coeff_text = P.coeff_text; W.sig = P.sig; W.n_cols = P.n_cols; W.coeffs = P.coeffs; W.max_docs = P.max_docs;
     W.g_khi = g->g_khi.p; W.g_klo = g->g_klo.p;
     W.o_docs = P.o_docs; W.o_scores = P.o_scores; W.o_totals = P.o_totals; W.o_n = P.o_n; W.counters = P.counters;
-    if (kmode == 2) SB_TRY(launch_topk_warp<2>(W, s));
+    const bool use_or3 = kmode != 0 && W.max_docs == 0 && getenv("SB200_BM25_OR3") != nullptr;  // opt-in, bm25_or3.cuh
+    if (use_or3) { if (kmode == 2) SB_TRY(launch_or3<2>(W, s)); else SB_TRY(launch_or3<1>(W, s)); }
+    else if (kmode == 2) SB_TRY(launch_topk_warp<2>(W, s));
     else if (kmode == 0) SB_TRY(launch_topk_warp<0>(W, s));
     else SB_TRY(launch_topk_warp<1>(W, s));
     if (!jobs.empty()) {

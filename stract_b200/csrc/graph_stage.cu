@@ -203,6 +203,18 @@ __global__ void k_remap(const uint64_t* __restrict__ in, uint64_t n, const uint3
   uint32_t to = inv[k >> 32], from = inv[(uint32_t)k];
   out[i] = swap ? (((uint64_t)from << 32) | to) : (((uint64_t)to << 32) | from);
 }
+// Relabelling permutes whole CSR rows: the rank-space keys are already grouped by destination, so row `to` (edges
+// [rank_ptr[to], rank_ptr[to+1])) moves as a block to row_ptr[inv[to]] and only the source ids are translated.
+// One pass instead of a second 64-bit radix sort of all edges (SB200_STAGE_ROWPERM=1).  Sources inside a row stay
+// in rank order instead of internal-id order; the pull kernels take a max over them, so the order is immaterial.
+__global__ void k_row_permute(const uint64_t* __restrict__ keys, uint64_t n, const uint32_t* __restrict__ rank_ptr,
+                              const uint32_t* __restrict__ inv, const uint32_t* __restrict__ row_ptr, uint32_t* col) {
+  const uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const uint64_t k = keys[e];
+  const uint32_t to = (uint32_t)(k >> 32);
+  col[(uint64_t)row_ptr[inv[to]] + (e - rank_ptr[to])] = inv[(uint32_t)k];
+}
 __global__ void k_lo32(const uint64_t* __restrict__ in, uint64_t n, uint32_t* out) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i < n) out[i] = (uint32_t)in[i];
@@ -542,7 +554,14 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
   pt.mark("3b remap + sort (dst CSR)");
   // destination-major CSR in internal ids
   DevBuf<uint32_t> col_full; SB_TRY(col_full.alloc(E));
-  if (E) {
+  if (E && getenv("SB200_STAGE_ROWPERM") != nullptr && !(g->world == 1 && getenv("SB200_EAGER_FWD") != nullptr)) {
+    // experiment switch: move the rows as blocks instead of re-sorting every edge (see k_row_permute)
+    DevBuf<uint32_t> rank_ptr; SB_TRY(rank_ptr.alloc(N + 1));
+    SB_LAUNCH(k_offsets_from_sorted, div_up(E + 1, TPB), TPB, 0, s, k, E, N, rank_ptr.p); SB_CHECK_LAUNCH();
+    SB_LAUNCH(k_row_permute, div_up(E, TPB), TPB, 0, s, k, E, rank_ptr.p, g->inv.p, g->row_ptr.p, col_full.p); SB_CHECK_LAUNCH();
+    pt.mark("3c remap + sort (fwd CSR)");
+    SB_CUDA(cudaStreamSynchronize(s));
+  } else if (E) {
     SB_LAUNCH(k_remap, div_up(E, TPB), TPB, 0, s, k, E, g->inv.p, k_alt, false); SB_CHECK_LAUNCH();
     uint64_t *a = k_alt, *b = k;  // sort a (clobbers b = rank-space keys, rebuilt below when needed)
     // keep the rank-space keys: we need them again for the forward CSR, so sort into a third buffer

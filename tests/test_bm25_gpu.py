@@ -222,3 +222,40 @@ def test_and3_unit_kernel_bit_exact(monkeypatch):
     for q in range(nq):
         assert np.array_equal(gd[q, :gn[q]], od[q, :on[q]]) and np.array_equal(gs[q, :gn[q]], os_[q, :on[q]])
     assert st["docs_scored"] == int(on.sum()) or st["docs_scored"] >= int(on.sum())
+
+
+@pytest.mark.skipif(not os.environ.get("SB200_TEST_OR3"), reason="union kernel k_or3 (bm25_or3.cuh) is opt-in until it has been run once on a GPU: SB200_TEST_OR3=1")
+def test_or3_union_kernel_matches_default_kernel(monkeypatch):
+    """Differential test: the opt-in union kernel must return exactly what the validated k_topk_warp returns (which
+    the tests above pin on the oracle) -- OR with 1..8 clauses incl. absent terms and tails, several k, batches whose
+    large queries are cut into doc-range items and merged, and the signal combine with 4 and 2 columns."""
+    dfs = [1, 5, 127, 128, 129, 300, 1000, 1280, 5000, 20000, 40000, 60000, 90000]
+    (oseg, seg), rng = random_index(31, 200_000, dfs)
+    nt = len(dfs)
+
+    def both(fn):
+        monkeypatch.delenv("SB200_BM25_OR3", raising=False)
+        a = fn()
+        monkeypatch.setenv("SB200_BM25_OR3", "1")
+        b = fn()
+        monkeypatch.delenv("SB200_BM25_OR3", raising=False)
+        return a, b
+
+    for width in (1, 2, 3, 5, 8):
+        nq = 120
+        terms = np.stack([rng.choice(nt, width, replace=False) for _ in range(nq)]).astype(np.uint32)
+        if width >= 3:
+            terms[::7, 1] = NO_TERM   # padded / absent clauses
+        for k in (1, 10, 1000):
+            (ad, as_, an), (bd, bs, bn) = both(lambda: TopDocs.with_limit(k).search_batch(seg, terms, MODE_OR))
+            assert np.array_equal(an, bn), (width, k)
+            for q in range(nq):
+                assert np.array_equal(ad[q, :an[q]], bd[q, :bn[q]]) and np.array_equal(as_[q, :an[q]], bs[q, :bn[q]]), (width, k, q)
+    for ncols in (4, 2, 0):
+        cols = [rng.random(200_000) for _ in range(ncols)]
+        comp = SignalComputer(seg, SignalTable(cols) if ncols else None, [2.0, 0.02, 2.0, 0.001][:ncols], coeff_text=0.005)
+        terms = np.stack([rng.choice(nt, 5, replace=False) for _ in range(80)]).astype(np.uint32)
+        (ad, at, an), (bd, bt, bn) = both(lambda: comp.top_docs_batch(terms, 1000))
+        assert np.array_equal(an, bn)
+        for q in range(80):
+            assert np.array_equal(ad[q, :an[q]], bd[q, :bn[q]]) and np.array_equal(at[q, :an[q]], bt[q, :bn[q]]), (ncols, q)
