@@ -23,7 +23,9 @@
 #include "common.cuh"
 #include "../../include/stract_b200_bm25.h"
 
+#ifndef SB200_EMU
 #include <cub/cub.cuh>
+#endif
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
@@ -310,7 +312,7 @@ struct Params {
 // MODE 0: AND (tantivy Intersection order), 1: OR (tantivy weights, query-order sum), 2: Stract signal combine
 template <int MODE>
 __global__ void __launch_bounds__(NT) k_topk(const Params P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SB_DYN_SMEM(smem_raw);
   Smem M;
   {
     unsigned char* p = smem_raw;

@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(256) k_and3_select(const uint64_t* __restrict_
                                                      const uint32_t* __restrict__ c_key, const uint32_t* __restrict__ c_doc,
                                                      const uint32_t* __restrict__ q_orig, uint32_t slot0, uint32_t k,
                                                      uint32_t* o_docs, float* o_scores, uint32_t* o_n) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SB_DYN_SMEM(smem_raw);
   uint32_t* kh = (uint32_t*)smem_raw;          // [A3_SEL_CAP]
   uint32_t* kl = kh + A3_SEL_CAP;              // [A3_SEL_CAP]  ~doc
   const uint32_t slot = slot0 + blockIdx.x, tid = threadIdx.x;

@@ -230,10 +230,11 @@ __global__ void __launch_bounds__(WQ * 32) k_or3(const WParams P) {
     __syncwarp();
     if (lane <= T) s_rstart[lane] = incl - cnt;   // lanes >= T have cnt == 0: s_rstart[T] == R
     if (lane < T) s_pos[lane] = my_pos;
+    const uint32_t have = *s_count;   // read before the barrier: behind it other lanes push
     __syncwarp();
-    if (*s_count + R > P.cap) {
-      w_sort_prefix_desc(khi, klo, *s_count, P.cap, lane);
-      const uint32_t c = min(*s_count, P.k);
+    if (have + R > P.cap) {
+      w_sort_prefix_desc(khi, klo, have, P.cap, lane);
+      const uint32_t c = min(have, P.k);
       if (c == P.k) { thr_on = true; thr_hi = khi[P.k - 1]; thr_lo = klo[P.k - 1]; }
       __syncwarp();
       if (lane == 0) *s_count = c;

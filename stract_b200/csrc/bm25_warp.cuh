@@ -169,7 +169,7 @@ __device__ __forceinline__ void w_sort_prefix_desc(uint64_t* khi, uint32_t* klo,
 
 template <int MODE>
 __global__ void __launch_bounds__(WQ * 32) k_topk_warp(const WParams P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SB_DYN_SMEM(smem_raw);
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t TM = P.n_terms_max;
   // layout: cache[256] | per warp: docs[TM][128] tfs[TM][128] st[TM] misc[32]
@@ -285,11 +285,14 @@ __global__ void __launch_bounds__(WQ * 32) k_topk_warp(const WParams P) {
       for (uint32_t s = 0; s < T; s++) { s_rstart[s] = acc; if (MODE != 0 || s == 0) acc += s_rhi[s] - st[s].pos; }
       s_rstart[T] = acc;
     }
+    // the fill level is read by every lane BEFORE the barrier: after it other lanes start pushing, and nothing but
+    // converged execution would order their atomics behind this read (found by the CPU emulator, tests/emu)
+    const uint32_t have = *s_count;
     __syncwarp();
     const uint32_t R = s_rstart[T];
-    if (*s_count + R > P.cap) {
-      w_sort_prefix_desc(khi, klo, *s_count, P.cap, lane);
-      const uint32_t c = min(*s_count, P.k);
+    if (have + R > P.cap) {
+      w_sort_prefix_desc(khi, klo, have, P.cap, lane);
+      const uint32_t c = min(have, P.k);
       if (c == P.k) { thr_on = true; thr_hi = khi[P.k - 1]; thr_lo = klo[P.k - 1]; }
       __syncwarp();
       if (lane == 0) *s_count = c;
@@ -446,7 +449,7 @@ __global__ void __launch_bounds__(WQ * 32) k_topk_warp(const WParams P) {
 template <int MODE>
 __global__ void __launch_bounds__(256) k_merge_topk(const MergeJob* __restrict__ jobs, uint32_t k, uint32_t capm,
                                                     uint32_t* o_docs, float* o_scores, double* o_totals, uint32_t* o_n) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SB_DYN_SMEM(smem_raw);
   uint64_t* khi = (uint64_t*)smem_raw;
   uint32_t* klo = (uint32_t*)(khi + capm);
   const MergeJob job = jobs[blockIdx.x];

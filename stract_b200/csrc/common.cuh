@@ -1,6 +1,8 @@
 // common.cuh -- shared helpers of libstract_b200 (error plumbing, launch accounting, small device utils)
 #pragma once
+#ifndef SB200_EMU   // tests/emu builds the same sources for a CPU SIMT emulator and force-includes its own shim
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -43,11 +45,15 @@ struct Err {
   } while (0)
 
 // every kernel launch goes through this so gpu_launches in bench.py is a counted number
+#ifndef SB200_EMU
 #define SB_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
   do {                                                                    \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);           \
     ::sb200::g_launches.fetch_add(1, std::memory_order_relaxed);          \
   } while (0)
+// dynamic shared memory of a kernel
+#define SB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
 
 #define SB_CHECK_LAUNCH() SB_CUDA(cudaGetLastError())
 
@@ -125,6 +131,7 @@ bool is_device_ptr(const void* p);
 static inline unsigned div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
 
 // ---- device helpers --------------------------------------------------------------------------
+#ifndef SB200_EMU   // inline PTX: path-1 kernels only, not part of the emulated sources
 // Byte-wise unsigned max of 4 packed bytes, valid when every byte is < 128 -- which holds for HyperLogLog<64>
 // registers (rho <= 65, hyperloglog.rs:4385-4396).  sm_100a has no SIMD byte max (`__vmaxu4` is emulated with
 // ~10 LOP3/SHF/PRMT/IADD; ncu showed the pull kernels issue-bound on exactly that), so use 3 instructions:
@@ -158,5 +165,6 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p) {
   asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
+#endif  // SB200_EMU
 
 }  // namespace sb200
