@@ -37,7 +37,13 @@ def lib():
     if not os.path.exists(_SO):
         raise ImportError(f"{_SO} is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(stract_b200 has no CPU fallback)")
-    L = C.CDLL(_SO)
+    _LIB = declare(C.CDLL(_SO))
+    return _LIB
+
+
+def declare(L):
+    """Attach the C-ABI prototypes to a loaded library handle (lib() does this for libstract_b200.so; the CPU
+    emulation tests do it for their own build of the same sources)."""
     vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
 
     def f(name, res, *args):
@@ -77,7 +83,6 @@ def lib():
         _lib_bm25.proto(L, f)
     except ImportError:
         pass
-    _LIB = L
     return L
 
 

@@ -32,7 +32,11 @@ uint64_t sb200_graph::hbm_bytes() const {
 extern "C" {
 
 const char* sb200_last_error(void) { return t_err; }
+#ifndef SB200_EMU
 const char* sb200_version(void) { return "stract_b200 0.1 (sm_100a)"; }
+#else
+const char* sb200_version(void) { return "stract_b200 0.1 CPU SIMT emulation (tests/emu, tests only)"; }
+#endif
 uint64_t sb200_kernel_launch_count(void) { return g_launches.load(); }
 
 #define SB_ENTER(g)                                            \

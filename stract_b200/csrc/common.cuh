@@ -131,7 +131,6 @@ bool is_device_ptr(const void* p);
 static inline unsigned div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
 
 // ---- device helpers --------------------------------------------------------------------------
-#ifndef SB200_EMU   // inline PTX: path-1 kernels only, not part of the emulated sources
 // Byte-wise unsigned max of 4 packed bytes, valid when every byte is < 128 -- which holds for HyperLogLog<64>
 // registers (rho <= 65, hyperloglog.rs:4385-4396).  sm_100a has no SIMD byte max (`__vmaxu4` is emulated with
 // ~10 LOP3/SHF/PRMT/IADD; ncu showed the pull kernels issue-bound on exactly that), so use 3 instructions:
@@ -143,7 +142,11 @@ __device__ __forceinline__ uint32_t bmax4_7bit(uint32_t a, uint32_t b) {
   uint32_t m;
   // generic-mode PRMT: a selector nibble with its msb set replicates the SIGN of the selected byte over the byte
   // (the `__byte_perm` intrinsic masks that bit off, hence the inline PTX)
+#ifndef SB200_EMU
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m) : "r"(d), "r"(0u), "r"(0xba98u));
+#else
+  m = ((d >> 7) & 0x01010101u) * 0xFFu;   // what that PRMT computes (tests/emu)
+#endif
   return (a & m) | (b & ~m);
 }
 __device__ __forceinline__ uint4 vmax_u8x16(uint4 a, uint4 b) {
@@ -155,16 +158,23 @@ __device__ __forceinline__ bool ne_u4(uint4 a, uint4 b) {
 
 // streaming (read-once) 16-byte load: do not allocate in L1, evict-first in L2
 __device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
+#ifndef SB200_EMU
   uint4 v;
   asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
+#else
+  return *p;
+#endif
 }
 __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p) {
+#ifndef SB200_EMU
   uint32_t v;
   asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
+#else
+  return *p;
+#endif
 }
-#endif  // SB200_EMU
 
 }  // namespace sb200

@@ -14,7 +14,9 @@
 // Radix sorts / scans / selects are CUB device primitives (staging, not the hot loop).
 #include "graph.cuh"
 
+#ifndef SB200_EMU
 #include <cub/cub.cuh>
+#endif
 #include <algorithm>
 #include <ctime>
 #include <cstdlib>
@@ -25,9 +27,15 @@ namespace sb200 {
 typedef unsigned __int128 u128;
 
 __device__ __forceinline__ u128 cas128(u128* addr, u128 cmp, u128 val) {
+#ifndef SB200_EMU
   u128 old;
   asm volatile("atom.global.cas.b128 %0, [%1], %2, %3;" : "=q"(old) : "l"(addr), "q"(cmp), "q"(val) : "memory");
   return old;
+#else
+  const u128 old = *addr;   // tests/emu runs one thread at a time
+  if (old == cmp) *addr = val;
+  return old;
+#endif
 }
 __device__ __forceinline__ uint64_t mix64(uint64_t z) {
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;

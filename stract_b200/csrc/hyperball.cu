@@ -33,7 +33,9 @@
 #include "graph.cuh"
 #include "../../include/sb200_hll_tables.h"
 
+#ifndef SB200_EMU
 #include <cub/cub.cuh>
+#endif
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>

@@ -22,18 +22,8 @@ EMU = os.path.join(HERE, "emu")
 @pytest.fixture(scope="module")
 def emulated():
     subprocess.check_call(["make", "-C", EMU], stdout=subprocess.DEVNULL)
-    from stract_b200 import _lib, _lib_bm25
-    L = C.CDLL(os.path.join(EMU, "libsb200_emu.so"))
-
-    def f(name, res, *args):
-        fn = getattr(L, name)
-        fn.restype = res
-        fn.argtypes = list(args)
-
-    f("sb200_last_error", C.c_char_p)
-    f("sb200_version", C.c_char_p)
-    f("sb200_kernel_launch_count", C.c_uint64)
-    _lib_bm25.proto(L, f)
+    from stract_b200 import _lib
+    L = _lib.declare(C.CDLL(os.path.join(EMU, "libsb200_emu.so")))
     assert b"emulation" in L.sb200_version()
     saved = _lib._LIB
     _lib._LIB = L
