@@ -312,6 +312,34 @@ __global__ void k_fwd_keys_items(uint64_t n_items, const uint32_t* __restrict__ 
   const uint32_t e0 = row_ptr[row] + c * (uint32_t)chunk, e1 = min(e0 + (uint32_t)chunk, row_ptr[row + 1]);
   for (uint32_t e = e0 + lane; e < e1; e += 32) keys[e] = ((uint64_t)col[e] << 32) | row;
 }
+// sharded handles: the same keys for the OWNED destination rows only (interleaved 32-row blocks), written densely
+// through own_ptr = exclusive scan of the owned in-degrees
+__global__ void k_owned_deg(const uint32_t* __restrict__ row_ptr, uint64_t n, uint32_t world, uint32_t rank, uint32_t* deg) {
+  const uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (v > n) return;
+  deg[v] = (v < n && ((v >> 5) % world) == rank) ? row_ptr[v + 1] - row_ptr[v] : 0u;
+}
+__global__ void k_fwd_keys_rows_own(uint64_t row_begin, uint64_t row_end, const uint32_t* __restrict__ row_ptr,
+                                    const uint32_t* __restrict__ own_ptr, const uint32_t* __restrict__ col, uint32_t world,
+                                    uint32_t rank, uint64_t* keys) {
+  const uint64_t row = row_begin + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (row >= row_end || ((row >> 5) % world) != rank) return;
+  const uint32_t e0 = row_ptr[row], e1 = row_ptr[row + 1], o0 = own_ptr[row];
+  for (uint32_t e = e0; e < e1; e++) keys[o0 + (e - e0)] = ((uint64_t)col[e] << 32) | (uint32_t)row;
+}
+__global__ void k_fwd_keys_items_own(uint64_t n_items, const uint32_t* __restrict__ item_row, const uint32_t* __restrict__ item_start,
+                                     uint32_t warp_row_begin, const uint32_t* __restrict__ row_ptr,
+                                     const uint32_t* __restrict__ own_ptr, const uint32_t* __restrict__ col, int chunk,
+                                     uint32_t world, uint32_t rank, uint64_t* keys) {
+  const uint64_t item = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  if (item >= n_items) return;
+  const uint32_t lane = threadIdx.x & 31, row = item_row[item];
+  if (((row >> 5) % world) != rank) return;
+  const uint32_t c = (uint32_t)item - item_start[row - warp_row_begin];
+  const uint32_t r0 = row_ptr[row], e0 = r0 + c * (uint32_t)chunk, e1 = min(e0 + (uint32_t)chunk, row_ptr[row + 1]);
+  const uint32_t o0 = own_ptr[row];
+  for (uint32_t e = e0 + lane; e < e1; e += 32) keys[o0 + (e - r0)] = ((uint64_t)col[e] << 32) | row;
+}
 // CSR offsets from keys sorted by their high word: ptr[r] = first index whose row >= r (no atomics)
 __global__ void k_offsets_from_sorted(const uint64_t* __restrict__ keys, uint64_t n, uint64_t n_rows, uint32_t* ptr) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -665,13 +693,34 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
 }
 
 int build_fwd_csr(sb200_graph* g) {
-  if (g->has_fwd || g->world != 1) return SB200_OK;
+  if (g->has_fwd) return SB200_OK;
   cudaStream_t s = g->stream;
-  const uint64_t N = g->N, E = g->E_kept;
+  const uint64_t N = g->N;
+  // a sharded handle pushes only into the rows it owns: its source-major CSR holds the E_local edges whose
+  // destination is owned (every rank resolves the whole frontier against its own slice)
+  const uint64_t E = g->world == 1 ? g->E_kept : g->E_local;
   const int TPB = 256;
   SB_TRY(g->fwd_ptr.alloc(N + 1));
-  if (E == 0) { SB_CUDA(cudaMemsetAsync(g->fwd_ptr.p, 0, (N + 1) * 4, s)); g->has_fwd = true; return SB200_OK; }
+  if (E == 0) { SB_CUDA(cudaMemsetAsync(g->fwd_ptr.p, 0, (N + 1) * 4, s)); SB_CUDA(cudaStreamSynchronize(s)); g->has_fwd = true; return SB200_OK; }
   DevBuf<uint64_t> ka, kb; SB_TRY(ka.alloc(E)); SB_TRY(kb.alloc(E));
+  if (g->world > 1) {
+    DevBuf<uint32_t> deg, own_ptr; SB_TRY(deg.alloc(N + 1)); SB_TRY(own_ptr.alloc(N + 1));
+    SB_LAUNCH(k_owned_deg, div_up(N + 1, TPB), TPB, 0, s, g->row_ptr.p, N, (uint32_t)g->world, (uint32_t)g->rank, deg.p);
+    SB_CHECK_LAUNCH();
+    SB_TRY(exclusive_scan_u32(g->cub_tmp, deg.p, own_ptr.p, N + 1, s));
+    if (g->n_items) {
+      SB_LAUNCH(k_fwd_keys_items_own, div_up(g->n_items * 32, TPB), TPB, 0, s, g->n_items, g->item_row.p, g->item_start.p,
+                (uint32_t)g->warp_row_begin, g->row_ptr.p, own_ptr.p, g->col.p, CHUNK_EDGES, (uint32_t)g->world,
+                (uint32_t)g->rank, ka.p);
+      SB_CHECK_LAUNCH();
+    }
+    if (g->quad_row_end > g->quad_row_begin) {
+      SB_LAUNCH(k_fwd_keys_rows_own, div_up(g->quad_row_end - g->quad_row_begin, TPB), TPB, 0, s, g->quad_row_begin,
+                g->quad_row_end, g->row_ptr.p, own_ptr.p, g->col.p, (uint32_t)g->world, (uint32_t)g->rank, ka.p);
+      SB_CHECK_LAUNCH();
+    }
+    SB_CUDA(cudaStreamSynchronize(s));  // deg / own_ptr go out of scope
+  } else {
   if (g->n_items) {
     SB_LAUNCH(k_fwd_keys_items, div_up(g->n_items * 32, TPB), TPB, 0, s, g->n_items, g->item_row.p, g->item_start.p,
               (uint32_t)g->warp_row_begin, g->row_ptr.p, g->col.p, CHUNK_EDGES, ka.p);
@@ -681,6 +730,7 @@ int build_fwd_csr(sb200_graph* g) {
     SB_LAUNCH(k_fwd_keys_rows, div_up(g->quad_row_end - g->quad_row_begin, TPB), TPB, 0, s, g->quad_row_begin, g->quad_row_end,
               g->row_ptr.p, g->col.p, ka.p);
     SB_CHECK_LAUNCH();
+  }
   }
   uint64_t *a = ka.p, *b = kb.p;
   SB_TRY(sort_keys<uint64_t>(g->cub_tmp, a, b, E, 0, 32 + bits_for(N), s));

@@ -308,26 +308,45 @@ __global__ void __launch_bounds__(256) k_pull_merge(uint64_t n_rows, const uint3
 }
 
 // ---- push from a small frontier (update_changed_counters, harmonic.rs:75-114) --------------------------
+// slot_sum (sharded handles): total of the out-degrees, i.e. the number of push slots of this rank
 __global__ void k_frontier_compact(const uint32_t* __restrict__ bm, uint64_t words, const uint32_t* __restrict__ fwd_ptr,
-                                   uint32_t* list, uint32_t* outdeg, unsigned long long* counter) {
+                                   uint32_t* list, uint32_t* outdeg, unsigned long long* counter,
+                                   unsigned long long* slot_sum) {
   uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (w >= words) return;
   uint32_t m = bm[w];
   if (!m) return;
   unsigned long long pos = atomicAdd(counter, (unsigned long long)__popc(m));
+  unsigned long long sum = 0;
   while (m) {
     int b = __ffs(m) - 1; m &= m - 1;
     uint32_t v = (uint32_t)(w * 32 + b);
-    list[pos] = v; outdeg[pos] = fwd_ptr[v + 1] - fwd_ptr[v]; pos++;
+    const uint32_t d = fwd_ptr[v + 1] - fwd_ptr[v];
+    list[pos] = v; outdeg[pos] = d; pos++; sum += d;
   }
+  if (slot_sum && sum) atomicAdd(slot_sum, sum);
 }
+// refresh the two-iteration-old rows of the frontier nodes; a sharded handle refreshes the rows it owns (the others
+// arrive from their owners)
 __global__ void k_copy_stale(const uint32_t* __restrict__ list, uint64_t n, const uint4* __restrict__ oldr,
-                             uint4* __restrict__ newr) {
+                             uint4* __restrict__ newr, uint32_t world, uint32_t rank) {
   uint64_t gt = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   uint64_t i = gt >> 2;
   if (i >= n) return;
   uint64_t v = list[i];
+  if (world > 1 && ((v >> 5) % world) != rank) return;
   newr[v * 4 + (gt & 3)] = oldr[v * 4 + (gt & 3)];
+}
+// fused exchange after a push: every owned row that was refreshed or changed in this iteration goes to the peers
+// (one quad per row, 16-B stores; the frontier is small by construction)
+__global__ void k_publish_rows(const uint32_t* __restrict__ bm_prev, const uint32_t* __restrict__ bm_cur, uint64_t n_rows,
+                               const uint4* __restrict__ newr, const PeerOut peers) {
+  const uint64_t gt = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t row = gt >> 2;
+  if (row >= n_rows || !owned_row(peers, (uint32_t)row)) return;
+  if (!(bm_test(bm_prev, (uint32_t)row) || bm_test(bm_cur, (uint32_t)row))) return;
+  const uint4 v = newr[row * 4 + (gt & 3)];
+  for (int p = 0; p < peers.n; p++) peers.newr[p][row * 4 + (gt & 3)] = v;
 }
 __global__ void __launch_bounds__(256) k_push(const uint32_t* __restrict__ list, const uint32_t* __restrict__ off,
     uint32_t n_front, uint64_t n_slots, const uint32_t* __restrict__ fwd_ptr, const uint32_t* __restrict__ fwd_dst,
@@ -540,21 +559,28 @@ static int launch_pull(sb200_graph* g, const uint4* oldr, uint4* newr, const uin
 static int run_push(sb200_graph* g, const uint4* oldr, uint4* newr, const uint32_t* bmp, uint32_t* bmc) {
   cudaStream_t s = g->stream;
   const uint64_t N = g->N, words = (N + 31) / 32;
-  const uint64_t nf = g->n_changed_prev, slots = g->frontier_edges_prev;
+  const uint64_t nf = g->n_changed_prev;
   if (nf == 0) return SB200_OK;  // empty frontier: a converged state is a fixed point
   if (g->frontier_list.n < nf + 1) { SB_TRY(g->frontier_list.alloc(nf + 1 + (nf >> 2))); }
   if (g->frontier_off.n < 2 * (nf + 1)) { SB_TRY(g->frontier_off.alloc(2 * (nf + 1) + (nf >> 1))); }
   uint32_t* outdeg = g->frontier_off.p + (g->frontier_off.n / 2);
-  SB_CUDA(cudaMemsetAsync(g->counters.p + 2, 0, sizeof(unsigned long long), s));
+  SB_CUDA(cudaMemsetAsync(g->counters.p + 2, 0, 2 * sizeof(unsigned long long), s));
   SB_LAUNCH(k_frontier_compact, div_up(words, 256), 256, 0, s, bmp, words, g->fwd_ptr.p, g->frontier_list.p, outdeg,
-            g->counters.p + 2);
+            g->counters.p + 2, g->world > 1 ? g->counters.p + 3 : (unsigned long long*)nullptr);
   SB_CHECK_LAUNCH();
+  uint64_t slots = g->frontier_edges_prev;
+  if (g->world > 1) {   // this rank's share of the frontier's out-edges is not known from the previous step
+    unsigned long long h = 0;
+    SB_CUDA(cudaMemcpyAsync(&h, g->counters.p + 3, sizeof(h), cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    slots = h;
+  }
   size_t need = 0;
   SB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, outdeg, g->frontier_off.p, (int64_t)nf, s));
   if (g->cub_tmp.n < need) SB_TRY(g->cub_tmp.alloc(need + 256));
   SB_CUDA(cub::DeviceScan::ExclusiveSum(g->cub_tmp.p, need, outdeg, g->frontier_off.p, (int64_t)nf, s));
   g_launches.fetch_add(2, std::memory_order_relaxed);
-  SB_LAUNCH(k_copy_stale, div_up(nf * 4, 256), 256, 0, s, g->frontier_list.p, nf, oldr, newr);
+  SB_LAUNCH(k_copy_stale, div_up(nf * 4, 256), 256, 0, s, g->frontier_list.p, nf, oldr, newr, (uint32_t)g->world, (uint32_t)g->rank);
   SB_CHECK_LAUNCH();
   if (slots) {
     unsigned grid = (unsigned)std::min<uint64_t>(div_up(slots * 16, 256), 148u * 16u);
@@ -563,6 +589,12 @@ static int run_push(sb200_graph* g, const uint4* oldr, uint4* newr, const uint32
               g->fwd_dst.p, (const uint32_t*)oldr, (uint32_t*)newr, bmc);
     SB_CHECK_LAUNCH();
     PROF_END(g, sb200_graph::F_PUSH, 132.0 * (double)slots);
+  }
+  if (g->p2p && g->n_peers > 0) {
+    PeerOut po; po.n = g->n_peers; po.world = (uint32_t)g->world; po.rank = (uint32_t)g->rank;
+    for (int p = 0; p < g->n_peers; p++) { po.newr[p] = (uint4*)g->peer_regs[g->cur ^ 1][p]; po.bmc[p] = nullptr; }
+    SB_LAUNCH(k_publish_rows, div_up(N * 4, 256), 256, 0, s, bmp, bmc, N, (const uint4*)newr, po);
+    SB_CHECK_LAUNCH();
   }
   return SB200_OK;
 }
@@ -623,9 +655,17 @@ int hb_step(sb200_graph* g, sb200_iter_stats* st) {
       mode = ((double)g->n_changed_prev >= 0.75 * (double)N) ? 0 : 1;
     }
   } else {
-    mode = ((double)g->n_changed_prev >= 0.25 * (double)N) ? 0 : 1;
+    // sharded handles: the same lazy rule for the source-major CSR (of the owned rows); every rank sees the same
+    // global changed count, so all ranks switch together
+    // (checked on the CPU emulator with 2 and 3 ranks, both exchanges; the automatic switch stays opt-in --
+    // SB200_SHARDED_PUSH=1 -- until it has run on a multi-GPU box; force_mode == 2 always works)
+    static const bool auto_push = getenv("SB200_SHARDED_PUSH") != nullptr;
+    const bool tiny = (double)g->n_changed_prev * 64.0 <= (double)N;
+    if (!g->has_fwd && ((auto_push && g->reuse > 0 && g->t > 0 && tiny) || force_mode == 2)) SB_TRY(build_fwd_csr(g));
+    if (g->has_fwd && tiny) mode = 2;
+    else mode = ((double)g->n_changed_prev >= 0.25 * (double)N) ? 0 : 1;
   }
-  if (force_mode >= 0 && (force_mode < 2 || (g->has_fwd && g->world == 1))) mode = force_mode;
+  if (force_mode >= 0 && (force_mode < 2 || g->has_fwd)) mode = force_mode;
   SB_CUDA(cudaEventRecord(g->ev0, s));
   // peers write their changed bits straight into this rank's bitmap, so with the fused exchange it is cleared
   // at the END of the previous step (before the inter-step barrier), never at the start of this one

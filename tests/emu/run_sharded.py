@@ -7,6 +7,8 @@ import ctypes as C
 import os
 import sys
 
+os.environ["SB200_SHARDED_PUSH"] = "1"   # the automatic switch to push on reused sharded handles is opt-in
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, os.path.dirname(HERE))
@@ -20,37 +22,66 @@ from oracle import DenseHyperBall, hyperball_faithful
 def aligned(nbytes, dtype):
     raw = np.zeros(nbytes + 64, np.uint8); off = (-raw.ctypes.data) % 64
     return raw[off:off + nbytes].view(dtype), raw
-for world in (2, 3):
+def np_view(ptr, nbytes, dtype):
+    return np.frombuffer((C.c_uint8 * nbytes).from_address(ptr), dtype=dtype)
+
+
+def run(world, fused, force_mode, reuse):
     d = synth.rmat_graph(3000, 40000, seed=7)
     g = Webgraph.from_arrays(d["from_lo"], d["from_hi"], d["to_lo"], d["to_hi"], d["rel_flags"])
     hs = [DeviceGraph(g, device=0, rank=r, world_size=world) for r in range(world)]
-    rb, bb = C.c_uint64(), C.c_uint64()
-    check(L.sb200_hyperball_state_bytes(hs[0]._h, C.byref(rb), C.byref(bb)))
-    bufs = []
-    for r in range(world):
-        b = [aligned(rb.value, np.uint8), aligned(rb.value, np.uint8), aligned(bb.value, np.uint32), aligned(bb.value, np.uint32)]
-        bufs.append(b)
-        check(L.sb200_hyperball_bind_state(hs[r]._h, *(x[0].ctypes.data for x in b)))
-    for r in range(world):
-        peers = [p for p in range(world) if p != r]
-        cols = [(C.c_uint64 * len(peers))(*(bufs[p][i][0].ctypes.data for p in peers)) for i in range(4)]
-        check(L.sb200_hyperball_set_publish_targets(hs[r]._h, len(peers), *cols))
-    ref = DenseHyperBall(d["from_lo"], d["from_hi"], d["to_lo"], d["to_hi"], d["rel_flags"])
-    t = 0
-    while True:
-        sts = [h.step() for h in hs]
-        total = sum(s["n_changed"] for s in sts)
-        for h in hs: h.exchange_done(total)
-        ch = ref.step(); t += 1
-        regs = [h.registers() for h in hs]
-        assert all(np.array_equal(regs[0], x) for x in regs[1:]), ("replicas differ", t)
-        assert np.array_equal(regs[0], ref.registers()), ("registers differ from the oracle", t)
-        assert (total == 0) == (not ch), (t, total, ch)
-        if total == 0: break
-    lo = np.concatenate([h.result()[0] for h in hs]); hi = np.concatenate([h.result()[1] for h in hs]); c = np.concatenate([h.result()[2] for h in hs])
+    keep = []
+    if fused:
+        rb, bb = C.c_uint64(), C.c_uint64()
+        check(L.sb200_hyperball_state_bytes(hs[0]._h, C.byref(rb), C.byref(bb)))
+        bufs = []
+        for r in range(world):
+            b = [aligned(rb.value, np.uint8), aligned(rb.value, np.uint8), aligned(bb.value, np.uint32), aligned(bb.value, np.uint32)]
+            bufs.append(b); keep.append(b)
+            check(L.sb200_hyperball_bind_state(hs[r]._h, *(x[0].ctypes.data for x in b)))
+        for r in range(world):
+            peers = [p for p in range(world) if p != r]
+            cols = [(C.c_uint64 * len(peers))(*(bufs[p][i][0].ctypes.data for p in peers)) for i in range(4)]
+            check(L.sb200_hyperball_set_publish_targets(hs[r]._h, len(peers), *cols))
+    for h in hs:
+        h.set_policy(force_mode=force_mode)
     f = hyperball_faithful(d["from_lo"], d["from_hi"], d["to_lo"], d["to_hi"], d["rel_flags"])
-    key = hi.astype(object) * (1 << 64) + lo.astype(object); o = np.argsort(key)
-    assert np.array_equal(lo[o], f["ids_lo"]) and np.array_equal(c[o], f["centrality"]) and t == f["iters"]
+    modes_seen = set()
+    for rep in range(2 if reuse else 1):
+        if rep:
+            for h in hs: h.reset()
+        ref = DenseHyperBall(d["from_lo"], d["from_hi"], d["to_lo"], d["to_hi"], d["rel_flags"])
+        t = 0
+        while True:
+            sts = [h.step() for h in hs]
+            modes_seen.update(s_["mode"] for s_ in sts)
+            total = sum(s_["n_changed"] for s_ in sts)
+            if not fused:   # the collective exchange: elementwise byte max over the replicas (what the NCCL MAX all-reduce does)
+                ptrs = [h.exchange_ptrs() for h in hs]
+                regs = [np_view(p[0], p[1], np.uint8) for p in ptrs]; fr = [np_view(p[2], p[3], np.uint8) for p in ptrs]
+                mr = np.maximum.reduce(regs); mf = np.maximum.reduce(fr)
+                for x in regs: x[:] = mr
+                for x in fr: x[:] = mf
+            for h in hs: h.exchange_done(total)
+            ch = ref.step(); t += 1
+            regs = [h.registers() for h in hs]
+            assert all(np.array_equal(regs[0], x) for x in regs[1:]), ("replicas differ", world, fused, force_mode, t)
+            assert np.array_equal(regs[0], ref.registers()), ("registers differ from the oracle", world, fused, force_mode, t)
+            assert (total == 0) == (not ch), (t, total, ch)
+            if total == 0: break
+        res = [h.result() for h in hs]
+        lo = np.concatenate([r[0] for r in res]); hi = np.concatenate([r[1] for r in res]); c = np.concatenate([r[2] for r in res])
+        key = hi.astype(object) * (1 << 64) + lo.astype(object); o = np.argsort(key)
+        assert np.array_equal(lo[o], f["ids_lo"]) and np.array_equal(c[o], f["centrality"]) and t == f["iters"], (world, fused, force_mode, rep)
     for h in hs: h.close()
-    print("world", world, "fused exchange by address: ok,", t, "iterations")
+    print("world", world, "fused" if fused else "collective", "force_mode", force_mode, "reuse", reuse, "modes", sorted(modes_seen), "ok", flush=True)
+    return modes_seen
+
+
+for world in (2, 3):
+    for fused in (True, False):
+        run(world, fused, -1, False)
+        run(world, fused, 2, False)                 # push on every iteration, owned-row source-major CSR
+        m = run(world, fused, -1, True)             # the policy builds it lazily on the second run and switches to push
+        assert 2 in m, m
 print("sharded emulated parity ok")
