@@ -43,3 +43,5 @@ r = bm25_bench.run_and(0, peaks, cpu=False)
 print({k: r[k] for k in ("value", "kernel_ms_per_batch", "docs_scored", "blocks_decoded")}, "e2e", r["e2e"]["ms_per_batch"])
 PY
 done
+
+# ---- 2-GPU follow-up (separate call: gpurun --gpus 2 --timeout 600 -- 'bash tools/gpu_r2_trip2.sh') is in tools/gpu_r2_trip2.sh
