@@ -130,6 +130,15 @@ SB200_API int sb200_hyperball_get_profile(sb200_graph* g, sb200_kernel_prof* out
 SB200_API int sb200_hyperball_result(sb200_graph* g, uint64_t* id_lo, uint64_t* id_hi, double* centrality,
                            uint64_t cap, uint64_t* len);
 
+/* Rank assignment, the step right behind the centrality computation: store_harmonic sorts
+ * (Reverse(SortableFloat(centrality)), node_id) and writes the position as `harmonic_rank`
+ * (crates/core/src/webgraph/centrality/mod.rs:88-108); top_nodes takes the k largest (centrality, node_id) pairs
+ * (mod.rs:17-37).  Output: the nodes with centrality > 0 ordered by centrality descending (f64 total order), ties by
+ * node id ascending (ties_desc == 0: entry i has harmonic rank i) or descending (ties_desc != 0: top_nodes' order);
+ * at most `cap` leading entries are written, *len = number of ranked nodes.  Single-rank handles only. */
+SB200_API int sb200_hyperball_ranked(sb200_graph* g, int ties_desc, uint64_t* id_lo, uint64_t* id_hi, double* centrality,
+                                     uint64_t cap, uint64_t* len);
+
 /* Parity/debug hooks: state of nodes [first, first+count) in ascending-u128-id (rank) order. */
 SB200_API int sb200_hyperball_registers(sb200_graph* g, uint64_t first, uint64_t count, uint8_t* out /* count*64 */);
 SB200_API int sb200_hyperball_kahan(sb200_graph* g, uint64_t first, uint64_t count, double* sum, double* err);

@@ -215,3 +215,17 @@ class DenseHyperBall:
             self.close()
         except Exception:
             pass
+
+
+def harmonic_ranks(ids_lo, ids_hi, values, ties_desc=False):
+    """Order of store_harmonic's rank pass (crates/core/src/webgraph/centrality/mod.rs:88-108): sort by
+    (Reverse(SortableFloat(centrality)), node_id) -- centrality descending under total_cmp, node id ascending; with
+    ties_desc the order of top_nodes (mod.rs:17-37): the largest (centrality, node_id) pairs first.  Returns the
+    permutation of the input (test infrastructure, numpy)."""
+    import numpy as np
+    lo = np.asarray(ids_lo, np.uint64); hi = np.asarray(ids_hi, np.uint64); v = np.asarray(values, np.float64)
+    bits = v.view(np.uint64)
+    key = np.where(bits >> np.uint64(63), ~bits, bits | np.uint64(1 << 63))   # total_cmp order as unsigned integers
+    if ties_desc:
+        return np.lexsort((~lo, ~hi, ~key))
+    return np.lexsort((lo, hi, ~key))

@@ -66,6 +66,7 @@ def declare(L):
     f("sb200_hyperball_get_profile", i32, vp, C.POINTER(KernelProf), u32, C.POINTER(u32))
     f("sb200_synth_edges", i32, i32, u64, u64, u64, u64, i32, i32, vp, vp, vp, vp, vp)
     f("sb200_hyperball_result", i32, vp, vp, vp, vp, u64, C.POINTER(u64))
+    f("sb200_hyperball_ranked", i32, vp, i32, vp, vp, vp, u64, C.POINTER(u64))
     f("sb200_hyperball_registers", i32, vp, u64, u64, vp)
     f("sb200_hyperball_kahan", i32, vp, u64, u64, vp, vp)
     f("sb200_graph_node_ids", i32, vp, u64, u64, vp, vp)

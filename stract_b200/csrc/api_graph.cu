@@ -18,6 +18,7 @@ int hb_reset(sb200_graph* g);
 int hb_step(sb200_graph* g, sb200_iter_stats* st);
 int hb_result(sb200_graph* g, uint64_t* id_lo, uint64_t* id_hi, double* cent, uint64_t cap, uint64_t* len);
 int hb_registers(sb200_graph* g, uint64_t first, uint64_t count, uint8_t* out);
+int hb_ranked(sb200_graph* g, int ties_desc, uint64_t* id_lo, uint64_t* id_hi, double* cent, uint64_t cap, uint64_t* len);
 int hb_kahan(sb200_graph* g, uint64_t first, uint64_t count, double* sum, double* err);
 }  // namespace sb200
 using namespace sb200;
@@ -187,6 +188,13 @@ int sb200_hyperball_result(sb200_graph* g, uint64_t* id_lo, uint64_t* id_hi, dou
   if (!len) SB_FAIL(SB200_EINVAL, "len is NULL");
   if (centrality && (!id_lo || !id_hi)) SB_FAIL(SB200_EINVAL, "id outputs are NULL");
   return hb_result(g, id_lo, id_hi, centrality, cap, len);
+}
+
+int sb200_hyperball_ranked(sb200_graph* g, int ties_desc, uint64_t* id_lo, uint64_t* id_hi, double* centrality, uint64_t cap, uint64_t* len) {
+  SB_ENTER(g);
+  if (!len) SB_FAIL(SB200_EINVAL, "len is NULL");
+  if (centrality && (!id_lo || !id_hi)) SB_FAIL(SB200_EINVAL, "id outputs are NULL");
+  return hb_ranked(g, ties_desc, id_lo, id_hi, centrality, cap, len);
 }
 
 int sb200_hyperball_registers(sb200_graph* g, uint64_t first, uint64_t count, uint8_t* out) { SB_ENTER(g); return hb_registers(g, first, count, out); }

@@ -767,6 +767,72 @@ int hb_result(sb200_graph* g, uint64_t* id_lo, uint64_t* id_hi, double* cent, ui
   return SB200_OK;
 }
 
+// ---- rank assignment (store_harmonic's second pass, crates/core/src/webgraph/centrality/mod.rs:88-108) -----------
+// key = ~order-preserving bits of the centrality (ascending key == descending f64 total order); the stable radix sort
+// keeps the input order among equal keys, so feeding the nodes in ascending (descending) id order yields the
+// (centrality desc, id asc) order of the rank store, or top_nodes' (centrality, id) descending order (mod.rs:17-37)
+__global__ void k_rank_keys(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos, const double* __restrict__ val,
+                            uint64_t N, uint32_t total, int ties_desc, uint64_t* keys, uint32_t* ranks) {
+  const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (r >= N || !flag[r]) return;
+  const uint32_t p = ties_desc ? total - 1u - pos[r] : pos[r];
+  const uint64_t b = (uint64_t)__double_as_longlong(val[r]);
+  keys[p] = ~((b >> 63) ? ~b : (b | 0x8000000000000000ull));
+  ranks[p] = (uint32_t)r;
+}
+__global__ void k_rank_gather(const uint32_t* __restrict__ order, const double* __restrict__ val, const uint64_t* __restrict__ id_lo,
+                              const uint64_t* __restrict__ id_hi, uint64_t k, uint64_t* out_lo, uint64_t* out_hi, double* out_c) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= k) return;
+  const uint32_t r = order[i];
+  out_lo[i] = id_lo[r]; out_hi[i] = id_hi[r]; out_c[i] = val[r];
+}
+
+int hb_ranked(sb200_graph* g, int ties_desc, uint64_t* id_lo, uint64_t* id_hi, double* cent, uint64_t cap, uint64_t* len) {
+  cudaStream_t s = g->stream;
+  const uint64_t N = g->N;
+  if (g->world != 1) SB_FAIL(SB200_ESTATE, "ranking needs every node: gather the sharded results first");
+  if (N == 0) { *len = 0; return SB200_OK; }
+  PoolScope scope(getenv("SB200_NO_POOL") ? nullptr : s);
+  DevBuf<uint32_t> flag, pos; DevBuf<double> val;
+  SB_TRY(flag.alloc(N + 1)); SB_TRY(pos.alloc(N + 1)); SB_TRY(val.alloc(N));
+  SB_CUDA(cudaMemsetAsync(flag.p + N, 0, 4, s));
+  SB_LAUNCH(k_result_flags, div_up(N, 256), 256, 0, s, g->inv.p, g->kahan_sum.p, N, g->row_begin, g->row_end, (double)(N - 1), flag.p,
+            val.p, 1u, 0u);
+  SB_CHECK_LAUNCH();
+  size_t need = 0;
+  SB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, flag.p, pos.p, (int64_t)(N + 1), s));
+  if (g->cub_tmp.n < need) SB_TRY(g->cub_tmp.alloc(need + 256));
+  SB_CUDA(cub::DeviceScan::ExclusiveSum(g->cub_tmp.p, need, flag.p, pos.p, (int64_t)(N + 1), s));
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  uint32_t total = 0;
+  SB_CUDA(cudaMemcpyAsync(&total, pos.p + N, 4, cudaMemcpyDeviceToHost, s));
+  SB_CUDA(cudaStreamSynchronize(s));
+  *len = total;
+  const uint64_t k = std::min<uint64_t>(total, cap);
+  if (!cent || k == 0) return SB200_OK;
+  DevBuf<uint64_t> ka, kb; DevBuf<uint32_t> va, vb;
+  SB_TRY(ka.alloc(total)); SB_TRY(kb.alloc(total)); SB_TRY(va.alloc(total)); SB_TRY(vb.alloc(total));
+  SB_LAUNCH(k_rank_keys, div_up(N, 256), 256, 0, s, flag.p, pos.p, val.p, N, total, ties_desc, ka.p, va.p);
+  SB_CHECK_LAUNCH();
+  cub::DoubleBuffer<uint64_t> dk(ka.p, kb.p);
+  cub::DoubleBuffer<uint32_t> dv(va.p, vb.p);
+  need = 0;
+  SB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, (int64_t)total, 0, 64, s));
+  if (g->cub_tmp.n < need) SB_TRY(g->cub_tmp.alloc(need + 256));
+  SB_CUDA(cub::DeviceRadixSort::SortPairs(g->cub_tmp.p, need, dk, dv, (int64_t)total, 0, 64, s));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  DevBuf<uint64_t> olo, ohi; DevBuf<double> oc;
+  SB_TRY(olo.alloc(k)); SB_TRY(ohi.alloc(k)); SB_TRY(oc.alloc(k));
+  SB_LAUNCH(k_rank_gather, div_up(k, 256), 256, 0, s, dv.Current(), val.p, g->id_lo.p, g->id_hi.p, k, olo.p, ohi.p, oc.p);
+  SB_CHECK_LAUNCH();
+  SB_CUDA(cudaMemcpyAsync(id_lo, olo.p, k * 8, cudaMemcpyDefault, s));
+  SB_CUDA(cudaMemcpyAsync(id_hi, ohi.p, k * 8, cudaMemcpyDefault, s));
+  SB_CUDA(cudaMemcpyAsync(cent, oc.p, k * 8, cudaMemcpyDefault, s));
+  SB_CUDA(cudaStreamSynchronize(s));
+  return SB200_OK;
+}
+
 int hb_registers(sb200_graph* g, uint64_t first, uint64_t count, uint8_t* out) {
   if (first + count > g->N) SB_FAIL(SB200_EINVAL, "register range [%llu,+%llu) outside %llu nodes", (unsigned long long)first, (unsigned long long)count, (unsigned long long)g->N);
   if (!count) return SB200_OK;

@@ -180,6 +180,19 @@ class DeviceGraph:
         k = ln.value
         return lo[:k], hi[:k], c[:k]
 
+    def ranked(self, ties_desc=False, limit=None):
+        """Nodes with centrality > 0 in rank order: centrality descending (f64 total order), ties by node id ascending
+        (entry i has harmonic rank i, store_harmonic, webgraph/centrality/mod.rs:88-108) or -- ties_desc -- descending
+        (top_nodes' order, mod.rs:17-37).  `limit` keeps the leading entries only."""
+        n = self.info()["n_nodes"]
+        cap = n if limit is None else min(int(limit), n)
+        ln = C.c_uint64(0)
+        lo = host_out(cap, np.uint64); hi = host_out(cap, np.uint64); c = host_out(cap, np.float64)
+        check(self._L.sb200_hyperball_ranked(self._h, 1 if ties_desc else 0, lo.ctypes.data if cap else None,
+                                              hi.ctypes.data if cap else None, c.ctypes.data if cap else None, cap, C.byref(ln)))
+        k = min(ln.value, cap)
+        return lo[:k], hi[:k], c[:k], ln.value
+
     def registers(self, first=0, count=None):
         n = self.info()["n_nodes"]
         count = n - first if count is None else count
@@ -296,7 +309,7 @@ class HarmonicCentrality:
         self._map = None
 
     @classmethod
-    def calculate(cls, graph, device=0, max_iters=0):
+    def calculate(cls, graph, device=0, max_iters=0, with_ranks=False, top=1_000_000):
         import time
         t0 = time.perf_counter()
         dg = DeviceGraph(graph, device=device)
@@ -307,13 +320,31 @@ class HarmonicCentrality:
             lo, hi, c = dg.result()
             t3 = time.perf_counter()
             info = dg.info()
+            ranks = None
+            if with_ranks:   # Centrality::build_harmonic: store_harmonic's rank pass + top_nodes (entrypoint/centrality.rs:41-71)
+                rlo, rhi, _, _ = dg.ranked(False)
+                tlo, thi, tc, _ = dg.ranked(True, limit=top)
+                ranks = ((rlo, rhi), (tlo, thi, tc))
         finally:
             dg.close()
         t4 = time.perf_counter()
         # host wall clock of the four C-ABI phases (every call returns synchronised)
         info["wall_ms"] = {"create": (t1 - t0) * 1e3, "run": (t2 - t1) * 1e3, "result": (t3 - t2) * 1e3,
                            "destroy": (t4 - t3) * 1e3, **{"result_" + k: v for k, v in dg.result_wall_ms.items()}}
-        return cls(lo, hi, c, info["n_nodes"], iters, stats, info)
+        r = cls(lo, hi, c, info["n_nodes"], iters, stats, info)
+        if ranks:
+            r.rank_ids, r.top = ranks
+        return r
+
+    def harmonic_rank(self):
+        """{node id: rank} as store_harmonic writes it into the `harmonic_rank` store (needs calculate(..., with_ranks=True))."""
+        lo, hi = self.rank_ids
+        return {(int(h) << 64) | int(l): i for i, (l, h) in enumerate(zip(lo, hi))}
+
+    def top_nodes(self, k):
+        """top_nodes(store, TopNodes::Top(k)): [(node id, centrality)], (centrality, id) descending."""
+        lo, hi, c = self.top
+        return [((int(h) << 64) | int(l), float(v)) for l, h, v in zip(lo[:k], hi[:k], c[:k])]
 
     def _m(self):
         if self._map is None:

@@ -27,6 +27,7 @@ for n, e, seed in cases:
         T.test_random_graph_stepwise(n, e, seed, mode)
 if full:
     T.test_long_rows_and_hubs()
+    T.test_rank_assignment_matches_store_harmonic_order()
 if os.environ.get("SB200_ARENA"):
     r, u, p, s = (C.c_uint64(0) for _ in range(4))
     L.sb200_arena_stats.argtypes = [C.c_int] + [C.POINTER(C.c_uint64)] * 4

@@ -173,3 +173,18 @@ def test_faithful_equals_dense_on_random_graphs():
         assert f["iters"] == r["iters"] and f["n_nodes"] == r["n_nodes"]
         assert np.array_equal(f["ids_lo"], r["ids_lo"]) and np.array_equal(f["ids_hi"], r["ids_hi"])
         assert np.array_equal(f["centrality"], r["centrality"])  # bit-exact
+
+
+def test_harmonic_rank_order_restatement():
+    """store_harmonic sorts (Reverse(SortableFloat(c)), node_id): centrality descending, equal centralities by
+    ascending id; top_nodes takes the largest (c, id) pairs, i.e. equal centralities by DESCENDING id
+    (crates/core/src/webgraph/centrality/mod.rs:17-37,88-108; SortableFloat = f64::total_cmp, core/src/lib.rs:259-262)."""
+    import numpy as np
+    from oracle import harmonic_ranks
+    lo = np.array([5, 1, 9, 3, 7], np.uint64); hi = np.array([0, 2, 0, 0, 2], np.uint64)
+    c = np.array([0.5, 0.25, 0.5, 1.0, 0.25])
+    ids = [(int(h) << 64) | int(l) for l, h in zip(lo, hi)]
+    want = sorted(range(5), key=lambda i: (-c[i], ids[i]))
+    assert list(harmonic_ranks(lo, hi, c)) == want == [3, 0, 2, 1, 4]
+    want_top = sorted(range(5), key=lambda i: (c[i], ids[i]), reverse=True)
+    assert list(harmonic_ranks(lo, hi, c, ties_desc=True)) == want_top == [3, 2, 0, 4, 1]
