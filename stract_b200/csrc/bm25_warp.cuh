@@ -454,8 +454,6 @@ __global__ void __launch_bounds__(256) k_merge_topk(const MergeJob* __restrict__
   uint32_t* klo = (uint32_t*)(khi + capm);
   const MergeJob job = jobs[blockIdx.x];
   const uint32_t tid = threadIdx.x;
-  for (uint32_t i = tid; i < capm; i += 256) { khi[i] = 0; klo[i] = 0; }
-  __syncthreads();
   uint32_t base = 0;
   for (uint32_t s = 0; s < job.n_slots; s++) {
     const uint32_t slot = job.first_slot + s, n = o_n[slot];
@@ -466,10 +464,15 @@ __global__ void __launch_bounds__(256) k_merge_topk(const MergeJob* __restrict__
     }
     base += n;
   }
-  for (uint32_t size = 2; size <= capm; size <<= 1) {
+  // only the next power of two above the entries actually present is padded and sorted (capm = W_max * k is the
+  // worst case; most jobs merge a few short lists)
+  uint32_t n2 = 2; while (n2 < base) n2 <<= 1;
+  if (n2 > capm) n2 = capm;
+  for (uint32_t i = base + tid; i < n2; i += 256) { khi[i] = 0; klo[i] = 0; }
+  for (uint32_t size = 2; size <= n2; size <<= 1) {
     for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
       __syncthreads();
-      for (uint32_t i = tid; i < (capm >> 1); i += 256) {
+      for (uint32_t i = tid; i < (n2 >> 1); i += 256) {
         const uint32_t lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
         const bool desc = ((lo & size) == 0);
         const uint64_t ah = khi[lo], bh = khi[hi]; const uint32_t al = klo[lo], bl = klo[hi];
