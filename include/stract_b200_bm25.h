@@ -112,6 +112,12 @@ SB200_API int sb200_signal_topk_batch(sb200_segment* seg, const sb200_signal_bat
 SB200_API int sb200_postings_encode(const uint32_t* docs, const uint32_t* tfs, const uint64_t* term_off, uint32_t n_terms,
                                     const uint8_t* fieldnorm_ids, uint32_t max_doc, float avg_fieldnorm, uint8_t* out,
                                     uint64_t out_cap, uint64_t* out_len, sb200_term_info* infos, int threads);
+/* The same writer with the record option spelled out: 1 = WithFreqs (8-byte skip entries), 2 = WithFreqsAndPositions,
+ * what Stract's position-bearing text fields use (core/src/schema/text_field.rs:124-130): 12-byte skip entries that carry
+ * the block's term-frequency sum (tantivy/src/postings/skip.rs:52-76,217-232); the positions themselves are another file. */
+SB200_API int sb200_postings_encode_ex(const uint32_t* docs, const uint32_t* tfs, const uint64_t* term_off, uint32_t n_terms,
+                                       const uint8_t* fieldnorm_ids, uint32_t max_doc, float avg_fieldnorm, int record_option,
+                                       uint8_t* out, uint64_t out_cap, uint64_t* out_len, sb200_term_info* infos, int threads);
 /* FIELD_NORMS_TABLE (tantivy/src/fieldnorm/code.rs:13-270) as the closed-form byte code it is tested against */
 SB200_API uint32_t sb200_fieldnorm_id_to_value(uint8_t id);
 SB200_API uint8_t sb200_fieldnorm_value_to_id(uint32_t fieldnorm);

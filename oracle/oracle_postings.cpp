@@ -181,6 +181,7 @@ struct Segment {
   uint32_t max_doc = 0;
   float avg_fieldnorm = 0;            // total_num_tokens / max_doc (f32), bm25.rs:112-114
   uint64_t total_tokens = 0;
+  int record = 1;                     // IndexRecordOption: 1 WithFreqs (8-byte skip entries), 2 WithFreqsAndPositions (12)
 };
 
 ORC_API void* orc_seg_new(const uint8_t* fieldnorm_ids, uint32_t max_doc) {
@@ -196,6 +197,7 @@ ORC_API void* orc_seg_new(const uint8_t* fieldnorm_ids, uint32_t max_doc) {
 ORC_API void orc_seg_free(void* h) { delete (Segment*)h; }
 ORC_API float orc_seg_avg_fieldnorm(void* h) { return ((Segment*)h)->avg_fieldnorm; }
 ORC_API void orc_seg_set_avg_fieldnorm(void* h, float a) { ((Segment*)h)->avg_fieldnorm = a; }
+ORC_API void orc_seg_set_record(void* h, int record) { ((Segment*)h)->record = record; }
 
 // PostingsSerializer for one term, IndexRecordOption::WithFreqs (serializer.rs:343-462)
 ORC_API uint32_t orc_seg_add_term(void* h, const uint32_t* docs, const uint32_t* tfs, uint32_t df) {
@@ -216,6 +218,11 @@ ORC_API uint32_t orc_seg_add_term(void* h, const uint32_t* docs, const uint32_t*
     uint8_t tnb; n = block_pack_tf(bt, &tnb, buf);
     post.insert(post.end(), buf, buf + n);
     skip.push_back(tnb);
+    if (s->record == 2) {  // write_total_term_freq (skip.rs:65-67), only with positions (serializer.rs:383-388)
+      uint32_t sum = 0;
+      for (int k = 0; k < BLOCK; k++) sum += bt[k];
+      for (int i = 0; i < 4; i++) skip.push_back((uint8_t)(sum >> (8 * i)));
+    }
     uint8_t best_id = 0; uint32_t best_tf = 0;
     if (have_bw) {  // max_by keeps the LAST maximum under partial_cmp
       float best = -1.0f; bool first = true;
@@ -261,18 +268,22 @@ ORC_API void orc_seg_set_postings(void* h, const uint8_t* bytes, uint64_t len, c
 }
 
 // ---------------------------------------------------------------- cursors --------------------
-struct SkipReader {  // skip.rs:85-281, IndexRecordOption::WithFreqs (8-byte entries)
+struct SkipReader {  // skip.rs:85-281: WithFreqs (8-byte entries) and WithFreqsAndPositions (12-byte entries)
   const uint8_t* p = nullptr;
+  int record = 1;
   uint32_t last_doc_in_block = 0, last_doc_in_previous_block = 0, remaining = 0;
   size_t byte_offset = 0;
   bool bitpacked = false; uint8_t doc_bits = 0, tf_bits = 0, bw_id = 0; bool strict = true; uint32_t bw_tf = 0, vint_docs = 0;
   void read_block_info() {
     last_doc_in_block = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
     doc_bits = p[4] & 0x3f; strict = (p[4] >> 6) & 1;
-    tf_bits = p[5]; bw_id = p[6]; bw_tf = (p[7] == 255) ? 0xFFFFFFFFu : p[7];
-    bitpacked = true; p += 8;
+    tf_bits = p[5];
+    const int bw = record == 2 ? 10 : 6;  // skip.rs:203-232: tf_sum u32 sits before the block-wand pair
+    bw_id = p[bw]; bw_tf = (p[bw + 1] == 255) ? 0xFFFFFFFFu : p[bw + 1];
+    bitpacked = true; p += (record == 2 ? 12 : 8);
   }
-  void reset(const uint8_t* data, uint32_t df) {
+  void reset(const uint8_t* data, uint32_t df, int rec) {
+    record = rec;
     last_doc_in_block = df >= (uint32_t)BLOCK ? 0 : TERMINATED;
     last_doc_in_previous_block = 0; p = data; bitpacked = false; vint_docs = df; byte_offset = 0; remaining = df;
     if (df >= (uint32_t)BLOCK) read_block_info();
@@ -309,7 +320,7 @@ struct Postings {  // BlockSegmentPostings + SegmentPostings
       skipdata = b; b += sl;
     }
     data = b;
-    skip.reset(skipdata, df);
+    skip.reset(skipdata, df, s->record);
     loaded = false; has_bm_cache = false; cur = 0;
     load_block();
   }

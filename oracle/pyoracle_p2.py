@@ -26,6 +26,7 @@ def proto(L, f):
     f("orc_seg_free", None, vp)
     f("orc_seg_avg_fieldnorm", f32, vp)
     f("orc_seg_set_avg_fieldnorm", None, vp, f32)
+    f("orc_seg_set_record", None, vp, i32)
     f("orc_seg_add_term", u32, vp, _u32p, _u32p, u32)
     f("orc_seg_postings_len", u64, vp)
     f("orc_seg_postings_copy", None, vp, _u8p)
@@ -97,13 +98,15 @@ def stract_bm25_weight(doc_freq, num_docs, avg_fieldnorm, k1=1.2, b=0.75):
 class Segment:
     """One field of one segment: postings file in tantivy's byte format + fieldnorm ids."""
 
-    def __init__(self, fieldnorm_ids, avg_fieldnorm=None):
+    def __init__(self, fieldnorm_ids, avg_fieldnorm=None, record_option=1):
         self.fieldnorm_ids = np.ascontiguousarray(fieldnorm_ids, np.uint8)
         self.max_doc = int(self.fieldnorm_ids.size)
         self.L = _L()
         self.h = self.L.orc_seg_new(self.fieldnorm_ids, self.max_doc)
         if avg_fieldnorm is not None:
             self.L.orc_seg_set_avg_fieldnorm(self.h, float(avg_fieldnorm))
+        self.record_option = int(record_option)
+        self.L.orc_seg_set_record(self.h, self.record_option)
 
     @property
     def avg_fieldnorm(self):

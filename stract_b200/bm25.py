@@ -107,18 +107,19 @@ def _p(a):
     return a.ctypes.data if a is not None else None
 
 
-def encode_postings(term_docs, term_tfs, fieldnorm_ids, avg_fieldnorm, threads=8):
-    """PostingsSerializer for a list of terms (WithFreqs).  Returns (bytes u8[], TermInfo array)."""
+def encode_postings(term_docs, term_tfs, fieldnorm_ids, avg_fieldnorm, threads=8, record_option=1):
+    """PostingsSerializer for a list of terms (record_option 1 = WithFreqs, 2 = WithFreqsAndPositions).  Returns
+    (bytes u8[], TermInfo array)."""
     n = len(term_docs)
     off = np.zeros(n + 1, np.uint64)
     for i, d in enumerate(term_docs):
         off[i + 1] = off[i] + len(d)
     docs = np.concatenate([np.asarray(d, np.uint32) for d in term_docs]) if n else np.zeros(0, np.uint32)
     tfs = np.concatenate([np.asarray(t, np.uint32) for t in term_tfs]) if n else np.zeros(0, np.uint32)
-    return encode_postings_csr(docs, tfs, off, fieldnorm_ids, avg_fieldnorm, threads)
+    return encode_postings_csr(docs, tfs, off, fieldnorm_ids, avg_fieldnorm, threads, record_option)
 
 
-def encode_postings_csr(docs, tfs, off, fieldnorm_ids, avg_fieldnorm, threads=8):
+def encode_postings_csr(docs, tfs, off, fieldnorm_ids, avg_fieldnorm, threads=8, record_option=1):
     L = lib()
     docs = np.ascontiguousarray(docs, np.uint32); tfs = np.ascontiguousarray(tfs, np.uint32)
     off = np.ascontiguousarray(off, np.uint64)
@@ -126,11 +127,11 @@ def encode_postings_csr(docs, tfs, off, fieldnorm_ids, avg_fieldnorm, threads=8)
     n = off.size - 1
     ln = C.c_uint64(0)
     infos = (B.TermInfo * max(n, 1))()
-    check(L.sb200_postings_encode(_p(docs), _p(tfs), _p(off), n, _p(fn), fn.size, float(avg_fieldnorm), None, 0,
-                                  C.byref(ln), None, threads))
+    check(L.sb200_postings_encode_ex(_p(docs), _p(tfs), _p(off), n, _p(fn), fn.size, float(avg_fieldnorm), int(record_option),
+                                     None, 0, C.byref(ln), None, threads))
     out = np.zeros(max(ln.value, 1), np.uint8)
-    check(L.sb200_postings_encode(_p(docs), _p(tfs), _p(off), n, _p(fn), fn.size, float(avg_fieldnorm), _p(out), out.size,
-                                  C.byref(ln), infos, threads))
+    check(L.sb200_postings_encode_ex(_p(docs), _p(tfs), _p(off), n, _p(fn), fn.size, float(avg_fieldnorm), int(record_option),
+                                     _p(out), out.size, C.byref(ln), infos, threads))
     return out[:ln.value], infos
 
 

@@ -67,8 +67,10 @@ struct TfNorm {
   float factor(uint8_t id, uint32_t tf) const { const float t = (float)tf; return t / (t + norm[id]); }
 };
 
+// record: 1 = IndexRecordOption::WithFreqs (8-byte skip entries), 2 = WithFreqsAndPositions (12 bytes: the sum of the
+// block's term freqs sits between tf_bits and the block-wand pair, skip.rs:52-76; positions live in another file)
 void encode_term(const uint32_t* docs, const uint32_t* tfs, uint32_t df, const uint8_t* fn_ids, bool have_fn,
-                 const TfNorm& tn, std::vector<uint8_t>& out) {
+                 const TfNorm& tn, int record, std::vector<uint8_t>& out) {
   std::vector<uint8_t> skip, body;
   const uint32_t full = df / 128;
   uint32_t prev = 0;
@@ -85,6 +87,11 @@ void encode_term(const uint32_t* docs, const uint32_t* tfs, uint32_t df, const u
     for (int i = 0; i < 4; i++) skip.push_back((uint8_t)(prev >> (8 * i)));
     skip.push_back((uint8_t)(wd | 0x40));
     skip.push_back((uint8_t)wt);
+    if (record == 2) {  // write_total_term_freq, serializer.rs:383-388
+      uint32_t sum = 0;
+      for (int i = 0; i < 128; i++) sum += t[i];
+      for (int i = 0; i < 4; i++) skip.push_back((uint8_t)(sum >> (8 * i)));
+    }
     uint8_t bid = 0; uint32_t btf = 0;
     if (have_fn) {  // Iterator::max_by keeps the last of equal maxima
       float best = 0; bool any = false;
@@ -115,8 +122,16 @@ uint8_t sb200_fieldnorm_value_to_id(uint32_t v) { return sb200::fieldnorm_id(v);
 int sb200_postings_encode(const uint32_t* docs, const uint32_t* tfs, const uint64_t* term_off, uint32_t n_terms,
                           const uint8_t* fieldnorm_ids, uint32_t max_doc, float avg_fieldnorm, uint8_t* out,
                           uint64_t out_cap, uint64_t* out_len, sb200_term_info* infos, int threads) {
+  return sb200_postings_encode_ex(docs, tfs, term_off, n_terms, fieldnorm_ids, max_doc, avg_fieldnorm, 1, out, out_cap, out_len,
+                                  infos, threads);
+}
+
+int sb200_postings_encode_ex(const uint32_t* docs, const uint32_t* tfs, const uint64_t* term_off, uint32_t n_terms,
+                             const uint8_t* fieldnorm_ids, uint32_t max_doc, float avg_fieldnorm, int record_option,
+                             uint8_t* out, uint64_t out_cap, uint64_t* out_len, sb200_term_info* infos, int threads) {
   using namespace sb200;
   if (!term_off || !out_len || (n_terms && (!docs || !tfs))) SB_FAIL(SB200_EINVAL, "NULL argument");
+  if (record_option != 1 && record_option != 2) SB_FAIL(SB200_EINVAL, "record_option %d: the writer covers WithFreqs (1) and WithFreqsAndPositions (2)", record_option);
   const bool have_fn = fieldnorm_ids != nullptr && max_doc > 0;
   const TfNorm tn(avg_fieldnorm);
   std::vector<TermBytes> enc(n_terms);
@@ -133,7 +148,7 @@ int sb200_postings_encode(const uint32_t* docs, const uint32_t* tfs, const uint6
         for (uint32_t i = 0; i < df; i++) {
           if (tfs[a + i] == 0 || (i && docs[a + i] <= docs[a + i - 1]) || (have_fn && docs[a + i] >= max_doc)) { bad = 1; break; }
         }
-        if (!bad) encode_term(docs + a, tfs + a, df, fieldnorm_ids, have_fn, tn, enc[u].bytes);
+        if (!bad) encode_term(docs + a, tfs + a, df, fieldnorm_ids, have_fn, tn, record_option, enc[u].bytes);
       }
     }
   };

@@ -12,27 +12,27 @@ from stract_b200.bm25 import MODE_AND, MODE_OR, NO_TERM, SegmentReader, SignalCo
 pytestmark = pytest.mark.gpu
 
 
-def build(term_docs, term_tfs, lens):
+def build(term_docs, term_tfs, lens, record_option=1):
     """The same index as an oracle Segment and as a device SegmentReader (library writer)."""
     ids = bm25.fieldnorms_to_ids(lens)
-    oseg = oracle.Segment(ids)
+    oseg = oracle.Segment(ids, record_option=record_option)
     for d, t in zip(term_docs, term_tfs):
         oseg.add_term(np.asarray(d, np.uint32), np.asarray(t, np.uint32))
-    data, infos = bm25.encode_postings(term_docs, term_tfs, ids, oseg.avg_fieldnorm)
+    data, infos = bm25.encode_postings(term_docs, term_tfs, ids, oseg.avg_fieldnorm, record_option=record_option)
     assert np.array_equal(data, oseg.postings_bytes())
-    seg = SegmentReader(data, infos, ids)
+    seg = SegmentReader(data, infos, ids, record_option=record_option)
     assert seg.average_fieldnorm == np.float32(oseg.avg_fieldnorm)
     return oseg, seg
 
 
-def random_index(seed, max_doc, dfs):
+def random_index(seed, max_doc, dfs, record_option=1):
     rng = np.random.default_rng(seed)
     lens = np.maximum(1, rng.lognormal(4.0, 0.8, max_doc)).astype(np.uint32)
     td, tt = [], []
     for df in dfs:
         td.append(np.sort(rng.choice(max_doc, df, replace=False)).astype(np.uint32))
         tt.append(np.minimum(rng.geometric(0.6, df), 255).astype(np.uint32))
-    return build(td, tt, lens), rng
+    return build(td, tt, lens, record_option), rng
 
 
 def weights_for(seg, q):
@@ -176,6 +176,28 @@ def test_signal_combine_bit_exact():
     od, ot, on, _ = oseg.signal_topk_batch(terms[:10], w[:10], caches[:50], 1.2, 1.0, [], [], 50)
     gd, gt, gn = comp0.top_docs_batch(terms[:10], 50)
     assert np.array_equal(gd, od) and np.array_equal(gt, ot)
+
+
+def test_positions_record_option_skip_entries():
+    """IndexRecordOption::WithFreqsAndPositions, the option of Stract's position-bearing text fields
+    (core/src/schema/text_field.rs:124-130): 12-byte skip entries with the block's tf sum (skip.rs:217-232).  Same
+    results as the WithFreqs file of the same postings, and bit-exact against the oracle reading the 12-byte entries
+    (AND, OR incl. block-max pruning in the oracle, signal combine)."""
+    (o1, s1), _ = random_index(17, 60_000, DFS, record_option=1)
+    (o2, s2), rng = random_index(17, 60_000, DFS, record_option=2)
+    assert o2.postings_bytes().size > o1.postings_bytes().size      # 4 more bytes per full block
+    nt = len(DFS)
+    for _ in range(25):
+        q = [int(x) for x in rng.choice(nt, int(rng.integers(1, 4)), replace=False)]
+        for mode in (MODE_AND, MODE_OR):
+            if mode == MODE_OR and len(q) > 2:
+                continue
+            check_query(o2, s2, q, mode, 100)
+            a = TopDocs.with_limit(100).search(s1, q, mode); b = TopDocs.with_limit(100).search(s2, q, mode)
+            assert a == b
+    check_query(o2, s2, [nt - 1, nt - 2], MODE_AND, 1000)
+    check_query(o2, s2, [nt - 1, nt - 2], MODE_OR, 1000)
+    s1.close(); s2.close()
 
 
 def test_malformed_postings_rejected():
