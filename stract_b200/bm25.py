@@ -212,13 +212,19 @@ def score_rank(rank):
 class TopDocs:
     """`TopDocs::with_limit(k)` over a BooleanQuery of TermQueries on one field, batched."""
 
-    def __init__(self, limit):
+    def __init__(self, limit, offset=0):
         assert limit >= 1, "Limit must be strictly greater than 0."  # top_collector.rs:85
         self.limit = limit
+        self.offset = offset
 
     @classmethod
     def with_limit(cls, limit):
         return cls(limit)
+
+    def and_offset(self, offset):
+        """TopDocs::and_offset (top_score_collector.rs:170-172): the segment collects limit + offset documents and the
+        merged fruit drops the first `offset` (top_collector.rs:109-129)."""
+        return TopDocs(self.limit, int(offset))
 
     def search_batch(self, segment, term_ords, mode=MODE_AND, weights=None, return_stats=False):
         """term_ords [n_queries, n_terms] (NO_TERM pads).  Returns (docs [nq,k], scores [nq,k], n_out [nq])."""
@@ -231,11 +237,15 @@ class TopDocs:
             weights = w_u[inv].reshape(nq, nt)
         weights = np.ascontiguousarray(weights, np.float32)
         cache = compute_tf_cache(segment.average_fieldnorm)
-        k = self.limit
+        k = self.limit + self.offset
         docs = host_out((nq, k), np.uint32); scores = host_out((nq, k), np.float32); n_out = np.zeros(nq, np.uint32)
         b = B.Bm25Batch(nq, nt, _p(term_ords), _p(weights), _p(cache), mode, k)
         st = B.Bm25Stats()
         check(segment._L.sb200_bm25_topk_batch(segment._h, C.byref(b), _p(docs), _p(scores), _p(n_out), C.byref(st)))
+        if self.offset:
+            o = self.offset
+            docs = np.ascontiguousarray(docs[:, o:]); scores = np.ascontiguousarray(scores[:, o:])
+            n_out = (np.maximum(n_out.astype(np.int64) - o, 0)).astype(np.uint32)
         if return_stats:
             return docs, scores, n_out, {k_: getattr(st, k_) for k_, _ in B.Bm25Stats._fields_ if not k_.startswith("_")}
         return docs, scores, n_out

@@ -65,6 +65,11 @@ def test_droopy_tax_kat():
     assert [d for _, d in TopDocs.with_limit(2).search(seg, q, MODE_OR)] == [1, 2]
     r = TopDocs.with_limit(4).search(seg, q, MODE_AND)
     assert [d for _, d in r] == [1] and abs(r[0][0] - 0.81221175) < 1e-6
+    # and_offset, top_score_collector.rs:701-751
+    r = TopDocs.with_limit(4).and_offset(2).search(seg, q, MODE_OR)
+    assert [d for _, d in r] == [0] and abs(r[0][0] - 0.48527452) < 1e-6
+    r = TopDocs.with_limit(2).and_offset(1).search(seg, q, MODE_OR)
+    assert [d for _, d in r] == [2, 0] and abs(r[0][0] - 0.5376842) < 1e-6 and abs(r[1][0] - 0.48527452) < 1e-6
 
 
 DFS = [1, 3, 100, 127, 128, 129, 255, 256, 257, 300, 511, 512, 1000, 1024, 2500, 6000, 15000, 40000]
