@@ -26,6 +26,8 @@ for n, e, seed in cases:
     for mode in ((-1, 0, 1, 2) if full else (-1, 2)):
         T.test_random_graph_stepwise(n, e, seed, mode)
 if full:
+    import test_golden
+    test_golden.check_path1_against_golden()   # committed fixtures, no oracle call
     T.test_long_rows_and_hubs()
     T.test_rank_assignment_matches_store_harmonic_order()
 if os.environ.get("SB200_ARENA"):

@@ -46,6 +46,8 @@ def test_default_kernels_against_oracle(emulated):
     T.test_signal_combine_bit_exact()
     T.test_positions_record_option_skip_entries()
     T.test_malformed_postings_rejected()
+    import test_golden
+    test_golden.check_path2_against_golden()   # committed fixtures, no oracle call
 
 
 def test_unit_based_and_kernel_against_oracle(emulated, monkeypatch):
