@@ -29,7 +29,8 @@ if full:
     import test_golden
     test_golden.check_path1_against_golden()   # committed fixtures, no oracle call
     T.test_long_rows_and_hubs()
-    T.test_rank_assignment_matches_store_harmonic_order()
+    import test_round1_late_gpu as late
+    late.test_rank_assignment_matches_store_harmonic_order()
 if os.environ.get("SB200_ARENA"):
     r, u, p, s = (C.c_uint64(0) for _ in range(4))
     L.sb200_arena_stats.argtypes = [C.c_int] + [C.POINTER(C.c_uint64)] * 4

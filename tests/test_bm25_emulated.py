@@ -44,7 +44,8 @@ def test_default_kernels_against_oracle(emulated):
     T.test_or_three_plus_terms_canonical_order()
     T.test_ties_order_by_doc_and_padding()
     T.test_signal_combine_bit_exact()
-    T.test_positions_record_option_skip_entries()
+    import test_round1_late_gpu as late
+    late.test_positions_record_option_skip_entries()
     T.test_malformed_postings_rejected()
     import test_golden
     test_golden.check_path2_against_golden()   # committed fixtures, no oracle call

@@ -183,28 +183,6 @@ def test_signal_combine_bit_exact():
     assert np.array_equal(gd, od) and np.array_equal(gt, ot)
 
 
-def test_positions_record_option_skip_entries():
-    """IndexRecordOption::WithFreqsAndPositions, the option of Stract's position-bearing text fields
-    (core/src/schema/text_field.rs:124-130): 12-byte skip entries with the block's tf sum (skip.rs:217-232).  Same
-    results as the WithFreqs file of the same postings, and bit-exact against the oracle reading the 12-byte entries
-    (AND, OR incl. block-max pruning in the oracle, signal combine)."""
-    (o1, s1), _ = random_index(17, 60_000, DFS, record_option=1)
-    (o2, s2), rng = random_index(17, 60_000, DFS, record_option=2)
-    assert o2.postings_bytes().size > o1.postings_bytes().size      # 4 more bytes per full block
-    nt = len(DFS)
-    for _ in range(25):
-        q = [int(x) for x in rng.choice(nt, int(rng.integers(1, 4)), replace=False)]
-        for mode in (MODE_AND, MODE_OR):
-            if mode == MODE_OR and len(q) > 2:
-                continue
-            check_query(o2, s2, q, mode, 100)
-            a = TopDocs.with_limit(100).search(s1, q, mode); b = TopDocs.with_limit(100).search(s2, q, mode)
-            assert a == b
-    check_query(o2, s2, [nt - 1, nt - 2], MODE_AND, 1000)
-    check_query(o2, s2, [nt - 1, nt - 2], MODE_OR, 1000)
-    s1.close(); s2.close()
-
-
 def test_malformed_postings_rejected():
     from stract_b200._lib import Sb200Error
     (oseg, seg), rng = random_index(16, 5000, [300, 10])

@@ -1,8 +1,8 @@
 """Committed golden fixtures (tests/golden/*.json; generator: tests/golden/make_golden.py).
 
 CPU: the oracle still reproduces every frozen number (so the checker cannot drift unnoticed), and the list of reference
-known-answer values stays in step with the oracle tests.  GPU: the CUDA path reproduces the frozen numbers directly
-through the C ABI -- no oracle call at run time.  The same two functions also run on the CPU SIMT emulator
+known-answer values stays in step with the oracle tests.  GPU (tests/test_round1_late_gpu.py): the CUDA path reproduces the frozen numbers
+directly through the C ABI -- no oracle call at run time.  The same two functions also run on the CPU SIMT emulator
 (tests/test_hyperball_emulated.py, tests/test_bm25_emulated.py)."""
 import json
 import os
@@ -95,13 +95,3 @@ def check_path2_against_golden():
             assert [int(x) for x in dd[0, :n[0]]] == want["docs"] and M.f64hex(tot[0, :n[0]]) == want["totals"], ("signal", q)
     finally:
         seg.close()
-
-
-@pytest.mark.gpu
-def test_cuda_path1_reproduces_golden():
-    check_path1_against_golden()
-
-
-@pytest.mark.gpu
-def test_cuda_path2_reproduces_golden():
-    check_path2_against_golden()

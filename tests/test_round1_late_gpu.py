@@ -1,0 +1,60 @@
+"""GPU tests added after the round's last GPU trip.  They passed on the CPU SIMT emulator (tests/emu) but have not run
+on hardware yet, so they live in a file that sorts behind the hardware-validated suites: `pytest -x` reaches them last."""
+import numpy as np
+import pytest
+
+import test_golden
+from test_bm25_gpu import DFS, MODE_AND, MODE_OR, TopDocs, check_query, random_index
+from test_hyperball_gpu import HarmonicCentrality, _graph, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cuda_path1_reproduces_golden():
+    test_golden.check_path1_against_golden()
+
+
+def test_cuda_path2_reproduces_golden():
+    test_golden.check_path2_against_golden()
+
+
+def test_positions_record_option_skip_entries():
+    """IndexRecordOption::WithFreqsAndPositions, the option of Stract's position-bearing text fields
+    (core/src/schema/text_field.rs:124-130): 12-byte skip entries with the block's tf sum (skip.rs:217-232).  Same
+    results as the WithFreqs file of the same postings, and bit-exact against the oracle reading the 12-byte entries
+    (AND, OR incl. block-max pruning in the oracle, signal combine)."""
+    (o1, s1), _ = random_index(17, 60_000, DFS, record_option=1)
+    (o2, s2), rng = random_index(17, 60_000, DFS, record_option=2)
+    assert o2.postings_bytes().size > o1.postings_bytes().size      # 4 more bytes per full block
+    nt = len(DFS)
+    for _ in range(25):
+        q = [int(x) for x in rng.choice(nt, int(rng.integers(1, 4)), replace=False)]
+        for mode in (MODE_AND, MODE_OR):
+            if mode == MODE_OR and len(q) > 2:
+                continue
+            check_query(o2, s2, q, mode, 100)
+            a = TopDocs.with_limit(100).search(s1, q, mode); b = TopDocs.with_limit(100).search(s2, q, mode)
+            assert a == b
+    check_query(o2, s2, [nt - 1, nt - 2], MODE_AND, 1000)
+    check_query(o2, s2, [nt - 1, nt - 2], MODE_OR, 1000)
+    s1.close(); s2.close()
+
+
+
+def test_rank_assignment_matches_store_harmonic_order():
+    """store_harmonic's rank pass and top_nodes (webgraph/centrality/mod.rs:17-37,88-108) on the
+    device, against the numpy restatement: order (centrality desc, id asc) resp. (centrality, id) desc, incl. the many
+    exact ties a HyperLogLog-estimated centrality has."""
+    from oracle import harmonic_ranks
+    d = synth.rmat_graph(20_000, 120_000, seed=5)
+    got = HarmonicCentrality.calculate(_graph(d), with_ranks=True, top=500)
+    order = harmonic_ranks(got.ids_lo, got.ids_hi, got.values, ties_desc=False)
+    assert len(np.unique(got.values)) < len(got.values)          # the tie rule is exercised
+    rlo, rhi = got.rank_ids
+    assert np.array_equal(rlo, got.ids_lo[order]) and np.array_equal(rhi, got.ids_hi[order])
+    ranks = got.harmonic_rank()
+    assert len(ranks) == len(got.values) and ranks[(int(rhi[0]) << 64) | int(rlo[0])] == 0
+    torder = harmonic_ranks(got.ids_lo, got.ids_hi, got.values, ties_desc=True)[:500]
+    tlo, thi, tc = got.top
+    assert np.array_equal(tlo, got.ids_lo[torder]) and np.array_equal(thi, got.ids_hi[torder]) and np.array_equal(tc, got.values[torder])
+    assert [c for _, c in got.top_nodes(10)] == sorted(got.values, reverse=True)[:10]
