@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-bm25", action="store_true")
+    ap.add_argument("--no-experimental", action="store_true", help="skip the subprocess that times the opt-in BM25 kernels")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL byte-max all-reduce exchange instead of the fused peer-memory stores")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "symm", "multicast"],
                     help="multi-GPU fused exchange transport: CUDA IPC peer mappings (default), torch symmetric memory "
@@ -415,6 +416,16 @@ def main():
                 line["bm25"] = bm25_bench.run(local_rank, peaks, peak_src)
             except ImportError:
                 line["bm25"] = None
+            if line.get("bm25") is not None and not args.no_experimental:
+                # the opt-in BM25 kernels have passed their parity tests on the CPU emulator only: measured in a separate
+                # process (own CUDA context, bounded time), reported beside -- never instead of -- the default kernels
+                try:
+                    r = subprocess.run([sys.executable, "-m", "stract_b200.bm25_bench", str(local_rank)], cwd=ROOT,
+                                       capture_output=True, text=True, timeout=420)
+                    line["bm25"]["experimental"] = (json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0
+                                                    else {"error": (r.stderr or r.stdout)[-400:]})
+                except Exception as ex:  # noqa: BLE001
+                    line["bm25"]["experimental"] = {"error": repr(ex)[:400]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -174,3 +174,76 @@ def run(device, peaks, peak_src, scale=1.0, cpu=True):
     res["and_top1000_10M"] = run_and(device, peaks, max_doc=int(10_000_000 * scale), df_scale=2.0e6 * scale, cpu=cpu)
     res["or5_signals_100M"] = run_signal(device, peaks, max_doc=int(100_000_000 * scale), df_scale=2.0e7 * scale, cpu=cpu)
     return res
+
+
+def run_experimental(device=0, max_doc=10_000_000, df_scale=2.0e6, n_and=10_000, n_sig=2_000, n_ranks=10_000):
+    """The two opt-in kernels (bm25_and3.cuh, bm25_or3.cuh) beside the default ones on the same resident index:
+    AND at the C3 size, the signal combine at 1/10 of C4.  Results must be identical to the default kernel's; the
+    numbers are reported as `experimental` by bench.py, which runs this in a SUBPROCESS so that a fault in a kernel
+    that has never run on hardware cannot touch the main measurement."""
+    out = {}
+    ix = synth_index(max_doc, df_scale, n_ranks=n_ranks)
+    seg = bm25.SegmentReader(ix["postings"], ix["infos"], ix["fieldnorm_ids"], device=device)
+    try:
+        top = bm25.TopDocs.with_limit(1000)
+        terms = log_uniform_queries(n_and, 2, hi=n_ranks)
+        res = {}
+        for name, env in (("default", None), ("unit_kernel", "SB200_BM25_AND3")):
+            if env:
+                os.environ[env] = "1"
+            try:
+                for _ in range(2):
+                    top.search_batch(seg, terms, bm25.MODE_AND)
+                ks = []
+                for _ in range(3):
+                    d, s, n, st = top.search_batch(seg, terms, bm25.MODE_AND, return_stats=True)
+                    ks.append(st["kernel_ms"])
+                res[name] = (d.copy(), s.copy(), n.copy(), float(np.median(ks)), st)
+            finally:
+                if env:
+                    os.environ.pop(env, None)
+        same = bool(np.array_equal(res["default"][2], res["unit_kernel"][2]) and all(
+            np.array_equal(res["default"][0][q, :res["default"][2][q]], res["unit_kernel"][0][q, :res["default"][2][q]]) and
+            np.array_equal(res["default"][1][q, :res["default"][2][q]], res["unit_kernel"][1][q, :res["default"][2][q]])
+            for q in range(len(terms))))
+        post = res["default"][4]["postings_scored"]
+        out["and_top1000_10M"] = {"identical_results": same, "default_kernel_ms": res["default"][3], "unit_kernel_ms": res["unit_kernel"][3],
+                                  "unit_kernel_postings_per_s": post / (res["unit_kernel"][3] * 1e-3),
+                                  "blocks_decoded": [res["default"][4]["blocks_decoded"], res["unit_kernel"][4]["blocks_decoded"]]}
+        # signal combine on the same 10 M-doc index (1/10 of C4), 2 000 x 5-term queries
+        rng = np.random.default_rng(99)
+        cols = [rng.random(max_doc) ** 8, rng.random(max_doc), rng.random(max_doc), 1.0 / (1.0 + rng.integers(0, 1000, max_doc))]
+        table = bm25.SignalTable(cols, device=device)
+        comp = bm25.SignalComputer(seg, table, [2.0, 0.02, 2.0, 0.001], coeff_text=0.005)
+        t5 = log_uniform_queries(n_sig, 5, hi=n_ranks)
+        res = {}
+        for name, env in (("default", None), ("or3", "SB200_BM25_OR3")):
+            if env:
+                os.environ[env] = "1"
+            try:
+                comp.top_docs_batch(t5, 1000)
+                ks = []
+                for _ in range(2):
+                    d, tot, n, st = comp.top_docs_batch(t5, 1000, return_stats=True)
+                    ks.append(st["kernel_ms"])
+                res[name] = (d.copy(), tot.copy(), n.copy(), float(np.median(ks)), st)
+            finally:
+                if env:
+                    os.environ.pop(env, None)
+        same = bool(np.array_equal(res["default"][2], res["or3"][2]) and all(
+            np.array_equal(res["default"][0][q, :res["default"][2][q]], res["or3"][0][q, :res["default"][2][q]]) and
+            np.array_equal(res["default"][1][q, :res["default"][2][q]], res["or3"][1][q, :res["default"][2][q]])
+            for q in range(len(t5))))
+        post = res["default"][4]["postings_scored"]
+        out["or5_signals_10M"] = {"identical_results": same, "default_kernel_ms": res["default"][3], "or3_kernel_ms": res["or3"][3],
+                                  "or3_postings_per_s": post / (res["or3"][3] * 1e-3), "postings_per_batch": post}
+        table.close()
+    finally:
+        seg.close()
+    return out
+
+
+if __name__ == "__main__":
+    import json
+    import sys
+    print(json.dumps(run_experimental(int(sys.argv[1]) if len(sys.argv) > 1 else 0)))
