@@ -162,6 +162,7 @@ def gen_device_graph(torch, L, dev_index, nodes, edges, scale):
 
 
 def main():
+    t_bench0 = time.perf_counter()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -426,6 +427,30 @@ def main():
                                                     else {"error": (r.stderr or r.stdout)[-400:]})
                 except Exception as ex:  # noqa: BLE001
                     line["bm25"]["experimental"] = {"error": repr(ex)[:400]}
+        if world == 1 and not args.no_experimental and args.nodes == 50_000_000 and args.edges == 1_000_000_000:
+            # path-1 switches that have only run on the CPU emulator, each in its own process and only
+            # while the whole bench is still short; reported beside the main numbers, never instead of them
+            exp = {}
+            variants = [("l2_persist_64MB", {"SB200_L2_PERSIST_MB": "64"}, ["--no-e2e", "--steps", "3"]),
+                        ("e2e_arena_rowperm", {"SB200_ARENA": "1", "SB200_STAGE_ROWPERM": "1"}, ["--steps", "1", "--e2e-steps", "3"])]
+            for name, env, extra in variants:
+                if time.perf_counter() - t_bench0 > 270:
+                    exp[name] = {"skipped": "bench time budget"}
+                    continue
+                try:
+                    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--no-bm25", "--no-cpu", "--no-experimental", *extra],
+                                       cwd=ROOT, env={**os.environ, **env}, capture_output=True, text=True, timeout=150)
+                    if r.returncode != 0:
+                        exp[name] = {"error": (r.stderr or r.stdout)[-300:]}
+                        continue
+                    d = json.loads(r.stdout.strip().splitlines()[-1])
+                    exp[name] = {"env": env, "ms_per_step": d["ms_per_step"], "iterations": d["config"]["iterations_per_step"],
+                                 "top_kernel_avg_ms": (d.get("roofline") or {}).get("avg_launch_ms"),
+                                 "e2e_ms_per_step": (d.get("e2e") or {}).get("ms_per_step"),
+                                 "e2e_step_wall_ms": (d.get("e2e") or {}).get("step_wall_ms")}
+                except Exception as ex:  # noqa: BLE001
+                    exp[name] = {"error": repr(ex)[:300]}
+            line["experimental"] = exp
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
