@@ -431,6 +431,12 @@ def main():
             # path-1 switches that have only run on the CPU emulator, each in its own process and only
             # while the whole bench is still short; reported beside the main numbers, never instead of them
             exp = {}
+            try:   # hand the staging pool of this process back first: the child needs the HBM
+                from stract_b200._lib import lib as _sblib
+                torch.cuda.empty_cache()
+                _sblib().sb200_release_cached_memory(local_rank)
+            except Exception:  # noqa: BLE001
+                pass
             variants = [("l2_persist_64MB", {"SB200_L2_PERSIST_MB": "64"}, ["--no-e2e", "--steps", "3"]),
                         ("e2e_arena_rowperm", {"SB200_ARENA": "1", "SB200_STAGE_ROWPERM": "1"}, ["--steps", "1", "--e2e-steps", "3"])]
             for name, env, extra in variants:

@@ -196,6 +196,8 @@ SB200_API int sb200_hyperball_exchange_done(sb200_graph* g, uint64_t global_n_ch
 SB200_API int sb200_arena_stats(int device, uint64_t* reserved_bytes, uint64_t* in_use_bytes, uint64_t* peak_bytes,
                                 uint64_t* n_slabs);
 SB200_API int sb200_arena_trim(int device);
+/* returns the memory cached for staging (the stream-ordered pool and empty arena slabs) to the driver */
+SB200_API int sb200_release_cached_memory(int device);
 SB200_API int sb200_arena_selftest(uint64_t seed, uint32_t ops);
 
 /* ===========================================================================================

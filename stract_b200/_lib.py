@@ -54,6 +54,7 @@ def declare(L):
     f("sb200_last_error", C.c_char_p)
     f("sb200_version", C.c_char_p)
     f("sb200_kernel_launch_count", u64)
+    f("sb200_release_cached_memory", i32, i32)
     f("sb200_graph_create", i32, vp, vp, vp, vp, vp, u64, u64, i32, i32, i32, C.POINTER(vp))
     f("sb200_graph_destroy", None, vp)
     f("sb200_graph_get_info", i32, vp, C.POINTER(GraphInfo))

@@ -78,6 +78,22 @@ int sb200_arena_trim(int device) {
   return SB200_OK;
 }
 
+// Give cached device memory back to the driver: the stream-ordered pool the staging pipeline keeps warm (release
+// threshold = max) and the slab arena's empty slabs.  For processes that are done with a large graph.
+int sb200_release_cached_memory(int device) {
+  int prev = -1;
+  SB_CUDA(cudaGetDevice(&prev));
+  SB_CUDA(cudaSetDevice(device));
+  SB_CUDA(cudaDeviceSynchronize());
+  cudaMemPool_t pool;
+  SB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  SB_CUDA(cudaMemPoolTrimTo(pool, 0));
+  Arena* a = arena_of(device, false);
+  if (a) a->trim();
+  SB_CUDA(cudaSetDevice(prev));
+  return SB200_OK;
+}
+
 // Randomised self-test of the allocator logic over host memory (no GPU): returns 0 when every invariant held.
 static int g_synced = 0;
 int sb200_arena_selftest(uint64_t seed, uint32_t ops) {

@@ -102,6 +102,7 @@ static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 typedef void* cudaMemPool_t;
 static inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* p, int) { *p = nullptr; return cudaSuccess; }
 static inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, int, void*) { return cudaSuccess; }
+static inline cudaError_t cudaMemPoolTrimTo(cudaMemPool_t, size_t) { return cudaSuccess; }
 struct cudaDeviceProp { int persistingL2CacheMaxSize; int accessPolicyMaxWindowSize; };
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->persistingL2CacheMaxSize = 0; p->accessPolicyMaxWindowSize = 0; return cudaSuccess; }
 static inline cudaError_t cudaDeviceSetLimit(int, size_t) { return cudaSuccess; }
