@@ -422,7 +422,7 @@ def main():
                 # process (own CUDA context, bounded time), reported beside -- never instead of -- the default kernels
                 try:
                     r = subprocess.run([sys.executable, "-m", "stract_b200.bm25_bench", str(local_rank)], cwd=ROOT,
-                                       capture_output=True, text=True, timeout=420)
+                                       capture_output=True, text=True, timeout=180)
                     line["bm25"]["experimental"] = (json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0
                                                     else {"error": (r.stderr or r.stdout)[-400:]})
                 except Exception as ex:  # noqa: BLE001
