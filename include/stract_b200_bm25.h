@@ -48,6 +48,14 @@ SB200_API int sb200_segment_create(const uint8_t* postings_file, uint64_t postin
                                    int record_option, int device, sb200_segment** out);
 SB200_API void sb200_segment_destroy(sb200_segment* seg);
 
+/* The "term ordinal -> TermInfo" half of the term dictionary: decodes a whole tantivy TermInfoStore
+ * (tantivy/src/termdict/fst_termdict/term_info_store.rs: 256-term blocks, a 47-byte TermInfoBlockMeta each, bit-packed
+ * offsets) on the device, one thread per ordinal, into the array sb200_segment_create takes.  `store` may be host or
+ * device memory, `infos` receives min(cap, n) entries, *n_terms the number of terms.  (The FST that maps term bytes to an
+ * ordinal is an external crate that is not part of the reference tree; callers address terms by ordinal.) */
+SB200_API int sb200_term_info_store_decode(const uint8_t* store, uint64_t len, int device, sb200_term_info* infos, uint64_t cap,
+                                           uint64_t* n_terms);
+
 typedef struct { uint64_t n_terms, n_blocks, n_postings, hbm_bytes; uint32_t max_doc; uint32_t _pad; double stage_ms; } sb200_segment_info;
 SB200_API int sb200_segment_get_info(const sb200_segment* seg, sb200_segment_info* info);
 

@@ -696,3 +696,104 @@ ORC_API float orc_cursor_max_score(void* c) { return ((TermScorer*)c)->max_sc; }
 ORC_API float orc_cursor_block_max_score(void* c) { return ((TermScorer*)c)->block_max_score(); }
 ORC_API uint32_t orc_cursor_last_doc_in_block(void* c) { return ((TermScorer*)c)->last_doc_in_block(); }
 ORC_API int orc_p2_proto_marker(void) { return 1; }
+
+// ---------------------------------------------------------------- term info store --------------
+// TermInfoStore (tantivy/src/termdict/fst_termdict/term_info_store.rs): blocks of 256 TermInfos; the first of a block
+// is stored verbatim in a 47-byte TermInfoBlockMeta (:14-48), the other 255 as bit-packed offsets relative to it
+// (:176-262), read back with unaligned 8-byte loads (:102-122,134-153).  BitPacker = tantivy's own LSB-first 64-bit
+// mini-buffer (tantivy/src/bitpacker/bitpacker.rs:18-68), compute_num_bits (bitpacker/mod.rs:32-39).
+namespace tis {
+struct Info { uint32_t df; uint64_t ps, pe, qs, qe; };  // doc_freq, postings range, positions range
+struct Packer {
+  uint64_t mini = 0; size_t written = 0;
+  void write(uint64_t v, uint8_t nb, std::vector<uint8_t>& out) {
+    if (written + nb > 64) {
+      mini |= (written < 64) ? (v << written) : 0;
+      for (int i = 0; i < 8; i++) out.push_back((uint8_t)(mini >> (8 * i)));
+      const size_t sh = 64 - written;
+      mini = sh >= 64 ? 0 : (v >> sh);
+      written = written + nb - 64;
+    } else {
+      mini |= (written < 64) ? (v << written) : 0;
+      written += nb;
+      if (written == 64) { for (int i = 0; i < 8; i++) out.push_back((uint8_t)(mini >> (8 * i))); written = 0; mini = 0; }
+    }
+  }
+  void flush(std::vector<uint8_t>& out) {
+    if (written > 0) { const size_t nbytes = (written + 7) / 8; for (size_t i = 0; i < nbytes; i++) out.push_back((uint8_t)(mini >> (8 * i))); written = 0; mini = 0; }
+  }
+};
+static uint8_t num_bits(uint64_t n) { const uint8_t a = n ? (uint8_t)(64 - __builtin_clzll(n)) : 0; return a <= 56 ? a : 64; }
+static void put64(std::vector<uint8_t>& o, uint64_t v) { for (int i = 0; i < 8; i++) o.push_back((uint8_t)(v >> (8 * i))); }
+static void put32(std::vector<uint8_t>& o, uint32_t v) { for (int i = 0; i < 4; i++) o.push_back((uint8_t)(v >> (8 * i))); }
+static uint64_t get64(const uint8_t* p) { uint64_t v = 0; for (int i = 0; i < 8; i++) v |= (uint64_t)p[i] << (8 * i); return v; }
+static uint32_t get32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+static uint64_t extract_bits(const uint8_t* data, size_t len, size_t addr_bits, uint8_t nb) {  // :102-122
+  const size_t ab = addr_bits / 8; const unsigned sh = addr_bits % 8;
+  uint8_t buf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (size_t i = 0; i < 8 && ab + i < len; i++) buf[i] = data[ab + i];
+  const uint64_t v = get64(buf) >> sh;
+  return v & ((1ull << nb) - 1ull);
+}
+static void flush_block(std::vector<Info>& b, std::vector<uint8_t>& metas, std::vector<uint8_t>& infos) {
+  if (b.empty()) return;
+  Packer bp;
+  const Info ref = b[0], last = b.back();
+  const uint64_t post_end = last.pe - ref.ps, pos_end = last.qe - ref.qs;
+  uint32_t max_df = 0;
+  for (size_t i = 1; i < b.size(); i++) { b[i].ps -= ref.ps; b[i].qs -= ref.qs; max_df = std::max(max_df, b[i].df); }
+  const uint8_t dfb = num_bits(max_df), pb = num_bits(post_end), qb = num_bits(pos_end);
+  put64(metas, infos.size());
+  put32(metas, ref.df); put64(metas, ref.ps); put64(metas, ref.pe - ref.ps); put64(metas, ref.qs); put64(metas, ref.qe - ref.qs);
+  metas.push_back(dfb); metas.push_back(pb); metas.push_back(qb);
+  for (size_t i = 1; i < b.size(); i++) { bp.write(b[i].ps, pb, infos); bp.write(b[i].qs, qb, infos); bp.write(b[i].df, dfb, infos); }
+  bp.write(post_end, pb, infos); bp.write(pos_end, qb, infos);
+  bp.flush(infos);
+  b.clear();
+}
+}  // namespace tis
+
+// writes the store for n TermInfos; returns the byte length (call with out == NULL first)
+ORC_API uint64_t orc_tis_write(const uint32_t* df, const uint64_t* ps, const uint64_t* pe, const uint64_t* qs, const uint64_t* qe,
+                               uint64_t n, uint8_t* out) {
+  std::vector<uint8_t> metas, infos; std::vector<tis::Info> blk;
+  for (uint64_t i = 0; i < n; i++) {
+    blk.push_back(tis::Info{df[i], ps[i], pe[i], qs[i], qe[i]});
+    if (blk.size() >= 256) tis::flush_block(blk, metas, infos);
+  }
+  tis::flush_block(blk, metas, infos);
+  std::vector<uint8_t> file;
+  tis::put64(file, metas.size()); tis::put64(file, n);
+  file.insert(file.end(), metas.begin(), metas.end());
+  file.insert(file.end(), infos.begin(), infos.end());
+  if (out) memcpy(out, file.data(), file.size());
+  return file.size();
+}
+// TermInfoStore::get (:134-153)
+ORC_API void orc_tis_get(const uint8_t* file, uint64_t len, uint64_t ord, uint32_t* df, uint64_t* ps, uint64_t* pe, uint64_t* qs, uint64_t* qe) {
+  const uint64_t meta_len = tis::get64(file);
+  const uint8_t* metas = file + 16; const uint8_t* infos = metas + meta_len; const size_t infos_len = (size_t)(len - 16 - meta_len);
+  const uint8_t* m = metas + (ord / 256) * 47;
+  const uint64_t off = tis::get64(m);
+  const uint32_t rdf = tis::get32(m + 8); const uint64_t rps = tis::get64(m + 12), rpl = tis::get64(m + 20), rqs = tis::get64(m + 28), rql = tis::get64(m + 36);
+  const uint8_t dfb = m[44], pb = m[45], qb = m[46];
+  const uint64_t inner = ord % 256;
+  if (inner == 0) { *df = rdf; *ps = rps; *pe = rps + rpl; *qs = rqs; *qe = rqs + rql; return; }
+  const size_t nb = (size_t)dfb + pb + qb, a0 = nb * (inner - 1);
+  const uint8_t* d = infos + off; const size_t dl = infos_len - (size_t)off;
+  *ps = rps + tis::extract_bits(d, dl, a0, pb);
+  *pe = rps + tis::extract_bits(d, dl, a0 + nb, pb);
+  *qs = rqs + tis::extract_bits(d, dl, a0 + pb, qb);
+  *qe = rqs + tis::extract_bits(d, dl, a0 + pb + nb, qb);
+  *df = (uint32_t)tis::extract_bits(d, dl, a0 + pb + qb, dfb);
+}
+ORC_API uint64_t orc_tis_num_terms(const uint8_t* file) { return tis::get64(file + 8); }
+// bitpacker KAT hook (term_info_store.rs:293-308): packs vals[i] at bits[i] and returns the byte length
+ORC_API uint64_t orc_bitpack(const uint64_t* vals, const uint8_t* bits, uint32_t n, uint8_t* out) {
+  tis::Packer bp; std::vector<uint8_t> o;
+  for (uint32_t i = 0; i < n; i++) bp.write(vals[i], bits[i], o);
+  bp.flush(o);
+  memcpy(out, o.data(), o.size());
+  return o.size();
+}
+ORC_API uint64_t orc_extract_bits(const uint8_t* data, uint64_t len, uint64_t addr_bits, uint8_t nb) { return tis::extract_bits(data, (size_t)len, (size_t)addr_bits, nb); }

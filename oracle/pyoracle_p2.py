@@ -27,6 +27,11 @@ def proto(L, f):
     f("orc_seg_avg_fieldnorm", f32, vp)
     f("orc_seg_set_avg_fieldnorm", None, vp, f32)
     f("orc_seg_set_record", None, vp, i32)
+    f("orc_tis_write", u64, _u32p, _u64p, _u64p, _u64p, _u64p, u64, vp)
+    f("orc_tis_get", None, _u8p, u64, u64, C.POINTER(u32), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64))
+    f("orc_tis_num_terms", u64, _u8p)
+    f("orc_bitpack", u64, _u64p, _u8p, u32, _u8p)
+    f("orc_extract_bits", u64, _u8p, u64, u64, C.c_uint8)
     f("orc_seg_add_term", u32, vp, _u32p, _u32p, u32)
     f("orc_seg_postings_len", u64, vp)
     f("orc_seg_postings_copy", None, vp, _u8p)
@@ -220,3 +225,39 @@ class Cursor:
             self.L.orc_cursor_free(self.h)
         except Exception:
             pass
+
+
+# ---- TermInfoStore (tantivy/src/termdict/fst_termdict/term_info_store.rs) -------------------------------------------
+def term_info_store_write(doc_freq, post_start, post_end, pos_start=None, pos_end=None):
+    """TermInfoStoreWriter: bytes of the store for the given TermInfos (positions ranges default to empty)."""
+    L = _L()
+    df = np.ascontiguousarray(doc_freq, np.uint32); n = df.size
+    ps = np.ascontiguousarray(post_start, np.uint64); pe = np.ascontiguousarray(post_end, np.uint64)
+    qs = np.zeros(n, np.uint64) if pos_start is None else np.ascontiguousarray(pos_start, np.uint64)
+    qe = np.zeros(n, np.uint64) if pos_end is None else np.ascontiguousarray(pos_end, np.uint64)
+    ln = L.orc_tis_write(df, ps, pe, qs, qe, n, None)
+    out = np.zeros(ln, np.uint8)
+    L.orc_tis_write(df, ps, pe, qs, qe, n, out.ctypes.data)
+    return out
+
+
+def term_info_store_get(store, ord_):
+    """TermInfoStore::get -> (doc_freq, postings_start, postings_end, positions_start, positions_end)."""
+    L = _L()
+    store = np.ascontiguousarray(store, np.uint8)
+    df = C.c_uint32(); a, b, c, d = (C.c_uint64() for _ in range(4))
+    L.orc_tis_get(store, store.size, int(ord_), C.byref(df), C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+    return df.value, a.value, b.value, c.value, d.value
+
+
+def bitpack(vals, bits):
+    L = _L()
+    v = np.ascontiguousarray(vals, np.uint64); b = np.ascontiguousarray(bits, np.uint8)
+    out = np.zeros(8 * v.size + 8, np.uint8)
+    n = L.orc_bitpack(v, b, v.size, out)
+    return out[:n]
+
+
+def extract_bits(data, addr_bits, num_bits):
+    d = np.ascontiguousarray(data, np.uint8)
+    return int(_L().orc_extract_bits(d, d.size, int(addr_bits), int(num_bits)))

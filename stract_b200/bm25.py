@@ -135,6 +135,18 @@ def encode_postings_csr(docs, tfs, off, fieldnorm_ids, avg_fieldnorm, threads=8,
     return out[:ln.value], infos
 
 
+def decode_term_info_store(store, device=0):
+    """TermInfoStore bytes (the `.term` store behind tantivy's FST term dictionary) -> TermInfo array, decoded on the
+    device (sb200_term_info_store_decode); pass the result to SegmentReader."""
+    L = lib()
+    store = np.ascontiguousarray(store, np.uint8)
+    n = C.c_uint64(0)
+    check(L.sb200_term_info_store_decode(_p(store), store.size, device, None, 0, C.byref(n)))
+    infos = (B.TermInfo * max(n.value, 1))()
+    check(L.sb200_term_info_store_decode(_p(store), store.size, device, infos, n.value, C.byref(n)))
+    return infos, int(n.value)
+
+
 class SegmentReader:
     """One field of one segment resident in HBM (postings file + fieldnorms + block directory)."""
 

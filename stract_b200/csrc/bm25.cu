@@ -837,7 +837,76 @@ static int run_batch(sb200_segment* g, const sb200_bm25_batch* b, int mode, cons
 }  // namespace sb200
 using namespace sb200;
 
+namespace sb200 {
+// TermInfoStore::get for every term ordinal (tantivy/src/termdict/fst_termdict/term_info_store.rs:55-99,134-153): the
+// block's first TermInfo comes verbatim from its 47-byte TermInfoBlockMeta, the other 255 are bit-packed offsets
+// relative to it, read with the reference's unaligned little-endian 8-byte window (:102-122).
+__device__ __forceinline__ uint64_t tis_u64(const uint8_t* p, uint64_t avail) {
+  uint64_t v = 0;
+  for (uint32_t i = 0; i < 8u && i < avail; i++) v |= (uint64_t)p[i] << (8u * i);
+  return v;
+}
+__device__ __forceinline__ uint64_t tis_bits(const uint8_t* data, uint64_t len, uint64_t addr_bits, uint32_t nb) {
+  const uint64_t ab = addr_bits >> 3;
+  if (ab >= len) return 0;
+  const uint64_t v = tis_u64(data + ab, len - ab) >> (addr_bits & 7u);
+  return v & ((1ull << nb) - 1ull);
+}
+__global__ void k_term_info_store(const uint8_t* __restrict__ file, uint64_t len, uint64_t meta_len, uint64_t n_terms,
+                                  sb200_term_info* out, int* err) {
+  const uint64_t ord = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (ord >= n_terms) return;
+  const uint8_t* m = file + 16 + (ord >> 8) * 47;
+  const uint8_t* infos = file + 16 + meta_len;
+  const uint64_t infos_len = len - 16 - meta_len;
+  const uint64_t off = tis_u64(m, 8);
+  const uint32_t rdf = (uint32_t)tis_u64(m + 8, 4);
+  const uint64_t rps = tis_u64(m + 12, 8), rpl = tis_u64(m + 20, 8);
+  const uint32_t dfb = m[44], pb = m[45], qb = m[46];
+  const uint32_t inner = (uint32_t)(ord & 255u);
+  sb200_term_info ti; ti._pad = 0;
+  if (inner == 0) { ti.postings_off = rps; ti.postings_len = rpl; ti.doc_freq = rdf; }
+  else {
+    if (off > infos_len || dfb > 56 || pb > 56 || qb > 56) { *err = 1; return; }
+    const uint64_t nb = (uint64_t)dfb + pb + qb, a0 = nb * (inner - 1);
+    const uint8_t* d = infos + off; const uint64_t dl = infos_len - off;
+    const uint64_t ps = rps + tis_bits(d, dl, a0, pb), pe = rps + tis_bits(d, dl, a0 + nb, pb);
+    if (pe < ps) { *err = 2; return; }
+    ti.postings_off = ps; ti.postings_len = pe - ps;
+    ti.doc_freq = (uint32_t)tis_bits(d, dl, a0 + pb + qb, dfb);
+  }
+  out[ord] = ti;
+}
+}  // namespace sb200
+
 extern "C" {
+
+int sb200_term_info_store_decode(const uint8_t* store, uint64_t len, int device, sb200_term_info* infos, uint64_t cap,
+                                 uint64_t* n_terms) {
+  using namespace sb200;
+  if (!store || !n_terms) SB_FAIL(SB200_EINVAL, "NULL argument");
+  if (len < 16) SB_FAIL(SB200_EFORMAT, "term info store shorter than its 16-byte header");
+  SB_CUDA(cudaSetDevice(device));
+  uint8_t head[16];
+  SB_CUDA(cudaMemcpy(head, store, 16, cudaMemcpyDefault));
+  uint64_t meta_len = 0, n = 0;
+  memcpy(&meta_len, head, 8); memcpy(&n, head + 8, 8);
+  if (meta_len > len - 16 || meta_len != 47ull * ((n + 255) / 256)) SB_FAIL(SB200_EFORMAT, "term info store: %llu terms need %llu bytes of block metadata, header says %llu", (unsigned long long)n, (unsigned long long)(47ull * ((n + 255) / 256)), (unsigned long long)meta_len);
+  *n_terms = n;
+  const uint64_t k = std::min<uint64_t>(n, cap);
+  if (!infos || k == 0) return SB200_OK;
+  DevBuf<uint8_t> d_store; DevBuf<sb200_term_info> d_out; DevBuf<int> d_err;
+  SB_TRY(d_store.alloc(len)); SB_TRY(d_out.alloc(n)); SB_TRY(d_err.alloc(1));
+  SB_CUDA(cudaMemcpy(d_store.p, store, len, cudaMemcpyDefault));
+  SB_CUDA(cudaMemset(d_err.p, 0, sizeof(int)));
+  SB_LAUNCH(k_term_info_store, div_up(n, 256), 256, 0, (cudaStream_t)0, d_store.p, len, meta_len, n, d_out.p, d_err.p);
+  SB_CHECK_LAUNCH();
+  int h_err = 0;
+  SB_CUDA(cudaMemcpy(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (h_err) SB_FAIL(SB200_EFORMAT, "term info store is inconsistent (code %d)", h_err);
+  SB_CUDA(cudaMemcpy(infos, d_out.p, k * sizeof(sb200_term_info), cudaMemcpyDefault));
+  return SB200_OK;
+}
 
 int sb200_segment_create(const uint8_t* postings_file, uint64_t postings_len, const sb200_term_info* terms, uint32_t n_terms,
                          const uint8_t* fieldnorm_ids, uint32_t max_doc, int record_option, int device, sb200_segment** out) {

@@ -46,6 +46,7 @@ def test_default_kernels_against_oracle(emulated):
     T.test_signal_combine_bit_exact()
     import test_round1_late_gpu as late
     late.test_positions_record_option_skip_entries()
+    late.test_term_info_store_decoded_on_device()
     T.test_malformed_postings_rejected()
     import test_golden
     test_golden.check_path2_against_golden()   # committed fixtures, no oracle call

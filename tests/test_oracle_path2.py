@@ -276,3 +276,21 @@ def test_stract_bm25_and_linear_combine():
     ranked = sorted(totals.items(), key=lambda kv: (-kv[1], kv[0]))[:50]
     assert list(d) == [k for k, _ in ranked]
     assert np.array_equal(tot, np.array([v for _, v in ranked]))
+
+
+def test_term_info_store_reference_kats():
+    """tantivy/src/termdict/fst_termdict/term_info_store.rs:293-308 (test_bitpacked) and :330-357 (test_pack), the
+    compute_num_bits values quoted there, and the fixed 47-byte TermInfoBlockMeta (:50-53)."""
+    from oracle import bitpack, extract_bits, term_info_store_get, term_info_store_write
+    buf = bitpack([321, 2, 51], [9, 2, 6])
+    assert len(buf) == 3
+    assert extract_bits(buf, 0, 9) == 321 and extract_bits(buf, 9, 2) == 2 and extract_bits(buf, 11, 6) == 51
+    off = lambda i: i * 13 + i * i   # noqa: E731
+    n = 1000
+    df = np.arange(n, dtype=np.uint32)
+    ps = np.array([off(i) for i in range(n)], np.uint64); pe = np.array([off(i + 1) for i in range(n)], np.uint64)
+    store = term_info_store_write(df, ps, pe, ps * 3, pe * 3)
+    meta_len = int(store[:8].view(np.uint64)[0])
+    assert int(store[8:16].view(np.uint64)[0]) == n and meta_len == 47 * ((n + 255) // 256)
+    for i in range(n):
+        assert term_info_store_get(store, i) == (i, off(i), off(i + 1), off(i) * 3, off(i + 1) * 3), i

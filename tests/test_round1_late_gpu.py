@@ -58,3 +58,30 @@ def test_rank_assignment_matches_store_harmonic_order():
     tlo, thi, tc = got.top
     assert np.array_equal(tlo, got.ids_lo[torder]) and np.array_equal(thi, got.ids_hi[torder]) and np.array_equal(tc, got.values[torder])
     assert [c for _, c in got.top_nodes(10)] == sorted(got.values, reverse=True)[:10]
+
+
+def test_term_info_store_decoded_on_device():
+    """SURVEY 8(f) rank 2, the ordinal -> TermInfo half: the device decoder of tantivy's TermInfoStore against the store
+    bytes the oracle's TermInfoStoreWriter produces -- the reference's own test_pack case (term_info_store.rs:330-357)
+    and the TermInfo table of a real postings file, which must open the same segment."""
+    import oracle
+    from stract_b200 import bm25
+    off = lambda i: i * 13 + i * i   # noqa: E731
+    n = 1000
+    ps = np.array([off(i) for i in range(n)], np.uint64); pe = np.array([off(i + 1) for i in range(n)], np.uint64)
+    store = oracle.term_info_store_write(np.arange(n, dtype=np.uint32), ps, pe, ps * 3, pe * 3)
+    infos, cnt = bm25.decode_term_info_store(store)
+    assert cnt == n
+    for i in range(n):
+        assert (infos[i].doc_freq, infos[i].postings_off, infos[i].postings_len) == (i, off(i), off(i + 1) - off(i)), i
+    (oseg, seg), rng = random_index(19, 60_000, DFS)
+    data = oseg.postings_bytes()
+    t_off, t_len, t_df = oseg.term_infos()
+    store = oracle.term_info_store_write(t_df, t_off, t_off + t_len)
+    infos, cnt = bm25.decode_term_info_store(store)
+    assert cnt == len(DFS)
+    seg2 = bm25.SegmentReader(data, infos, oseg.fieldnorm_ids)
+    for q in ([len(DFS) - 1, len(DFS) - 2], [3, len(DFS) - 1], [len(DFS) - 4]):
+        for mode in (MODE_AND, MODE_OR):
+            assert TopDocs.with_limit(100).search(seg, q, mode) == TopDocs.with_limit(100).search(seg2, q, mode)
+    seg.close(); seg2.close()
