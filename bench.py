@@ -438,9 +438,10 @@ def main():
             except Exception:  # noqa: BLE001
                 pass
             variants = [("l2_persist_64MB", {"SB200_L2_PERSIST_MB": "64"}, ["--no-e2e", "--steps", "3"]),
+                        ("l2_evict_first_hints", {"SB200_L2_HINTS": "1"}, ["--no-e2e", "--steps", "3"]),
                         ("e2e_arena_rowperm", {"SB200_ARENA": "1", "SB200_STAGE_ROWPERM": "1"}, ["--steps", "1", "--e2e-steps", "3"])]
             for name, env, extra in variants:
-                if time.perf_counter() - t_bench0 > 270:
+                if time.perf_counter() - t_bench0 > 300:
                     exp[name] = {"skipped": "bench time budget"}
                     continue
                 try:

@@ -168,9 +168,10 @@ __global__ void k_bm_fill(uint32_t* bm, uint64_t N, uint64_t words) {
 __device__ __forceinline__ bool owned_row(const PeerOut& o, uint32_t row) {
   return o.world <= 1u || ((row >> 5) % o.world) == o.rank;
 }
+template <bool HINT = false>
 __device__ __forceinline__ void publish_row(uint4* __restrict__ newr, uint32_t* __restrict__ bm_cur, const PeerOut& peers,
-                                            uint32_t row, uint32_t sub, uint4 acc, bool write, bool changed) {
-  if (write) newr[(uint64_t)row * 4 + sub] = acc;
+                                            uint32_t row, uint32_t sub, uint4 acc, bool write, bool changed, uint64_t pol = 0) {
+  if (write) { if (HINT) st_hint_u4(newr + (uint64_t)row * 4 + sub, acc, pol); else newr[(uint64_t)row * 4 + sub] = acc; }
   if (changed && sub == 0) atomicOr(bm_cur + (row >> 5), 1u << (row & 31));
   for (int p = 0; p < peers.n; p++) {
     if (write) peers.newr[p][(uint64_t)row * 4 + sub] = acc;
@@ -185,7 +186,7 @@ __device__ __forceinline__ bool bm_test(const uint32_t* __restrict__ bm, uint32_
 }
 
 // ---- pull, short rows: 4 lanes per destination row ----------------------------------------------------
-template <bool FRONTIER>
+template <bool FRONTIER, bool HINT = false>
 __global__ void __launch_bounds__(256, 7) k_pull_quad(uint64_t row_begin, uint64_t row_end,
     const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col, uint32_t col_base,
     const uint4* __restrict__ oldr, uint4* __restrict__ newr,
@@ -199,17 +200,18 @@ __global__ void __launch_bounds__(256, 7) k_pull_quad(uint64_t row_begin, uint64
   live = live && owned_row(peers, (uint32_t)row);
   if (__ballot_sync(0xffffffffu, live) == 0u) return;  // none of this warp's rows belongs to this rank
   const uint32_t e0 = live ? row_ptr[row] - col_base : 0u, e1 = live ? row_ptr[row + 1] - col_base : 0u;
-  const uint4 own = oldr[row * 4 + sub];
+  const uint64_t pol = HINT ? l2_policy_evict_first() : 0ull;
+  const uint4 own = HINT ? ld_hint_u4(oldr + row * 4 + sub, pol) : oldr[row * 4 + sub];
   uint4 acc = own;
   // lane `sub` fetches source index e+sub (one 16-B request per quad per 4 edges, prefetched one step ahead)
   // and the quad shares the four indices by shuffle; an out-of-range or (FRONTIER) unchanged source is
   // redirected to the row itself, which is a no-op under max and hits L1.
   const unsigned qmask = 0xFu << (lane & ~3u);
   const uint32_t self = (uint32_t)row;
-  uint32_t nxt = (e0 + sub < e1) ? ld_stream_u32(col + e0 + sub) : self;
+  uint32_t nxt = (e0 + sub < e1) ? (HINT ? ld_stream_hint_u32(col + e0 + sub, pol) : ld_stream_u32(col + e0 + sub)) : self;
   for (uint32_t e = e0; e < e1; e += 4) {
     uint32_t mine = nxt;
-    nxt = (e + 4 + sub < e1) ? ld_stream_u32(col + e + 4 + sub) : self;
+    nxt = (e + 4 + sub < e1) ? (HINT ? ld_stream_hint_u32(col + e + 4 + sub, pol) : ld_stream_u32(col + e + 4 + sub)) : self;
     if (FRONTIER) mine = bm_test(bm_prev, mine) ? mine : self;
     const uint32_t i0 = __shfl_sync(qmask, mine, 0, 4);
     const uint32_t i1 = __shfl_sync(qmask, mine, 1, 4);
@@ -224,11 +226,11 @@ __global__ void __launch_bounds__(256, 7) k_pull_quad(uint64_t row_begin, uint64
   const unsigned ball = __ballot_sync(0xffffffffu, ne_u4(acc, own));
   const bool changed = ((ball >> (lane & ~3u)) & 0xFu) != 0u;
   if (!live) return;
-  publish_row(newr, bm_cur, peers, (uint32_t)row, sub, acc, changed || bm_test(bm_prev, (uint32_t)row), changed);
+  publish_row<HINT>(newr, bm_cur, peers, (uint32_t)row, sub, acc, changed || bm_test(bm_prev, (uint32_t)row), changed, pol);
 }
 
 // ---- pull, long rows: one warp per <=CHUNK_EDGES work item ---------------------------------------------
-template <bool FRONTIER>
+template <bool FRONTIER, bool HINT = false>
 // 8 CTAs/SM (<= 32 registers): at full scale the gathers are DRAM-latency bound and the kernel's speed tracks the
 // number of resident warps (36 registers = 7 CTAs measured 11 % slower than 32 registers = 8 CTAs)
 __global__ void __launch_bounds__(256, 8) k_pull_warp(uint64_t n_items, uint64_t first_multi_free_item,
@@ -246,12 +248,13 @@ __global__ void __launch_bounds__(256, 8) k_pull_warp(uint64_t n_items, uint64_t
   const uint32_t e0 = rs + chunk * (uint32_t)CHUNK_EDGES;
   const uint32_t e1 = min(e0 + (uint32_t)CHUNK_EDGES, re);
   uint4 acc = make_uint4(0, 0, 0, 0);
+  const uint64_t pol = HINT ? l2_policy_evict_first() : 0ull;
   // out-of-range lanes and (FRONTIER) unchanged sources are redirected to the row itself: merging one's own row
   // is a no-op under max and hits L1, so the gather loop is branch-free
-  uint32_t nxt = (e0 + lane < e1) ? ld_stream_u32(col + e0 + lane) : row;
+  uint32_t nxt = (e0 + lane < e1) ? (HINT ? ld_stream_hint_u32(col + e0 + lane, pol) : ld_stream_u32(col + e0 + lane)) : row;
   for (uint32_t base = e0; base < e1; base += 32) {
     uint32_t mine = nxt;
-    nxt = (base + 32 + lane < e1) ? ld_stream_u32(col + base + 32 + lane) : row;
+    nxt = (base + 32 + lane < e1) ? (HINT ? ld_stream_hint_u32(col + base + 32 + lane, pol) : ld_stream_u32(col + base + 32 + lane)) : row;
     if (FRONTIER) mine = bm_test(bm_prev, mine) ? mine : row;
     const uint32_t i0 = __shfl_sync(0xffffffffu, mine, q);
     const uint32_t i1 = __shfl_sync(0xffffffffu, mine, q + 8);
@@ -274,11 +277,11 @@ __global__ void __launch_bounds__(256, 8) k_pull_warp(uint64_t n_items, uint64_t
     if (q == 0) partial[item * 4 + sub] = acc;
     return;
   }
-  const uint4 own = oldr[(uint64_t)row * 4 + sub];
+  const uint4 own = HINT ? ld_hint_u4(oldr + (uint64_t)row * 4 + sub, pol) : oldr[(uint64_t)row * 4 + sub];
   acc = vmax_u8x16(acc, own);
   const unsigned ball = __ballot_sync(0xffffffffu, ne_u4(acc, own));
   const bool changed = (ball & 0xFu) != 0u;
-  if (q == 0) publish_row(newr, bm_cur, peers, row, sub, acc, changed || bm_test(bm_prev, row), changed);
+  if (q == 0) publish_row<HINT>(newr, bm_cur, peers, row, sub, acc, changed || bm_test(bm_prev, row), changed, pol);
 }
 
 // rows spanning several work items: one warp reduces the parked partials
@@ -530,9 +533,11 @@ static int launch_pull(sb200_graph* g, const uint4* oldr, uint4* newr, const uin
   const int FW = FRONTIER ? sb200_graph::F_PULL_WARP_FRONT : sb200_graph::F_PULL_WARP_DENSE;
   const int FQ = FRONTIER ? sb200_graph::F_PULL_QUAD_FRONT : sb200_graph::F_PULL_QUAD_DENSE;
   const double per_edge = FRONTIER ? 4.0 : 68.0;  // col index (+ the 64-B gather when every source is read)
+  static const bool hints = getenv("SB200_L2_HINTS") != nullptr;  // experiment switch, see common.cuh
   if (g->n_items) {
     PROF_BEGIN(g, FW);
-    SB_LAUNCH(k_pull_warp<FRONTIER>, div_up(g->n_items * 32, 256), 256, 0, s, g->n_items, g->n_multi_items,
+    auto kw = hints ? k_pull_warp<FRONTIER, true> : k_pull_warp<FRONTIER, false>;
+    SB_LAUNCH(kw, div_up(g->n_items * 32, 256), 256, 0, s, g->n_items, g->n_multi_items,
               g->item_row.p, g->item_start.p, (uint32_t)g->warp_row_begin, g->row_ptr.p, g->col.p, g->col_base, oldr, newr,
               g->partial.p, bmp, bmc, po);
     SB_CHECK_LAUNCH();
@@ -548,7 +553,8 @@ static int launch_pull(sb200_graph* g, const uint4* oldr, uint4* newr, const uin
   const uint64_t nq = g->quad_row_end - g->quad_row_begin;
   if (nq) {
     PROF_BEGIN(g, FQ);
-    SB_LAUNCH(k_pull_quad<FRONTIER>, div_up(nq * 4, 256), 256, 0, s, g->quad_row_begin, g->quad_row_end, g->row_ptr.p,
+    auto kq = hints ? k_pull_quad<FRONTIER, true> : k_pull_quad<FRONTIER, false>;
+    SB_LAUNCH(kq, div_up(nq * 4, 256), 256, 0, s, g->quad_row_begin, g->quad_row_end, g->row_ptr.p,
               g->col.p, g->col_base, oldr, newr, bmp, bmc, po);
     SB_CHECK_LAUNCH();
     PROF_END(g, FQ, per_edge * (double)g->E_quad + 68.0 * (double)nq);

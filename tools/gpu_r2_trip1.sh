@@ -19,6 +19,7 @@ pick='import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); 
 for v in "" "SB200_ARENA=1" "SB200_STAGE_ROWPERM=1" "SB200_ARENA=1 SB200_STAGE_ROWPERM=1"; do
   echo; echo "== e2e with [$v]"; env $v timeout 150 $B 2> gpurun_out/r2_e2e.err | python -c "$pick" || tail -3 gpurun_out/r2_e2e.err
 done
+echo; echo "== SB200_L2_HINTS=1"; env SB200_L2_HINTS=1 timeout 150 $B --no-e2e 2> gpurun_out/r2_l2.err | python -c 'import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print("ms/step %.2f" % d["ms_per_step"], [(k["name"], round(k["ms"]/k["launches"],3)) for k in d["kernels"]])' || tail -3 gpurun_out/r2_l2.err
 for mb in 32 64 96; do
   echo; echo "== SB200_L2_PERSIST_MB=$mb"; env SB200_L2_PERSIST_MB=$mb timeout 150 $B --no-e2e 2> gpurun_out/r2_l2.err | python -c 'import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print("ms/step %.2f" % d["ms_per_step"], [(k["name"], round(k["ms"]/k["launches"],3)) for k in d["kernels"]])' || tail -3 gpurun_out/r2_l2.err
 done
