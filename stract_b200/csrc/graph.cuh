@@ -80,7 +80,8 @@ struct sb200_graph {
   cudaEvent_t prof_ev[F_COUNT][2] = {{nullptr}};
   bool prof_used[F_COUNT] = {false};
   double prof_step_bytes[F_COUNT] = {0};
-  uint64_t E_warp = 0, E_quad = 0;   // edges of the owned warp-class / quad-class rows
+  uint64_t E_warp = 0, E_quad = 0;   // edges of the warp-class / quad-class rows
+  double own_frac = 1.0;             // sharded handles: fraction of the rows / edges of every class this rank owns
   cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr;
   float last_run_ms = 0;
 

@@ -662,6 +662,8 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
     g->E_warp = rp[1] - rp[0];
     g->E_quad = (g->quad_row_end > g->quad_row_begin) ? rp[2] - rp[1] : 0;
   }
+  g->own_frac = 1.0;
+  if (g->world > 1 && E) g->own_frac = (double)g->E_local / (double)E;   // share of every degree class this rank owns (interleaved blocks)
   const uint64_t nwr = g->warp_row_end - g->warp_row_begin;
   g->n_items = 0; g->n_multi_rows = 0; g->n_multi_items = 0;
   if (nwr) {

@@ -541,7 +541,7 @@ static int launch_pull(sb200_graph* g, const uint4* oldr, uint4* newr, const uin
               g->item_row.p, g->item_start.p, (uint32_t)g->warp_row_begin, g->row_ptr.p, g->col.p, g->col_base, oldr, newr,
               g->partial.p, bmp, bmc, po);
     SB_CHECK_LAUNCH();
-    PROF_END(g, FW, per_edge * (double)g->E_warp + 68.0 * (double)(g->warp_row_end - g->warp_row_begin - g->n_multi_rows));
+    PROF_END(g, FW, g->own_frac * (per_edge * (double)g->E_warp + 68.0 * (double)(g->warp_row_end - g->warp_row_begin - g->n_multi_rows)));
   }
   if (g->n_multi_rows) {
     PROF_BEGIN(g, sb200_graph::F_PULL_MERGE);
@@ -557,7 +557,7 @@ static int launch_pull(sb200_graph* g, const uint4* oldr, uint4* newr, const uin
     SB_LAUNCH(kq, div_up(nq * 4, 256), 256, 0, s, g->quad_row_begin, g->quad_row_end, g->row_ptr.p,
               g->col.p, g->col_base, oldr, newr, bmp, bmc, po);
     SB_CHECK_LAUNCH();
-    PROF_END(g, FQ, per_edge * (double)g->E_quad + 68.0 * (double)nq);
+    PROF_END(g, FQ, g->own_frac * (per_edge * (double)g->E_quad + 68.0 * (double)nq));
   }
   return SB200_OK;
 }
