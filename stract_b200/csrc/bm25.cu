@@ -789,7 +789,13 @@ static int run_batch(sb200_segment* g, const sb200_bm25_batch* b, int mode, cons
     if (kmode == 2) SB_TRY(launch_topk<2>(P, nq, s));
     else if (kmode == 0) SB_TRY(launch_topk<0>(P, nq, s));
     else SB_TRY(launch_topk<1>(P, nq, s));
-  } else if (kmode == 0 && getenv("SB200_BM25_AND3") != nullptr) {
+  } else if (kmode == 0 && getenv("SB200_BM25_AND3") != nullptr && [&] {
+               // a single-clause "intersection" makes every posting a hit: its candidate list is the whole posting list and
+               // the select pass would crawl through it chunk by chunk; the threshold-pruning kernel handles those batches
+               for (uint32_t slot = 0; slot < nq; slot++)
+                 if (nterms[slot] == 1 && g->h_df[terms[(size_t)slot * nt]] > 65536u) return false;
+               return true;
+             }()) {
     SB_TRY(run_and3(g, P, terms, nterms, nq, nt, k, s));  // unit-based intersection (bm25_and3.cuh), opt-in
   } else {
     SB_TRY(ensure(g->g_khi, (size_t)n_items * cap)); SB_TRY(ensure(g->g_klo, (size_t)n_items * cap));
