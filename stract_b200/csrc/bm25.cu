@@ -351,6 +351,7 @@ __global__ void __launch_bounds__(NT) k_topk(const Params P) {
   if (tid == 0) { *s_count = 0; *s_flag = 0; *s_thr_hi = 0; *s_thr_lo = 0; }
   __syncthreads();
   unsigned long long my_docs = 0, my_blocks = 0;
+  unsigned bad_doc = 0u;
   uint32_t cand_seen = 0;  // path B short-circuit counter (uniform)
   bool stop_all = (T == 0);
   // watchdog: every pass of the loop below consumes a block, skips blocks or advances a cursor; a corrupt file
@@ -492,6 +493,7 @@ __global__ void __launch_bounds__(NT) k_topk(const Params P) {
         else if (found && x < i) ok = false;  // a lower slot owns this doc
       }
       if (!ok) continue;
+      if (d >= S.max_doc) { bad_doc = 1u; continue; }  // corrupt deltas: never index the doc tables with it
       my_docs++;
       const uint32_t fid = S.fieldnorm[d];
       const float norm = M.cache[fid];
@@ -546,6 +548,7 @@ __global__ void __launch_bounds__(NT) k_topk(const Params P) {
     else P.o_scores[(size_t)oq * P.k + i] = unord_f32((uint32_t)(M.khi[i] >> 32));
   }
   if (tid == 0) P.o_n[oq] = n;
+  if (bad_doc) atomicAdd(P.counters + 2, 1ull);  // a decoded doc id outside the segment: reported like a decode failure
   for (int o = 16; o; o >>= 1) { my_docs += __shfl_down_sync(0xffffffffu, my_docs, o); }
   if ((tid & 31) == 0 && my_docs) atomicAdd(P.counters + 0, my_docs);
   if (tid == 0 && my_blocks) atomicAdd(P.counters + 1, my_blocks);

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(A3_WARPS * 32) k_and3(const A3Params P) {
   if (T == 0) return;
   const A3Term tA = a3_load_term(P, q, 0);
   unsigned long long n_blocks = 0, n_hits = 0;
-  bool watchdog = false;
+  bool watchdog = false, bad_doc = false;
 
   for (uint32_t ablk = U.blk_lo; ablk < U.blk_hi; ablk++) {
     // ---- this lane's four docs of the A block
@@ -201,7 +201,10 @@ __global__ void __launch_bounds__(A3_WARPS * 32) k_and3(const A3Params P) {
     n_blocks++;
     uint32_t alive = 0;
 #pragma unroll
-    for (int b = 0; b < 4; b++) if (lane * 4 + b < nA) alive |= 1u << b;
+    for (int b = 0; b < 4; b++) if (lane * 4 + b < nA) {
+      if (d[b] < S.max_doc) alive |= 1u << b;
+      else bad_doc = true;   // corrupt deltas: never index the doc tables with it
+    }
     float nrm[4] = {0.f, 0.f, 0.f, 0.f}, acc[4] = {0.f, 0.f, 0.f, 0.f}, oth[4] = {0.f, 0.f, 0.f, 0.f};
 
     // ---- every other clause, rarest first; only the survivors of clause x-1 are looked up in clause x
@@ -288,6 +291,7 @@ __global__ void __launch_bounds__(A3_WARPS * 32) k_and3(const A3Params P) {
     }
     __syncwarp();
   }
+  if (__any_sync(0xffffffffu, bad_doc)) watchdog = true;
   if (lane == 0) {
     if (n_hits) atomicAdd(P.counters + 0, n_hits);
     if (n_blocks) atomicAdd(P.counters + 1, n_blocks);

@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(WQ * 32) k_or3(const WParams P) {
   }
   bool thr_on = false; uint64_t thr_hi = 0; uint32_t thr_lo = 0;   // warp-uniform
   unsigned long long my_docs = 0, my_blocks = 0;
-  bool watchdog = false;
+  bool watchdog = false, bad_doc = false;
 
   while (T > 0) {
     if (budget-- == 0) { watchdog = true; break; }
@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(WQ * 32) k_or3(const WParams P) {
 #pragma unroll
           for (int x = 1; x < TMAX; x++) if ((uint32_t)x < T && e >= s_rstart[x]) i = x;   // s_rstart ascends
           pi[u] = i; pj[u] = s_pos[i] + (e - s_rstart[i]); pd[u] = docs[i * 128 + pj[u]];
+          if (pd[u] >= S.max_doc) { pv[u] = false; bad_doc = true; continue; }   // corrupt deltas: never index the doc tables with it
           pf[u] = S.fieldnorm[pd[u]];
           if (sig4) { const double2* r = (const double2*)(P.sig + (size_t)pd[u] * 4); ps0[u] = __ldg(r); ps1[u] = __ldg(r + 1); }
         }
@@ -333,6 +334,7 @@ __global__ void __launch_bounds__(WQ * 32) k_or3(const WParams P) {
   }
   if (lane == 0) P.o_n[oq] = n;
   for (int o = 16; o; o >>= 1) my_docs += __shfl_down_sync(0xffffffffu, my_docs, o);
+  if (__any_sync(0xffffffffu, bad_doc)) watchdog = true;
   if (lane == 0) {
     if (my_docs) atomicAdd(P.counters + 0, my_docs);
     if (my_blocks) atomicAdd(P.counters + 1, my_blocks);

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(WQ * 32) k_topk_warp(const WParams P) {
   uint32_t cand_seen = 0;
   unsigned long long budget = 64;
   for (uint32_t s = 0; s < T; s++) budget += 4ull * (st[s].nfull + 2);
-  bool watchdog = false;
+  bool watchdog = false, bad_doc = false;
   if (lo_doc > 0)  // start every cursor at the first block that can hold a doc >= lo
     for (uint32_t s = 0; s < T; s++) if (!st[s].done && st[s].nfull) w_dir_skip(P, st, s, lo_doc, lane);
   const bool ranged = lo_doc > 0 || hi_doc != 0xFFFFFFFFu;
@@ -347,6 +347,7 @@ __global__ void __launch_bounds__(WQ * 32) k_topk_warp(const WParams P) {
           uint32_t i = 0; while (e >= s_rstart[i + 1]) i++;
           pi[u] = i; pj[u] = st[i].pos + (e - s_rstart[i]); pd[u] = docs[i * 128 + pj[u]];
           pv[u] = pd[u] <= cutoff;
+          if (pv[u] && pd[u] >= S.max_doc) { pv[u] = false; bad_doc = true; }  // corrupt deltas: never index the doc tables with it
           if (pv[u]) {
             if (MODE != 0) pf[u] = S.fieldnorm[pd[u]];   // AND: almost every entry fails the membership test, fetch later
             if (sig4) { const double2* r = (const double2*)(P.sig + (size_t)pd[u] * 4); ps0[u] = __ldg(r); ps1[u] = __ldg(r + 1); }
@@ -436,6 +437,7 @@ __global__ void __launch_bounds__(WQ * 32) k_topk_warp(const WParams P) {
   }
   if (lane == 0) P.o_n[oq] = n;
   for (int o = 16; o; o >>= 1) my_docs += __shfl_down_sync(0xffffffffu, my_docs, o);
+  if (__any_sync(0xffffffffu, bad_doc)) watchdog = true;   // a decoded doc id outside the segment: reported like a decode failure
   if (lane == 0) {
     if (my_docs) atomicAdd(P.counters + 0, my_docs);
     if (my_blocks) atomicAdd(P.counters + 1, my_blocks);
