@@ -238,8 +238,9 @@ class TopDocs:
         merged fruit drops the first `offset` (top_collector.rs:109-129)."""
         return TopDocs(self.limit, int(offset))
 
-    def search_batch(self, segment, term_ords, mode=MODE_AND, weights=None, return_stats=False):
-        """term_ords [n_queries, n_terms] (NO_TERM pads).  Returns (docs [nq,k], scores [nq,k], n_out [nq])."""
+    def search_batch(self, segment, term_ords, mode=MODE_AND, weights=None, return_stats=False, average_fieldnorm=None):
+        """term_ords [n_queries, n_terms] (NO_TERM pads).  Returns (docs [nq,k], scores [nq,k], n_out [nq]).
+        `weights` / `average_fieldnorm` override the segment's own statistics (a Searcher passes the index-wide ones)."""
         term_ords = np.ascontiguousarray(term_ords, np.uint32)
         nq, nt = term_ords.shape
         if weights is None:  # Bm25Weight::for_terms with the segment's own statistics (bm25.rs:98-134)
@@ -248,7 +249,7 @@ class TopDocs:
             w_u = np.array([np.float32(idf(int(d), segment.max_doc) * (np.float32(1.0) + K1)) for d in uniq], np.float32)
             weights = w_u[inv].reshape(nq, nt)
         weights = np.ascontiguousarray(weights, np.float32)
-        cache = compute_tf_cache(segment.average_fieldnorm)
+        cache = compute_tf_cache(segment.average_fieldnorm if average_fieldnorm is None else average_fieldnorm)
         k = self.limit + self.offset
         docs = host_out((nq, k), np.uint32); scores = host_out((nq, k), np.float32); n_out = np.zeros(nq, np.uint32)
         b = B.Bm25Batch(nq, nt, _p(term_ords), _p(weights), _p(cache), mode, k)
@@ -268,6 +269,61 @@ class TopDocs:
         w = None if weights is None else np.asarray(weights, np.float32)[None, :]
         d, s, n = self.search_batch(segment, t, mode, w)
         return [(float(s[0, i]), int(d[0, i])) for i in range(int(n[0]))]
+
+
+class Searcher:
+    """tantivy `Searcher` + `TopDocs` over several segments of one field.  The BM25 statistics are the index-wide ones
+    (Bm25StatisticsProvider / Bm25Weight::for_terms, tantivy/src/query/bm25.rs:15-50,98-134: total_num_docs,
+    total_num_tokens and doc_freq summed over the segments); every segment collects limit + offset documents on the
+    device and the fruits are merged by (score desc, DocAddress(segment_ord, doc_id) asc), then the offset is dropped
+    (TopCollector::merge_fruits, tantivy/src/collector/top_collector.rs:109-129)."""
+
+    def __init__(self, segments):
+        self.segments = list(segments)
+        self.total_num_docs = int(sum(s.max_doc for s in self.segments))
+        self.total_num_tokens = int(sum(s.total_num_tokens for s in self.segments))
+        self.average_fieldnorm = np.float32(np.float32(self.total_num_tokens) / np.float32(max(self.total_num_docs, 1)))
+
+    def doc_freq(self, term_ords_per_segment):
+        df = np.zeros(np.asarray(term_ords_per_segment[0]).shape, np.int64)
+        for seg, ords in zip(self.segments, term_ords_per_segment):
+            ords = np.asarray(ords, np.uint32)
+            present = ords != NO_TERM
+            df += np.where(present, seg.doc_freq[np.minimum(ords, max(seg.n_terms - 1, 0))].astype(np.int64), 0)
+        return df
+
+    def search_batch(self, top_docs, term_ords_per_segment, mode=MODE_AND, n_clauses=None):
+        """term_ords_per_segment[s] is [n_queries, n_terms] in segment s's own ordinals, NO_TERM where the segment does not
+        hold the term; n_clauses[q] = number of leading columns that are real clauses (default: all).  Returns
+        (segment_ord [nq,k], docs [nq,k], scores [nq,k], n [nq])."""
+        ords = [np.ascontiguousarray(o, np.uint32) for o in term_ords_per_segment]
+        nq, nt = ords[0].shape
+        n_clauses = np.full(nq, nt, np.int64) if n_clauses is None else np.asarray(n_clauses, np.int64)
+        real = np.arange(nt)[None, :] < n_clauses[:, None]
+        df = self.doc_freq(ords)
+        uniq, inv = np.unique(df, return_inverse=True)
+        w_u = np.array([np.float32(idf(int(d), self.total_num_docs) * (np.float32(1.0) + K1)) for d in uniq], np.float32)
+        weights = np.ascontiguousarray(w_u[inv].reshape(nq, nt))
+        inner = TopDocs(top_docs.limit + top_docs.offset)
+        parts = []
+        for s_ord, (seg, o) in enumerate(zip(self.segments, ords)):
+            o = np.where(real, o, NO_TERM).astype(np.uint32)
+            if mode == MODE_AND:   # a clause this segment cannot satisfy empties its intersection
+                dead = ((o == NO_TERM) & real).any(axis=1)
+                o[dead] = NO_TERM
+            d, sc, n = inner.search_batch(seg, o, mode, weights=weights, average_fieldnorm=self.average_fieldnorm)
+            parts.append((s_ord, d, sc, n))
+        k = top_docs.limit
+        out_seg = np.zeros((nq, k), np.uint32); out_doc = np.zeros((nq, k), np.uint32)
+        out_sc = np.zeros((nq, k), np.float32); out_n = np.zeros(nq, np.uint32)
+        for q in range(nq):
+            segs = np.concatenate([np.full(int(n[q]), s_ord, np.uint32) for s_ord, _, _, n in parts])
+            docs = np.concatenate([d[q, :n[q]] for _, d, _, n in parts])
+            scs = np.concatenate([sc[q, :n[q]] for _, _, sc, n in parts])
+            order = np.lexsort((docs, segs, -scs.astype(np.float64)))[top_docs.offset:top_docs.offset + k]
+            m = order.size
+            out_seg[q, :m], out_doc[q, :m], out_sc[q, :m], out_n[q] = segs[order], docs[order], scs[order], m
+        return out_seg, out_doc, out_sc, out_n
 
 
 class SignalComputer:

@@ -85,3 +85,54 @@ def test_term_info_store_decoded_on_device():
         for mode in (MODE_AND, MODE_OR):
             assert TopDocs.with_limit(100).search(seg, q, mode) == TopDocs.with_limit(100).search(seg2, q, mode)
     seg.close(); seg2.close()
+
+
+def test_searcher_over_three_segments_matches_one_big_segment():
+    """tantivy Searcher semantics for path A: index-wide BM25 statistics (bm25.rs:98-134) and merge_fruits
+    (top_collector.rs:109-129).  The same collection as ONE oracle segment and as THREE device segments must give the
+    same (doc, score) lists, bit for bit -- (segment_ord, doc) order equals global doc order for contiguous splits."""
+    import oracle
+    from stract_b200 import bm25
+    from stract_b200.bm25 import NO_TERM, Searcher, SegmentReader
+    rng = np.random.default_rng(27)
+    max_doc, cuts = 45_000, [0, 12_000, 30_000, 45_000]
+    dfs = [40, 300, 2_000, 9_000, 20_000]
+    lens = np.maximum(1, rng.lognormal(4.0, 0.8, max_doc)).astype(np.uint32)
+    ids = bm25.fieldnorms_to_ids(lens)
+    td = [np.sort(rng.choice(max_doc, df, replace=False)).astype(np.uint32) for df in dfs]
+    td[0] = td[0][td[0] >= cuts[1]]                      # the rarest term does not occur in segment 0 at all
+    tt = [np.minimum(rng.geometric(0.6, len(d)), 255).astype(np.uint32) for d in td]
+    whole = oracle.Segment(ids)
+    for d, t in zip(td, tt):
+        whole.add_term(d, t)
+    segs, ords = [], []
+    for s in range(3):
+        lo, hi = cuts[s], cuts[s + 1]
+        sd, st, present = [], [], []
+        for d, t in zip(td, tt):
+            m = (d >= lo) & (d < hi)
+            if m.any():
+                present.append(len(sd)); sd.append(d[m] - lo); st.append(t[m])
+            else:
+                present.append(NO_TERM)
+        data, infos = bm25.encode_postings(sd, st, ids[lo:hi], 1.0)
+        segs.append(SegmentReader(data, infos, ids[lo:hi]))
+        ords.append(present)
+    searcher = Searcher(segs)
+    assert searcher.total_num_docs == max_doc and np.float32(searcher.average_fieldnorm) == np.float32(whole.avg_fieldnorm)
+    queries = [[4, 3], [0, 4], [2, 1], [0, 1], [3], [4, 2]]
+    cache = bm25.compute_tf_cache(searcher.average_fieldnorm)
+    full_df = np.array([len(d) for d in td])
+    for mode in (MODE_AND, MODE_OR):
+        for q in queries:
+            per_seg = [np.array([[o[t] for t in q]], np.uint32) for o in ords]
+            for limit, offset in ((50, 0), (20, 7)):
+                sg, dd, sc, n = searcher.search_batch(TopDocs.with_limit(limit).and_offset(offset), per_seg, mode)
+                w = np.array([bm25.Bm25Weight.for_one_term(int(full_df[t]), max_doc, searcher.average_fieldnorm).weight for t in q], np.float32)
+                od, os_, _ = whole.topk(np.array(q, np.uint32), w, np.tile(cache, (len(q), 1)), mode, limit + offset)
+                od, os_ = od[offset:], os_[offset:]
+                glob = np.array(cuts, np.uint32)[sg[0, :n[0]]] + dd[0, :n[0]]
+                assert np.array_equal(glob, od), (mode, q, limit, offset)
+                assert np.array_equal(sc[0, :n[0]], os_), (mode, q, limit, offset)
+    for s in segs:
+        s.close()
