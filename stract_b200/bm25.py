@@ -337,15 +337,19 @@ class SignalComputer:
         self.coeff_text = float(coeff_text)
         self.k1, self.b = np.float32(k1), np.float32(b)
 
-    def top_docs_batch(self, term_ords, k, max_docs=0, return_stats=False):
+    def top_docs_batch(self, term_ords, k, max_docs=0, return_stats=False, weights=None, average_fieldnorm=None):
+        """`weights` (idf per clause) / `average_fieldnorm` override the segment's own statistics: MultiBm25Weight::for_terms
+        takes them from the whole searcher (core/src/ranking/bm25.rs:52-92), see SignalSearcher."""
         seg = self.segment
         term_ords = np.ascontiguousarray(term_ords, np.uint32)
         nq, nt = term_ords.shape
-        df = seg.doc_freq[np.minimum(term_ords, seg.n_terms - 1)]
-        uniq, inv = np.unique(df, return_inverse=True)  # one scalar idf per distinct doc_freq
-        w_u = np.array([idf(int(d), seg.max_doc) for d in uniq], np.float32)
-        weights = np.ascontiguousarray(w_u[inv].reshape(nq, nt))
-        cache = compute_tf_cache(seg.average_fieldnorm, self.k1, self.b)
+        if weights is None:
+            df = seg.doc_freq[np.minimum(term_ords, seg.n_terms - 1)]
+            uniq, inv = np.unique(df, return_inverse=True)  # one scalar idf per distinct doc_freq
+            w_u = np.array([idf(int(d), seg.max_doc) for d in uniq], np.float32)
+            weights = w_u[inv].reshape(nq, nt)
+        weights = np.ascontiguousarray(weights, np.float32)
+        cache = compute_tf_cache(seg.average_fieldnorm if average_fieldnorm is None else average_fieldnorm, self.k1, self.b)
         docs = host_out((nq, k), np.uint32); totals = host_out((nq, k), np.float64); n_out = np.zeros(nq, np.uint32)
         sb = B.SignalBatch()
         sb.q = B.Bm25Batch(nq, nt, _p(term_ords), _p(weights), _p(cache), MODE_OR, k)
@@ -358,6 +362,46 @@ class SignalComputer:
         if return_stats:
             return docs, totals, n_out, {k_: getattr(st, k_) for k_, _ in B.Bm25Stats._fields_ if not k_.startswith("_")}
         return docs, totals, n_out
+
+
+class SignalSearcher:
+    """Path B over several segments: Stract's MultiBm25Weight::for_terms sums total_num_tokens / total_num_docs over the
+    segment readers and takes doc_freq from the searcher (core/src/ranking/bm25.rs:52-92); every segment collects its top
+    k by `total` and the fruits are merged by (total desc, (segment_ord, doc) asc) like any tantivy top collector
+    (tweak_score_top_collector.rs -> TopCollector::merge_fruits, top_collector.rs:109-129)."""
+
+    def __init__(self, computers):
+        self.computers = list(computers)          # one SignalComputer per segment (same coefficients)
+        segs = [c.segment for c in self.computers]
+        self.total_num_docs = int(sum(s.max_doc for s in segs))
+        self.total_num_tokens = int(sum(s.total_num_tokens for s in segs))
+        self.average_fieldnorm = np.float32(np.float32(self.total_num_tokens) / np.float32(max(self.total_num_docs, 1)))
+
+    def top_docs_batch(self, term_ords_per_segment, k):
+        ords = [np.ascontiguousarray(o, np.uint32) for o in term_ords_per_segment]
+        nq, nt = ords[0].shape
+        df = np.zeros((nq, nt), np.int64)
+        for c, o in zip(self.computers, ords):
+            seg = c.segment
+            df += np.where(o != NO_TERM, seg.doc_freq[np.minimum(o, max(seg.n_terms - 1, 0))].astype(np.int64), 0)
+        uniq, inv = np.unique(df, return_inverse=True)
+        w_u = np.array([idf(int(d), self.total_num_docs) for d in uniq], np.float32)
+        weights = w_u[inv].reshape(nq, nt)
+        parts = []
+        for s_ord, (c, o) in enumerate(zip(self.computers, ords)):
+            # a clause the segment does not hold contributes 0 to every doc: it is dropped, the f32 sum is unchanged
+            d, t, n = c.top_docs_batch(o, k, weights=weights, average_fieldnorm=self.average_fieldnorm)
+            parts.append((s_ord, d, t, n))
+        out_seg = np.zeros((nq, k), np.uint32); out_doc = np.zeros((nq, k), np.uint32)
+        out_t = np.zeros((nq, k), np.float64); out_n = np.zeros(nq, np.uint32)
+        for q in range(nq):
+            segs = np.concatenate([np.full(int(n[q]), s_ord, np.uint32) for s_ord, _, _, n in parts])
+            docs = np.concatenate([d[q, :n[q]] for _, d, _, n in parts])
+            tot = np.concatenate([t[q, :n[q]] for _, _, t, n in parts])
+            order = np.lexsort((docs, segs, -tot))[:k]
+            m = order.size
+            out_seg[q, :m], out_doc[q, :m], out_t[q, :m], out_n[q] = segs[order], docs[order], tot[order], m
+        return out_seg, out_doc, out_t, out_n
 
 
 def smoke():

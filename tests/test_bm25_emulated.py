@@ -48,6 +48,7 @@ def test_default_kernels_against_oracle(emulated):
     late.test_positions_record_option_skip_entries()
     late.test_term_info_store_decoded_on_device()
     late.test_searcher_over_three_segments_matches_one_big_segment()
+    late.test_signal_searcher_over_segments_matches_one_big_segment()
     T.test_malformed_postings_rejected()
     import test_golden
     test_golden.check_path2_against_golden()   # committed fixtures, no oracle call

@@ -136,3 +136,52 @@ def test_searcher_over_three_segments_matches_one_big_segment():
                 assert np.array_equal(sc[0, :n[0]], os_), (mode, q, limit, offset)
     for s in segs:
         s.close()
+
+
+def test_signal_searcher_over_segments_matches_one_big_segment():
+    """Path B with searcher-wide BM25 statistics (core/src/ranking/bm25.rs:52-92) and the fruit merge: three device
+    segments with their own signal tables against one oracle segment holding everything."""
+    import oracle
+    from stract_b200 import bm25
+    from stract_b200.bm25 import NO_TERM, SegmentReader, SignalComputer, SignalSearcher, SignalTable
+    rng = np.random.default_rng(29)
+    max_doc, cuts = 36_000, [0, 9_000, 25_000, 36_000]
+    dfs = [60, 500, 3_000, 8_000, 15_000]
+    lens = np.maximum(1, rng.lognormal(4.0, 0.8, max_doc)).astype(np.uint32)
+    ids = bm25.fieldnorms_to_ids(lens)
+    td = [np.sort(rng.choice(max_doc, df, replace=False)).astype(np.uint32) for df in dfs]
+    td[0] = td[0][td[0] < cuts[2]]                       # the rarest term is missing from the last segment
+    tt = [np.minimum(rng.geometric(0.6, len(d)), 255).astype(np.uint32) for d in td]
+    cols = [rng.random(max_doc) ** 8, rng.random(max_doc), rng.random(max_doc), 1.0 / (1.0 + rng.integers(0, 1000, max_doc))]
+    coeffs = [2.0, 0.02, 2.0, 0.001]
+    whole = oracle.Segment(ids)
+    for d, t in zip(td, tt):
+        whole.add_term(d, t)
+    comps, ords, keep = [], [], []
+    for s in range(3):
+        lo, hi = cuts[s], cuts[s + 1]
+        sd, st, present = [], [], []
+        for d, t in zip(td, tt):
+            m = (d >= lo) & (d < hi)
+            if m.any():
+                present.append(len(sd)); sd.append(d[m] - lo); st.append(t[m])
+            else:
+                present.append(NO_TERM)
+        data, infos = bm25.encode_postings(sd, st, ids[lo:hi], 1.0)
+        seg = SegmentReader(data, infos, ids[lo:hi])
+        table = SignalTable([c[lo:hi] for c in cols])
+        comps.append(SignalComputer(seg, table, coeffs, coeff_text=0.005)); ords.append(present); keep.append((seg, table))
+    searcher = SignalSearcher(comps)
+    queries = np.array([[4, 3, 2, 1, 0], [0, 1, 2, 3, 4], [2, 4, 1, 3, 0]], np.uint32)
+    per_seg = [np.array([[o[t] for t in q] for q in queries], np.uint32) for o in ords]
+    sg, dd, tot, n = searcher.top_docs_batch(per_seg, 200)
+    cache = bm25.compute_tf_cache(searcher.average_fieldnorm)
+    full_df = np.array([len(d) for d in td])
+    w = np.array([[bm25.StractBm25Weight.for_one_term(int(full_df[t]), max_doc, searcher.average_fieldnorm).weight for t in q] for q in queries], np.float32)
+    od, ot, on, _ = whole.signal_topk_batch(queries, w, np.tile(cache, (queries.size, 1)), 1.2, 0.005, cols, coeffs, 200)
+    assert np.array_equal(n, on)
+    for q in range(len(queries)):
+        glob = np.array(cuts, np.uint32)[sg[q, :n[q]]] + dd[q, :n[q]]
+        assert np.array_equal(glob, od[q, :on[q]]) and np.array_equal(tot[q, :n[q]], ot[q, :on[q]]), q
+    for seg, table in keep:
+        table.close(); seg.close()
