@@ -25,6 +25,7 @@ def test_oracle_reproduces_golden_fixtures():
     import make_golden as M
     assert json.loads(json.dumps(M.path1())) == _load("path1_small.json")
     assert json.loads(json.dumps(M.path2())) == _load("path2_small.json")
+    assert json.loads(json.dumps(M.path1_c1())) == _load("path1_c1.json")
 
 
 def test_reference_kat_list_matches_oracle_tests():
@@ -65,6 +66,27 @@ def check_path1_against_golden():
     rlo, rhi = r.rank_ids
     order = np.array(g["rank_order_head"])
     assert np.array_equal(rlo[:32], r.ids_lo[order]) and np.array_equal(rhi[:32], r.ids_hi[order])
+
+
+def check_c1_against_golden():
+    """BASELINE configs[0] at full size against the frozen hashes."""
+    import make_golden as M
+    from stract_b200 import synth
+    from stract_b200.webgraph import DeviceGraph, Webgraph
+    g = _load("path1_c1.json")
+    d = synth.uniform_graph(100_000, 1_000_000, 42)
+    a = (d["from_lo"], d["from_hi"], d["to_lo"], d["to_hi"], d["rel_flags"])
+    assert M.sha(np.stack(a)) == g["input_sha256"]
+    dg = DeviceGraph(Webgraph.from_arrays(*a))
+    try:
+        iters, _ = dg.run(20)
+        lo, hi, c = dg.result()
+        assert iters == g["iterations"] and len(c) == g["n_positive"]
+        assert M.sha(dg.registers()) == g["registers_sha256"]
+        assert M.sha(lo) == g["ids_lo_sha256"] and M.sha(hi) == g["ids_hi_sha256"]
+        assert M.f64hex(c[:8]) == g["centrality_head"] and M.sha(c) == g["centrality_sha256"]
+    finally:
+        dg.close()
 
 
 def check_path2_against_golden():

@@ -14,6 +14,10 @@ def test_cuda_path1_reproduces_golden():
     test_golden.check_path1_against_golden()
 
 
+def test_cuda_c1_reproduces_golden():
+    test_golden.check_c1_against_golden()
+
+
 def test_cuda_path2_reproduces_golden():
     test_golden.check_path2_against_golden()
 
