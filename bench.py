@@ -7,19 +7,26 @@ same graph is destination-row partitioned over N GPUs = configs[2]).  A "step" i
 HarmonicCentrality computation (reset + all HyperBall iterations to convergence) on the graph
 resident in HBM; value = kept_edges x iterations / device time.  `e2e` is the same metric through the
 C-ABI call sequence a Rust shim makes (sb200_graph_create from HOST buffers -> run -> result to host),
-host<->device copies and the on-device CSR staging inside the timed region.  BM25 postings/sec is
-reported in the same line under "bm25".
+host<->device copies and the on-device CSR staging inside the timed region.
+
+Parity is part of the line: at N = 1 the CPU oracle (oracle/, test infrastructure) computes the SAME
+full-size graph on all host threads and its registers / ids / centralities are compared bit for bit
+with the GPU's (`parity.c2`); that run is also the `cpu_baseline` (median of 3).  At N > 1 every rank's
+register replica and the union of the owned results are compared with the hashes frozen from that
+check (tests/golden/path1_c2.json).  BASELINE configs[0] (100k / 1M, the reference's own CPU case)
+runs on the GPU as `c1` and is checked against tests/golden/path1_c1.json.  BM25 postings/sec
+(configs[3], configs[4]) is reported under "bm25" with its own parity objects (bench_bm25.py).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path
   python bench.py --impl reference ...                          the reference's CPU path (oracle port)
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -27,6 +34,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "webgraph_edges_per_sec_per_centrality_iter"
 UNIT = "edges/s"
+GOLDEN_C2 = os.path.join(ROOT, "tests", "golden", "path1_c2.json")
+GOLDEN_C1 = os.path.join(ROOT, "tests", "golden", "path1_c1.json")
 
 
 def _peaks():
@@ -37,6 +46,14 @@ def _peaks():
         except Exception:
             pass
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def workload_config(nodes, edges, kept, n_nodes, iters):
+    """The `config` object: identical for every arm and every N (the driver compares the arms on it)."""
+    return {"workload": f"webgraph harmonic centrality (HyperBall) to convergence, R-MAT(0.57,0.19,0.19,0.05) {nodes} nodes / "
+                        f"{edges} edges, seed 42 (BASELINE configs[1]; with --gpus N the same graph partitioned over N GPUs = configs[2])",
+            "kept_edges": kept, "n_nodes": n_nodes, "iterations_per_step": iters,
+            "l2_policy": "inputs >> L2: 2 x 1.8 GB register arrays + 3.6 GB CSR per iteration, no flush needed"}
 
 
 class ClockSampler:
@@ -90,79 +107,211 @@ class ClockSampler:
         return out
 
 
-def _unique_kept_edges(d):
+# ------------------------------------------------------------------------------------------------
+# result fingerprints (shared by the N = 1 oracle check, the golden file and the N > 1 check)
+def sha(a):
     import numpy as np
-    from stract_b200.webgraph import SKIPPED_REL
-    key = np.stack([d["from_lo"], d["from_hi"], d["to_lo"], d["to_hi"]], 1)
-    _, first = np.unique(key, axis=0, return_index=True)
-    keep = (d["rel_flags"][first] & np.uint64(SKIPPED_REL)) == 0
-    return int(keep.sum())
+    return hashlib.sha256(memoryview(np.ascontiguousarray(a)).cast("B")).hexdigest()
+
+
+def result_checksum(ids_lo, ids_hi, values):
+    """Order-independent 64-bit checksum of {(id, centrality)}: a wrapping sum of a mixed word per entry, so the owned
+    shares of several ranks add up to the checksum of the whole result."""
+    import numpy as np
+    with np.errstate(over="ignore"):
+        z = (np.asarray(ids_lo, np.uint64) * np.uint64(0x9E3779B97F4A7C15)) ^ (np.asarray(ids_hi, np.uint64) * np.uint64(0xC2B2AE3D27D4EB4F))
+        z ^= np.asarray(values, np.float64).view(np.uint64) * np.uint64(0x165667B19E3779F9)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+        return int(z.sum(dtype=np.uint64))
+
+
+def registers_checksum(regs, owned=None):
+    """Wrapping 64-bit sum over (owned) nodes of a mixed word of (position in id order, the node's 64 registers): the owned
+    shares of several ranks add up to the checksum of the whole register array."""
+    import numpy as np
+    a = np.ascontiguousarray(regs).view(np.uint64).reshape(-1, 8)
+    with np.errstate(over="ignore"):
+        z = np.arange(a.shape[0], dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+        for j in range(8):
+            z = (z ^ a[:, j]) * np.uint64(0xBF58476D1CE4E5B9)
+            z ^= z >> np.uint64(29)
+        if owned is not None:
+            z = z[np.asarray(owned).astype(bool)]
+        return int(z.sum(dtype=np.uint64))
+
+
+def _i64(x):
+    return x - (1 << 64) if x >= (1 << 63) else x
+
+
+def host_threads():
+    return os.cpu_count() or 1
+
+
+def _np_u64(t):
+    """numpy uint64 view of a host torch tensor / numpy array (no copy)."""
+    import numpy as np
+    a = t.numpy() if hasattr(t, "numpy") else np.asarray(t)
+    return a.view(np.uint64)
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline_dense(nodes, edges, threads):
-    """Oracle 'dense' port (flat arrays, all host threads) on a bounded R-MAT sample of the workload."""
+def oracle_c2(cols_host, threads, runs=3, budget_s=150.0):
+    """The dense CPU restatement on the full graph: all-threads staging, `runs` timed iteration loops (median),
+    final registers / result kept for the comparison.  Returns (oracle handle, info dict)."""
+    import numpy as np
     import oracle
-    from stract_b200 import synth
-    d = synth.rmat_graph(nodes, edges, seed=42)
-    a = (d["from_lo"], d["from_hi"], d["to_lo"], d["to_hi"], d["rel_flags"])
-    o = oracle.DenseHyperBall(*a, threads=threads)
+    a = [_np_u64(c) for c in cols_host]
     t0 = time.perf_counter()
-    iters = o.run()
-    dt = time.perf_counter() - t0
-    kept = o.n_edges
-    o.close()
-    return {"value": kept * iters / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"R-MAT {nodes} nodes / {edges} edges (same generator, seed 42), {iters} iterations to convergence, "
-                      f"oracle dense port on {threads} threads, iteration loop only (graph already staged in RAM)"}
+    o = oracle.DenseHyperBall(*a, threads=threads, mt=True)
+    stage_s = time.perf_counter() - t0
+    loops, iters = [], 0
+    t_all = time.perf_counter()
+    for i in range(runs):
+        if i:
+            o.reset()
+        t1 = time.perf_counter()
+        iters = o.run()
+        loops.append(time.perf_counter() - t1)
+        if time.perf_counter() - t_all + loops[-1] > budget_s:
+            break
+    kept = o.n_edges - o.num_self_loops()
+    med = float(np.median(loops))
+    return o, {"kept_edges": kept, "n_nodes": o.n_nodes, "iterations": iters, "stage_s": round(stage_s, 2),
+               "loop_s": [round(x, 3) for x in loops], "median_loop_s": med, "value": kept * iters / med}
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU path = oracle 'faithful' port (the reference is Rust; no
-    toolchain here).  It mirrors harmonic.rs structure by structure and is single-threaded because the
-    reference's loop is (harmonic.rs:129-154).  Each step = one HarmonicCentrality::calculate on a bounded
-    sample, graph scan/dedup/maps included, exactly what the reference call does."""
+    """--impl reference: the reference's CPU path on this box's host cores.  The reference is Rust (no toolchain in
+    this image), so what runs is the oracle port.  Headline = the dense port on ALL host threads over the SAME full
+    workload as the GPU arm (a generous stand-in: harmonic.rs:129-154 itself is one sequential iterator over ordered
+    maps); `c1` = the structure-faithful single-threaded port on BASELINE configs[0] exactly, which is the case the
+    reference's own CPU path is quoted on.  A step = one complete calculate() loop on the staged graph."""
+    import numpy as np
     import oracle
-    from stract_b200 import synth
-    nodes, edges = args.ref_nodes, args.ref_edges
-    d = synth.rmat_graph(nodes, edges, seed=42)
-    a = (d["from_lo"], d["from_hi"], d["to_lo"], d["to_hi"], d["rel_flags"])
-    kept = _unique_kept_edges(d)
-    for _ in range(min(args.warmup, 1)):
-        oracle.hyperball_faithful(*a)
+    import psutil
+    threads = host_threads()
+    nodes, edges, scale = args.nodes, args.edges, args.scale
+    need = edges * 40 + edges * 36 + 20e9   # edge stream + staging transients + state
+    avail = psutil.virtual_memory().available
+    note = "full workload"
+    if avail < need:
+        f = 1
+        while (edges // f) * 76 + 20e9 / f > avail and f < 4096:
+            f *= 2
+        nodes, edges = max(nodes // f, 1000), edges // f
+        scale = max(1, int(np.ceil(np.log2(nodes))))
+        note = f"host RAM {avail / 2**30:.0f} GiB too small for the 10^9-edge stream: scaled 1/{f}"
     t0 = time.perf_counter()
-    iters = 0
-    for _ in range(args.steps):
-        r = oracle.hyperball_faithful(*a)
-        iters = r["iters"]
-    dt = (time.perf_counter() - t0) / args.steps
+    d = oracle.synth_edges(1, nodes, edges, seed=42, scale=scale, threads=threads)
+    gen_s = time.perf_counter() - t0
+    cols = [d["from_lo"], d["from_hi"], d["to_lo"], d["to_hi"], d["rel_flags"]]
+    t0 = time.perf_counter()
+    o = oracle.DenseHyperBall(*cols, threads=threads, mt=True)
+    stage_s = time.perf_counter() - t0
+    del d, cols
+    kept = o.n_edges - o.num_self_loops()
+    budget = args.ref_budget_s
+    warm = 0
+    t_all = time.perf_counter()
+    iters = o.run()
+    first = time.perf_counter() - t_all
+    if args.warmup > 0:
+        warm = 1
+    loops = [] if warm else [first]
+    while len(loops) < args.steps and (time.perf_counter() - t_all) + first < budget:
+        o.reset()
+        t1 = time.perf_counter()
+        iters = o.run()
+        loops.append(time.perf_counter() - t1)
+    if not loops:
+        loops, warm = [first], 0
+    dt = float(np.mean(loops))
     value = kept * iters / dt
-    sample = (f"R-MAT {nodes} nodes / {edges} edges (bounded sample of the 50M/1B workload, same generator), "
-              f"{iters} iterations, one full calculate() per step")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+    r = o.result()
+    fp = {"n_positive": int(len(r["centrality"])), "result_checksum": result_checksum(r["ids_lo"], r["ids_hi"], r["centrality"])}
+    n_nodes = o.n_nodes
+    o.close()
+    # configs[0] exactly: the structure-faithful port, one thread, 20-iteration cap
+    u = oracle.synth_edges(0, 100_000, 1_000_000, seed=42, scale=0, threads=threads)
+    ua = (u["from_lo"], u["from_hi"], u["to_lo"], u["to_hi"], u["rel_flags"])
+    t1 = time.perf_counter()
+    fr = oracle.hyperball_faithful(*ua, max_iters=20)
+    c1_s = time.perf_counter() - t1
+    c1_dense = oracle.DenseHyperBall(*ua)
+    c1_kept = c1_dense.n_edges - c1_dense.num_self_loops()
+    c1_dense.close()
+    c1 = {"workload": "BASELINE configs[0]: uniform 100000 nodes / 1000000 edges, seed 42, <= 20 iterations", "kind": "port",
+          "structure": "faithful (ordered maps keyed by u128, heap vector per counter, deep clone per iteration, bloom frontier)",
+          "cores": 1, "kept_edges": c1_kept, "iterations": fr["iters"], "ms_per_step": c1_s * 1e3, "value": c1_kept * fr["iters"] / c1_s, "unit": UNIT,
+          "centrality_sha256": sha(fr["centrality"])}
+    sample = (f"{note}: R-MAT {nodes} nodes / {edges} edges, oracle dense port on {threads} threads, graph staged in RAM "
+              f"({stage_s:.1f} s, untimed like the GPU arm's staging), {len(loops)} timed calculate() loops of {iters} iterations "
+              f"(requested {args.steps}; bounded by a {budget:.0f} s budget), {warm} warm-up")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(loops),
+            "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "webgraph harmonic centrality (HyperBall), R-MAT 50M nodes / 1B edges -- bounded CPU sample",
-                       "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "config": workload_config(args.nodes, args.edges, kept, n_nodes, iters) if note == "full workload" else
+                      {"workload": f"webgraph harmonic centrality (HyperBall), R-MAT {nodes} nodes / {edges} edges -- {note}",
+                       "kept_edges": kept, "n_nodes": n_nodes, "iterations_per_step": iters},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "loop_s": [round(x, 3) for x in loops], "gen_s": round(gen_s, 1), "stage_s": round(stage_s, 1)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "fingerprint": fp, "c1": c1, "gpu_launches": 0}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
-def gen_device_graph(torch, L, dev_index, nodes, edges, scale):
+def gen_device_graph(torch, L, dev_index, nodes, edges, scale, kind=1):
     from stract_b200._lib import check
     t = [torch.empty(edges, dtype=torch.int64, device=f"cuda:{dev_index}") for _ in range(5)]
     CH = 1 << 27
     for first in range(0, edges, CH):
         cnt = min(CH, edges - first)
-        check(L.sb200_synth_edges(1, nodes, first, cnt, 42, scale, dev_index, *(x.data_ptr() + first * 8 for x in t)))
+        check(L.sb200_synth_edges(kind, nodes, first, cnt, 42, scale, dev_index, *(x.data_ptr() + first * 8 for x in t)))
     return t
 
 
+def run_c1(torch, device, reps=10):
+    """BASELINE configs[0] (100k nodes / 1M edges, <= 20 iterations) on the GPU through the host-buffer C-ABI sequence,
+    checked against the frozen oracle output (tests/golden/path1_c1.json)."""
+    import numpy as np
+    from stract_b200 import synth
+    from stract_b200.webgraph import DeviceGraph, HarmonicCentrality, Webgraph
+    d = synth.uniform_graph(100_000, 1_000_000, 42)
+    g = Webgraph.from_arrays(d["from_lo"], d["from_hi"], d["to_lo"], d["to_hi"], d["rel_flags"])
+    for _ in range(2):
+        r = HarmonicCentrality.calculate(g, device=device, max_iters=20)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        r = HarmonicCentrality.calculate(g, device=device, max_iters=20)
+    e2e_ms = (time.perf_counter() - t0) / reps * 1e3
+    dg = DeviceGraph(g, device=device)
+    for _ in range(3):
+        dg.reset(); dg.run(20)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(reps):
+        dg.reset(); iters, _ = dg.run(20)
+    ev1.record(); torch.cuda.synchronize()
+    dev_ms = ev0.elapsed_time(ev1) / reps
+    regs = dg.registers()
+    kept = dg.info()["n_edges_kept"]
+    dg.close()
+    gold = json.load(open(GOLDEN_C1))
+    ok = {"iterations": r.iterations == gold["iterations"], "registers": sha(regs) == gold["registers_sha256"],
+          "ids": sha(r.ids_lo) == gold["ids_lo_sha256"] and sha(r.ids_hi) == gold["ids_hi_sha256"],
+          "centrality": sha(r.values) == gold["centrality_sha256"]}
+    return {"workload": "BASELINE configs[0]: uniform 100000 nodes / 1000000 edges, seed 42, <= 20 iterations",
+            "kept_edges": kept, "iterations": r.iterations, "ms_per_step": dev_ms, "value": kept * r.iterations / (dev_ms * 1e-3), "unit": UNIT,
+            "e2e_ms_per_step": e2e_ms, "e2e_value": kept * r.iterations / (e2e_ms * 1e-3),
+            "parity": {"against": "tests/golden/path1_c1.json (frozen oracle output)", "equal": ok, "green": all(ok.values())},
+            "centrality_sha256": sha(r.values)}
+
+
 def main():
-    t_bench0 = time.perf_counter()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -171,19 +320,17 @@ def main():
     ap.add_argument("--nodes", type=int, default=50_000_000)
     ap.add_argument("--edges", type=int, default=1_000_000_000)
     ap.add_argument("--scale", type=int, default=26)
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the full-size oracle run (parity + cpu_baseline)")
     ap.add_argument("--no-bm25", action="store_true")
-    ap.add_argument("--no-experimental", action="store_true", help="skip the subprocess that times the opt-in BM25 kernels")
+    ap.add_argument("--no-c1", action="store_true")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL byte-max all-reduce exchange instead of the fused peer-memory stores")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "symm", "multicast"],
                     help="multi-GPU fused exchange transport: CUDA IPC peer mappings (default), torch symmetric memory "
                          "unicast, or NVSwitch multicast stores")
-    ap.add_argument("--cpu-nodes", type=int, default=1_000_000)
-    ap.add_argument("--cpu-edges", type=int, default=20_000_000)
-    ap.add_argument("--ref-nodes", type=int, default=50_000)
-    ap.add_argument("--ref-edges", type=int, default=500_000)
+    ap.add_argument("--ref-budget-s", type=float, default=170.0, help="--impl reference: wall budget of the timed loops")
+    ap.add_argument("--write-golden", action="store_true", help="N=1, after a green oracle check: rewrite tests/golden/path1_c2.json")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -200,7 +347,7 @@ def main():
     import torch
     import torch.distributed as dist
     from stract_b200 import kernel_launch_count, lib
-    from stract_b200.webgraph import DeviceGraph, ShardedHarmonicCentrality, Webgraph
+    from stract_b200.webgraph import DeviceGraph, HarmonicCentrality, Webgraph
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (the product path has no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -209,6 +356,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     L = lib()
     peaks, peak_src = _peaks()
+    full_size = args.nodes == 50_000_000 and args.edges == 1_000_000_000 and args.scale == 26
 
     nodes, edges = args.nodes, args.edges
     tg = time.perf_counter()
@@ -223,8 +371,9 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    launches0 = kernel_launch_count()
     result = {}
+    parity = {}
+    W = max(args.warmup, 3)
     if world == 1:
         dg = DeviceGraph(graph, device=local_rank)
         info = dg.info()
@@ -232,9 +381,8 @@ def main():
 
         def one_step():
             dg.reset()
-            iters, stats = dg.run()
-            return iters, stats
-        for _ in range(max(args.warmup, 3)):
+            return dg.run()
+        for _ in range(W):
             one_step()
         dg.set_profiling(True)
         sampler = ClockSampler(local_rank); sampler.start()
@@ -242,8 +390,7 @@ def main():
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches_t0 = kernel_launch_count()
         ev0.record()
-        tot_iters = 0
-        stats_last = None
+        tot_iters, stats_last = 0, None
         for _ in range(args.steps):
             iters, stats_last = one_step()
             tot_iters += iters
@@ -256,39 +403,37 @@ def main():
         dg.set_profiling(False)
         value = E * tot_iters / (ms_total * 1e-3)
         iters = tot_iters // args.steps
-        dom = max((p for p in prof if "dense" in p["name"] and p["launches"]), key=lambda p: p["ms"], default=None)
-        roofline = None
-        if dom:
-            ach = dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9
-            # DRAM bytes per launch come from the committed `ncu --set full` capture of this kernel and only
-            # apply when the workload is the one that was captured; otherwise null
-            traffic, traffic_src = None, None
-            try:
-                with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as fh:
-                    cap = json.load(fh)
-                if cap["config"]["nodes"] == args.nodes and cap["config"]["edges"] == args.edges and "pull_warp" in dom["name"]:
-                    traffic = cap["k_pull_warp<dense>"]["dram_bytes_per_launch"]
-                    traffic_src = cap["source"]
-            except (OSError, KeyError, ValueError):
-                pass
-            roofline = {"bound": "hbm", "kernel": dom["name"], "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
-                        "peak_source": peak_src,
-                        "launches": dom["launches"], "avg_launch_ms": dom["ms"] / dom["launches"],
-                        "alg_bytes_per_launch": dom["alg_bytes"] / dom["launches"]}
+        cap = {}
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        except (OSError, ValueError):
+            pass
+        same_workload = bool(cap) and cap["config"]["nodes"] == args.nodes and cap["config"]["edges"] == args.edges
+
+        def kernel_roofline(p):
+            ach = p["alg_bytes"] / (p["ms"] * 1e-3) / 1e9
+            r = {"bound": "hbm", "kernel": p["name"], "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                 "frac": ach / peaks["hbm_gbs"], "traffic": None, "dram_frac": None, "peak_source": peak_src,
+                 "launches": p["launches"], "avg_launch_ms": p["ms"] / p["launches"],
+                 "alg_bytes_per_launch": p["alg_bytes"] / p["launches"], "share_of_step": p["ms"] / ms_total}
+            c = cap.get(p["name"]) if same_workload else None
+            if c:
+                # physical twin of `frac`: DRAM bytes of the committed `ncu --set full` capture of this kernel at this
+                # workload over the launch time measured live here
+                r["traffic"] = c["dram_bytes_per_launch"]
+                r["dram_frac"] = c["dram_bytes_per_launch"] / (r["avg_launch_ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"]
+                r["traffic_source"] = c.get("source", cap.get("source"))
+            return r
+        kern = [kernel_roofline(p) for p in prof if p["launches"]]
+        dom = max((k for k in kern if "dense" in k["kernel"]), key=lambda k: k["share_of_step"], default=None)
         result.update(value=value, ms_per_step=ms_total / args.steps, iters=iters, E=E, info=info, clocks=clocks,
-                      roofline=roofline, launches=launches_timed,
-                      kernels=[{**p, "share_of_step": p["ms"] / ms_total} for p in prof if p["launches"]],
+                      roofline=dom, launches=launches_timed, kernels=kern,
                       per_iter=[{"t": s["t"], "mode": s["mode"], "n_changed": s["n_changed"], "ms": round(s["ms"], 3)} for s in stats_last])
-        dg.close()
+        exchange_kind = None
     else:
         # configs[2]: the same graph, destination rows partitioned over `world` GPUs
-        def one_run():
-            return ShardedHarmonicCentrality.calculate(graph, local_rank, rank, world)
-        # staging happens inside calculate(); time only the iteration loops via the per-iteration stats
-        # (device ms of the step kernels) + exchange wall time => use wall clock around the loop
-        from stract_b200.webgraph import DeviceGraph as _DG
-        dg = _DG(graph, device=local_rank, rank=rank, world_size=world)
+        from stract_b200.webgraph import run_sharded_loop
+        dg = DeviceGraph(graph, device=local_rank, rank=rank, world_size=world)
         exchange_kind = "nccl"
         if args.exchange in ("symm", "multicast"):
             exchange_kind = "symmetric-memory " + dg.enable_symmetric(multicast=(args.exchange == "multicast"))
@@ -297,14 +442,13 @@ def main():
             exchange_kind = "p2p"
         info = dg.info()
         E = info["n_edges_kept"]
-        ranges = dg.row_ranges()
-        from stract_b200.webgraph import run_sharded_loop
+
+        behind_abi = exchange_kind == "p2p"   # sb200_hyperball_run_sharded: round loop + device-side barrier, no NCCL
 
         def one_step():
             dg.reset()
-            t, _ = run_sharded_loop(dg, world)
-            return t
-        for _ in range(max(args.warmup, 3)):
+            return dg.run_sharded() if behind_abi else run_sharded_loop(dg, world)
+        for _ in range(W):
             one_step()
         dg.set_profiling(True)
         sampler = ClockSampler(local_rank); sampler.start()
@@ -312,9 +456,10 @@ def main():
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches_t0 = kernel_launch_count()
         ev0.record()
-        tot_iters = 0
+        tot_iters, st_last = 0, None
         for _ in range(args.steps):
-            tot_iters += one_step()
+            t, st_last = one_step()
+            tot_iters += t
         ev1.record()
         barrier()
         clocks = sampler.stop()
@@ -338,142 +483,163 @@ def main():
         nl = torch.tensor([kernel_launch_count() - launches_t0], device=dev, dtype=torch.int64)
         dist.all_reduce(nl)
         value = E * tot_iters / (ms_total * 1e-3)
-        # one extra untimed run for the per-rank, per-iteration device times (load balance evidence)
-        dg.reset()
-        _, st_last = run_sharded_loop(dg, world)
-        mine = {"rank": rank, "rows": [info["row_begin"], info["row_end"]], "edges_local": info["n_edges_local"],
+        mine = {"rank": rank, "edges_local": info["n_edges_local"],
                 "iter_ms": [round(s["ms"], 3) for s in st_last], "modes": [s["mode"] for s in st_last]}
         allr = [None] * world
         dist.all_gather_object(allr, mine)
-        result.update(exchange_kind=exchange_kind)
+        # ---- parity at N > 1: the owned register rows and the owned results of all ranks together against the frozen
+        #      N = 1 fingerprint (with the subscriber filter a replica is authoritative only for the rows its rank owns or reads)
+        owned, _subs = dg.ownership()
+        lo, hi, c = dg.result()
+        part = torch.tensor([_i64(registers_checksum(dg.registers(), owned)), _i64(result_checksum(lo, hi, c)), len(c), int(owned.sum())],
+                            dtype=torch.int64, device=dev)
+        dist.all_reduce(part)   # int64 addition wraps like the uint64 sums
+        M = (1 << 64) - 1
+        got = {"registers_checksum": int(part[0].item()) & M, "result_checksum": int(part[1].item()) & M, "n_positive": int(part[2].item()),
+               "n_nodes": int(part[3].item()), "iterations": tot_iters // args.steps}
+        gold = None
+        if full_size and os.path.exists(GOLDEN_C2):
+            gold = json.load(open(GOLDEN_C2))
+        if gold:
+            eq = {k: got[k] == gold[k] for k in ("registers_checksum", "result_checksum", "n_positive", "n_nodes", "iterations")}
+            parity["c2"] = {"against": "tests/golden/path1_c2.json (fingerprint of the N=1 run that equalled the full-size oracle bit for bit)",
+                            "equal": eq, "green": all(eq.values())}
+        else:
+            parity["c2"] = {"against": None, "green": None, "fingerprint": got}
         result.update(value=value, ms_per_step=ms_total / args.steps, iters=tot_iters // args.steps, E=E, info=info,
                       clocks=clocks, roofline=roofline_n, launches=int(nl.item()), kernels=[], per_iter=allr)
         dg.close()
+        dg = None
 
-    # ---- e2e: the C-ABI call sequence from HOST buffers (rank 0 only drives it at N=1) ----------
-    e2e = None
-    if not args.no_e2e and world == 1:
+    # ---- e2e: the C-ABI call sequence from HOST buffers (N = 1) ----------------------------------
+    e2e, host = None, None
+    if world == 1 and (not args.no_e2e or not args.no_cpu):
         import psutil
         need = edges * 40
         avail = psutil.virtual_memory().available
-        e_nodes, e_edges, e_scale, note = nodes, edges, args.scale, "full workload"
-        if avail < need * 1.6:
-            f = 1
-            while (edges // f) * 40 * 1.6 > avail and f < 1024:
-                f *= 2
-            e_nodes, e_edges = max(nodes // f, 1000), edges // f
-            e_scale = max(1, int(np.ceil(np.log2(e_nodes))))
-            note = f"host RAM {avail / 2**30:.0f} GiB < 1.6x the {need / 2**30:.0f} GiB edge stream: scaled 1/{f}"
-            del cols, graph
-            torch.cuda.empty_cache()
-            cols = gen_device_graph(torch, L, local_rank, e_nodes, e_edges, e_scale)
-        host = []
-        for c in cols:
-            try:
-                h = torch.empty(c.shape, dtype=c.dtype, pin_memory=True)
-            except Exception:
-                h = torch.empty(c.shape, dtype=c.dtype)
-            h.copy_(c)
-            host.append(h)
+        if avail < need * 1.3:
+            e2e = {"skipped": f"host RAM {avail / 2**30:.0f} GiB < 1.3x the {need / 2**30:.0f} GiB edge stream"}
+        else:
+            host = []
+            for c in cols:
+                try:
+                    h = torch.empty(c.shape, dtype=c.dtype, pin_memory=True)
+                except Exception:
+                    h = torch.empty(c.shape, dtype=c.dtype)
+                h.copy_(c)
+                host.append(h)
+    del cols, graph
+    torch.cuda.empty_cache()
+    if host is not None and not args.no_e2e:
         pinned = all(h.is_pinned() for h in host)
-        del cols
-        torch.cuda.empty_cache()
         hgraph = Webgraph.from_arrays(*host)
-        from stract_b200.webgraph import HarmonicCentrality
-
-        def e2e_step():
-            r = HarmonicCentrality.calculate(hgraph, device=local_rank)
-            return r
         for _ in range(2):  # warm-up: device memory pool and the page-locked result blocks reach steady state
-            r = e2e_step()
+            r = HarmonicCentrality.calculate(hgraph, device=local_rank)
             del r
         barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        tot, d2h, checksum, walls = 0, 0, 0.0, []
+        per_step, tot, d2h, walls, last_r = [], 0, 0, [], None
         for _ in range(args.e2e_steps):
-            r = e2e_step()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            r = HarmonicCentrality.calculate(hgraph, device=local_rank)
+            chk = float(r.values[:1024].sum())  # the caller reads the result on the host  # noqa: F841
+            ev1.record(); torch.cuda.synchronize()
+            per_step.append(ev0.elapsed_time(ev1))
             tot += r.info["n_edges_kept"] * r.iterations
             d2h = len(r.values) * 24
-            checksum += float(r.values[:1024].sum())  # the caller reads the result on the host, then drops it
-            last = {"stage_ms": r.info["stage_ms"], "iterations": r.iterations}
             walls.append({k: round(v, 1) for k, v in (r.info.get("wall_ms") or {}).items()})
-            del r
-        ev1.record()
-        barrier()
-        ms_e = ev0.elapsed_time(ev1)
-        e2e = {"value": tot / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e_edges * 40, "d2h_bytes_per_step": d2h,
-               "ms_per_step": ms_e / args.e2e_steps, "steps": args.e2e_steps, "pinned_host": pinned, "workload": note,
-               "nodes": e_nodes, "edges": e_edges, "stage_ms": last["stage_ms"], "iterations": last["iterations"],
-               "step_wall_ms": walls}
+            last_r = r
+        ms_e = float(sum(per_step))
+        e2e = {"value": tot / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": edges * 40, "d2h_bytes_per_step": d2h,
+               "ms_per_step": ms_e / args.e2e_steps, "steps": args.e2e_steps, "pinned_host": pinned, "workload": "full workload",
+               "ms_min_median_max": [round(min(per_step), 1), round(float(np.median(per_step)), 1), round(max(per_step), 1)],
+               "stage_ms": last_r.info["stage_ms"], "iterations": last_r.iterations, "step_wall_ms": walls}
+        # the e2e result is the one compared with the oracle below (it went through the host-buffer path)
+        e2e_result = (last_r.ids_lo, last_r.ids_hi, last_r.values, last_r.iterations)
+    else:
+        e2e_result = None
+
+    # ---- full-size parity + same-config CPU baseline (N = 1) -------------------------------------
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu and host is not None:
+        threads = host_threads()
+        o, oi = oracle_c2(host, threads)
+        g_regs = dg.registers()
+        lo, hi, c = dg.result()
+        ores = o.result()
+        eq = {"n_nodes": oi["n_nodes"] == info["n_nodes"], "kept_edges": oi["kept_edges"] == E, "iterations": oi["iterations"] == result["iters"],
+              "registers": bool(np.array_equal(g_regs, o.registers_view())),
+              "ids": bool(np.array_equal(lo, ores["ids_lo"]) and np.array_equal(hi, ores["ids_hi"])),
+              "centrality": bool(np.array_equal(c, ores["centrality"]))}
+        if e2e_result is not None:
+            eq["e2e_result"] = bool(e2e_result[3] == oi["iterations"] and np.array_equal(e2e_result[0], ores["ids_lo"]) and
+                                    np.array_equal(e2e_result[1], ores["ids_hi"]) and np.array_equal(e2e_result[2], ores["centrality"]))
+        fp = {"registers_sha256": sha(g_regs), "registers_checksum": registers_checksum(g_regs), "result_checksum": result_checksum(lo, hi, c), "n_positive": int(len(c)),
+              "iterations": result["iters"], "centrality_sha256": sha(c), "n_nodes": info["n_nodes"], "kept_edges": E}
+        parity["c2"] = {"against": f"oracle dense restatement, full graph, {threads} host threads (bit-exact compare of all "
+                                   f"{info['n_nodes']} x 64 registers, ids and f64 centralities)",
+                        "equal": eq, "green": all(eq.values()), "fingerprint": fp}
+        if args.write_golden and full_size and all(eq.values()):
+            with open(GOLDEN_C2, "w") as fh:
+                json.dump({"generator": {"fn": "sb200_synth_edges kind 1 (== stract_b200.synth.rmat_graph)", "nodes": nodes, "edges": edges,
+                                         "seed": 42, "scale": args.scale}, **fp}, fh, indent=1)
+        cpu_baseline = {"value": oi["value"], "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"the full workload (same graph as the GPU arm): oracle dense port on {threads} threads, iteration loop "
+                                  f"to convergence ({oi['iterations']} iterations), median of {len(oi['loop_s'])} runs; graph staged in RAM "
+                                  f"beforehand ({oi['stage_s']} s, all threads)",
+                        "loop_s": oi["loop_s"], "stage_s": oi["stage_s"]}
+        o.close()
+        del o, g_regs
+    elif world == 1 and full_size and os.path.exists(GOLDEN_C2):
+        gold = json.load(open(GOLDEN_C2))
+        lo, hi, c = dg.result()
+        eq = {"registers": registers_checksum(dg.registers()) == gold["registers_checksum"], "result_checksum": result_checksum(lo, hi, c) == gold["result_checksum"],
+              "n_positive": len(c) == gold["n_positive"], "iterations": result["iters"] == gold["iterations"]}
+        parity["c2"] = {"against": "tests/golden/path1_c2.json", "equal": eq, "green": all(eq.values())}
+    if dg is not None:
+        dg.close()
+    del host
+    try:
+        torch.cuda.empty_cache()
+        L.sb200_release_cached_memory(local_rank)
+    except Exception:  # noqa: BLE001
+        pass
 
     if rank == 0:
+        cfg = workload_config(nodes, edges, result["E"], result["info"]["n_nodes"], result["iters"])
+        par = "1 GPU" if world == 1 else (f"destination-row partition x{world}, " + {
+            "nccl": "NCCL byte-max all-reduce of the register replicas per iteration",
+            "p2p": "fused exchange: pull kernels store produced rows into the subscribing peers' replicas over NVLink (CUDA IPC); round loop "
+                   "behind the ABI (sb200_hyperball_run_sharded), device-side barrier + changed-count sum over peer memory, no NCCL in the loop"}.get(
+            exchange_kind, "fused exchange over " + str(exchange_kind) + " stores, changed-count all-reduce as barrier"))
         line = {"metric": METRIC, "value": result["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": result["ms_per_step"], "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": f"webgraph harmonic centrality (HyperBall) to convergence, R-MAT(0.57,0.19,0.19,0.05) "
-                                       f"{nodes} nodes / {edges} edges (BASELINE configs[{1 if world == 1 else 2}])",
-                           "kept_edges": result["E"], "n_nodes": result["info"]["n_nodes"],
-                           "iterations_per_step": result["iters"],
-                           "l2_policy": "inputs >> L2: 2 x 3.2 GB register arrays + 4 GB CSR per iteration",
-                           "parallelism": "1 GPU" if world == 1 else (f"destination-row partition x{world}, " + {"nccl": "NCCL byte-max all-reduce of the register replicas per iteration",
-                                                                                                    "p2p": "fused exchange: pull kernels store produced rows into all peers' replicas over NVLink (CUDA IPC), NCCL all-reduce of the changed count as barrier"}.get(
-                               result.get("exchange_kind", "p2p"), "fused exchange over " + str(result.get("exchange_kind")) + " stores, NCCL all-reduce of the changed count as barrier")),
-                           "hbm_bytes": result["info"]["hbm_bytes"], "gen_s": round(gen_s, 2),
-                           "stage_ms": result["info"]["stage_ms"]},
+                "warmup": W, "ms_per_step": result["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
+                "run": {"parallelism": par, "hbm_bytes": result["info"]["hbm_bytes"], "gen_s": round(gen_s, 2),
+                        "stage_ms": result["info"]["stage_ms"]},
                 "clocks": result["clocks"], "gpu_launches": result["launches"], "roofline": result["roofline"],
-                "kernels": result["kernels"], "per_iter": result["per_iter"], "e2e": e2e}
-        if not args.no_cpu and world == 1:
-            threads = os.cpu_count() or 1
-            line["cpu_baseline"] = cpu_baseline_dense(args.cpu_nodes, args.cpu_edges, threads)
-        if not args.no_bm25 and world == 1:
+                "kernels": result["kernels"], "per_iter": result["per_iter"], "e2e": e2e, "parity": parity}
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        if world == 1 and not args.no_c1:
             try:
-                from stract_b200 import bm25_bench
-                line["bm25"] = bm25_bench.run(local_rank, peaks, peak_src)
-            except ImportError:
-                line["bm25"] = None
-            if line.get("bm25") is not None and not args.no_experimental:
-                # the opt-in BM25 kernels have passed their parity tests on the CPU emulator only: measured in a separate
-                # process (own CUDA context, bounded time), reported beside -- never instead of -- the default kernels
-                try:
-                    r = subprocess.run([sys.executable, "-m", "stract_b200.bm25_bench", str(local_rank)], cwd=ROOT,
-                                       capture_output=True, text=True, timeout=180)
-                    line["bm25"]["experimental"] = (json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0
-                                                    else {"error": (r.stderr or r.stdout)[-400:]})
-                except Exception as ex:  # noqa: BLE001
-                    line["bm25"]["experimental"] = {"error": repr(ex)[:400]}
-        if world == 1 and not args.no_experimental and args.nodes == 50_000_000 and args.edges == 1_000_000_000:
-            # path-1 switches that have only run on the CPU emulator, each in its own process and only
-            # while the whole bench is still short; reported beside the main numbers, never instead of them
-            exp = {}
-            try:   # hand the staging pool of this process back first: the child needs the HBM
-                from stract_b200._lib import lib as _sblib
-                torch.cuda.empty_cache()
-                _sblib().sb200_release_cached_memory(local_rank)
-            except Exception:  # noqa: BLE001
-                pass
-            variants = [("l2_persist_64MB", {"SB200_L2_PERSIST_MB": "64"}, ["--no-e2e", "--steps", "3"]),
-                        ("l2_evict_first_hints", {"SB200_L2_HINTS": "1"}, ["--no-e2e", "--steps", "3"]),
-                        ("e2e_arena_rowperm", {"SB200_ARENA": "1", "SB200_STAGE_ROWPERM": "1"}, ["--steps", "1", "--e2e-steps", "3"])]
-            for name, env, extra in variants:
-                if time.perf_counter() - t_bench0 > 300:
-                    exp[name] = {"skipped": "bench time budget"}
-                    continue
-                try:
-                    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--no-bm25", "--no-cpu", "--no-experimental", *extra],
-                                       cwd=ROOT, env={**os.environ, **env}, capture_output=True, text=True, timeout=150)
-                    if r.returncode != 0:
-                        exp[name] = {"error": (r.stderr or r.stdout)[-300:]}
-                        continue
-                    d = json.loads(r.stdout.strip().splitlines()[-1])
-                    exp[name] = {"env": env, "ms_per_step": d["ms_per_step"], "iterations": d["config"]["iterations_per_step"],
-                                 "top_kernel_avg_ms": (d.get("roofline") or {}).get("avg_launch_ms"),
-                                 "e2e_ms_per_step": (d.get("e2e") or {}).get("ms_per_step"),
-                                 "e2e_step_wall_ms": (d.get("e2e") or {}).get("step_wall_ms")}
-                except Exception as ex:  # noqa: BLE001
-                    exp[name] = {"error": repr(ex)[:300]}
-            line["experimental"] = exp
+                line["c1"] = run_c1(torch, local_rank)
+            except Exception as ex:  # noqa: BLE001
+                line["c1"] = {"error": repr(ex)[:300]}
+        if not args.no_bm25 and world == 1:
+            import bench_bm25
+            line["bm25"] = bench_bm25.run(local_rank, peaks, peak_src, cpu=not args.no_cpu)
+            for k in ("and_top1000_10M", "or5_signals_100M"):
+                if isinstance(line["bm25"].get(k), dict) and "parity" in line["bm25"][k]:
+                    parity[k] = line["bm25"][k]["parity"]
         print(json.dumps(line))
+        greens = [v.get("green") for v in parity.values() if isinstance(v, dict)]
+        if any(g is False for g in greens):
+            print("PARITY MISMATCH: " + json.dumps({k: v for k, v in parity.items() if isinstance(v, dict) and v.get("green") is False})[:2000],
+                  file=sys.stderr)
+            if world > 1:
+                dist.destroy_process_group()
+            return 3
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -156,17 +156,40 @@ SB200_API int sb200_graph_node_ids(sb200_graph* g, uint64_t first, uint64_t coun
 SB200_API int sb200_hyperball_exchange_ptrs(sb200_graph* g, void** regs, uint64_t* regs_bytes,
                                   void** frontier_words, uint64_t* frontier_bytes);
 SB200_API int sb200_graph_row_ranges(sb200_graph* g, uint64_t* begins /* world_size+1 */);
-/* Fused exchange (one process per GPU on one NVLink/NVSwitch box): every rank exports CUDA IPC handles of its two
- * register arrays and two bitmaps, imports those of all other ranks (any order) and enables p2p.  From then on
- * sb200_hyperball_step stores every produced row directly into the peers' replicas from inside the pull kernels
- * (st.global on peer pointers) and copies its owned changed-bitmap words to them, so no all-gather is needed:
- * between steps the caller only needs a barrier plus the sum of the per-rank changed counts (one small all-reduce
- * does both), then sb200_hyperball_exchange_done.  A barrier is also required after create/reset before the
- * first step. */
+/* Fused exchange (one process per GPU on one NVLink/NVSwitch box): every rank exports one blob -- CUDA IPC handles of
+ * its two register arrays, two bitmaps and its sync page, plus its rank -- imports the blobs of all other ranks (any
+ * order) and enables p2p.  From then on a step stores every produced row directly into the peers' replicas from inside
+ * the pull kernels (st.global on peer pointers) and copies its owned changed-bitmap words to them, so no all-gather is
+ * needed.  A row is stored only into the replicas of the ranks that gather it (subscriber mask = the owners of the
+ * node's out-neighbours, derived from the CSR at create): a replica is authoritative for the rows its rank owns or
+ * reads, the rest keep their initial value (sb200_graph_ownership names both sets).
+ *   - sb200_hyperball_run_sharded runs the whole round loop (the AMPC coordinator's, crates/core/src/ampc/
+ *     coordinator.rs:151-213, Meta.round_had_changes = the summed changed count): all ranks call it together; between
+ *     iterations they meet in a device-side barrier over the mapped sync pages that also sums the changed counts --
+ *     no host collective, no NCCL.  Returns SB200_ESTATE if a peer does not arrive within 20 s.
+ *   - stepping by hand (sb200_hyperball_step) stays possible: the caller then supplies a barrier plus the sum of the
+ *     per-rank changed counts between steps (one small all-reduce does both) and sb200_hyperball_exchange_done;
+ *     a barrier is also required after create/reset before the first step. */
 #define SB200_IPC_HANDLE_BYTES 64
-SB200_API int sb200_hyperball_ipc_export(sb200_graph* g, uint8_t* out /* 4 * SB200_IPC_HANDLE_BYTES */);
-SB200_API int sb200_hyperball_ipc_import(sb200_graph* g, const uint8_t* handles /* one peer's 4 handles */);
+#define SB200_IPC_BLOB_BYTES 384 /* 5 handles + {rank, world_size} as u32 + padding */
+SB200_API int sb200_hyperball_ipc_export(sb200_graph* g, uint8_t* out /* SB200_IPC_BLOB_BYTES */);
+SB200_API int sb200_hyperball_ipc_import(sb200_graph* g, const uint8_t* blob /* one peer's blob */);
 SB200_API int sb200_hyperball_p2p_enable(sb200_graph* g, int on);
+SB200_API int sb200_hyperball_run_sharded(sb200_graph* g, uint32_t max_iters, uint32_t* iters_done,
+                                          sb200_iter_stats* per_iter /* nullable, capacity cap */, uint32_t cap);
+
+/* The single-process form (one thread drives n handles: the n GPUs of one box, or several ranks on one GPU):
+ * handles[i] must have been created with rank i / world_size n from the same edge stream.  group_link enables peer
+ * access between the devices and wires every handle's publish targets to the other handles' arrays by address;
+ * group_run is the round loop: each round launches the iteration on every handle, then waits for all of them and sums
+ * the changed counts on the host.  per_iter (nullable) is an [n][cap] array. */
+SB200_API int sb200_hyperball_group_link(sb200_graph** handles, int n);
+SB200_API int sb200_hyperball_group_run(sb200_graph** handles, int n, uint32_t max_iters, uint32_t* iters_done,
+                                        sb200_iter_stats* per_iter, uint32_t cap);
+
+/* Per node, in ascending-id order: owned[i] = 1 iff this rank owns the node's row; subscribers[i] = bit mask of the ranks
+ * whose replica receives the row (all ranks when the subscriber filter is off).  Either output may be NULL. */
+SB200_API int sb200_graph_ownership(sb200_graph* g, uint8_t* owned, uint32_t* subscribers);
 
 /* The same fused exchange over caller-owned memory, addressed directly instead of through CUDA IPC.  Meant for
  * "symmetric" memory that is bound to an NVSwitch multicast object on every rank (cuMemCreate +
@@ -176,7 +199,8 @@ SB200_API int sb200_hyperball_p2p_enable(sb200_graph* g, int on);
  *      sb200_hyperball_bind_state right after create: the handle drops its own arrays, uses these (never frees
  *      them; they must outlive the handle) and re-initialises the HyperBall state;
  *   3. sb200_hyperball_set_publish_targets names where produced rows / bitmap words are stored in addition to the
- *      local replica: either world_size-1 unicast peer mappings, or ONE multicast mapping (n_targets = 1) -- a store
+ *      local replica: either world_size-1 unicast peer mappings IN RANK ORDER (own rank left out; the subscriber
+ *      filter applies), or ONE multicast mapping (n_targets = 1; reaches every replica, filter off) -- a store
  *      to a multicast address is replicated by the switch into every rank's replica, so a produced row leaves the
  *      GPU once instead of world_size-1 times.  n_targets = 0 switches the fused exchange off.
  * Inter-step protocol as above (barrier + changed-count all-reduce, then sb200_hyperball_exchange_done). */

@@ -24,6 +24,7 @@
 //                      baseline.
 #include "oracle_common.h"
 #include "../include/sb200_hll_tables.h"
+#include "oracle_dense.h"
 
 #include <algorithm>
 #include <cmath>
@@ -206,7 +207,6 @@ static std::vector<EdgeIn> gather_edges(const uint64_t* flo, const uint64_t* fhi
 
 // ---------------------------------------------------------------- faithful HyperBall --------
 typedef std::vector<uint8_t> Hll;
-struct Kahan { double sum = 0, err = 0; };
 
 struct Faithful {
   std::vector<EdgeIn> edges;  // raw stream as the Webgraph iterator would yield it
@@ -342,19 +342,6 @@ ORC_API void orc_hb_faithful_free(void* h) { delete (Faithful*)h; }
 // ---------------------------------------------------------------- dense HyperBall -----------
 // Same math over dense node ranks (rank = position in ascending u128 order), synchronous
 // update new[v] = max(old[v], max_{u->v kept, u changed} old[u]); steppable.
-struct Dense {
-  std::vector<u128> ids;            // ascending
-  std::vector<uint64_t> row_ptr;    // dst-major CSR over kept, unique, non-skipped edges
-  std::vector<uint32_t> col;
-  std::vector<uint8_t> old_r, new_r;  // N x 64
-  std::vector<uint8_t> changed, new_changed;
-  std::vector<Kahan> cent;
-  std::vector<uint64_t> size_old;
-  uint64_t t = 0;
-  bool has_changes = true;
-  uint64_t n_changed_last = 0;
-  int threads = 1;
-};
 
 ORC_API void* orc_hb_dense_create(const uint64_t* flo, const uint64_t* fhi, const uint64_t* tlo,
                                   const uint64_t* thi, const uint64_t* rel, uint64_t n_edges,

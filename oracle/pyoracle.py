@@ -72,6 +72,12 @@ def _proto(L):
     f("orc_hb_dense_kahan", None, C.c_void_p, _f64p, _f64p)
     f("orc_hb_dense_result", C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
     f("orc_hb_dense_free", None, C.c_void_p)
+    f("orc_hb_dense_create_mt", C.c_void_p, *edge_args, C.c_int)
+    f("orc_hb_dense_reset", None, C.c_void_p)
+    f("orc_hb_dense_num_self_loops", C.c_uint64, C.c_void_p)
+    f("orc_hb_dense_registers_ptr", C.c_void_p, C.c_void_p)
+    f("orc_synth_edges", None, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int,
+      _u64p, _u64p, _u64p, _u64p, _u64p, C.c_int)
     if hasattr(L, "orc_p2_proto_marker"):
         from . import pyoracle_p2
         pyoracle_p2.proto(L, f)
@@ -164,15 +170,31 @@ def hyperball_faithful(from_lo, from_hi, to_lo, to_hi, rel, skip_mask=SKIPPED_RE
 class DenseHyperBall:
     """Flat-array HyperBall over dense ranks; steppable (parity checker for registers)."""
 
-    def __init__(self, from_lo, from_hi, to_lo, to_hi, rel, skip_mask=SKIPPED_REL_MASK, threads=1):
+    def __init__(self, from_lo, from_hi, to_lo, to_hi, rel, skip_mask=SKIPPED_REL_MASK, threads=1, mt=False):
+        """mt=True stages with all `threads` (oracle_hyperball_mt.cpp; same object, for 10^9-edge inputs)."""
         arrs, n = _edges(from_lo, from_hi, to_lo, to_hi, rel)
         self.L = lib()
-        self.h = self.L.orc_hb_dense_create(*arrs, n, skip_mask, threads)
+        create = self.L.orc_hb_dense_create_mt if mt else self.L.orc_hb_dense_create
+        self.h = create(*arrs, n, skip_mask, threads)
+        if not self.h:
+            raise ValueError("more than 2^32-1 nodes")
         self.n_nodes = int(self.L.orc_hb_dense_num_nodes(self.h))
         self.n_edges = int(self.L.orc_hb_dense_num_edges(self.h))
 
     def step(self):
         return int(self.L.orc_hb_dense_step(self.h))
+
+    def reset(self):
+        self.L.orc_hb_dense_reset(self.h)
+
+    def num_self_loops(self):
+        return int(self.L.orc_hb_dense_num_self_loops(self.h))
+
+    def registers_view(self):
+        """Zero-copy (n_nodes, 64) uint8 view of the current registers (valid until the next step / close)."""
+        p = self.L.orc_hb_dense_registers_ptr(self.h)
+        buf = (C.c_uint8 * (self.n_nodes * 64)).from_address(p)
+        return np.frombuffer(buf, np.uint8).reshape(self.n_nodes, 64)
 
     def run(self, max_iters=0):
         return int(self.L.orc_hb_dense_run(self.h, max_iters))
@@ -215,6 +237,14 @@ class DenseHyperBall:
             self.close()
         except Exception:
             pass
+
+
+def synth_edges(kind, n_nodes, n_edges, seed=42, scale=26, first=0, threads=1):
+    """CPU port of the repo's synthetic edge generator (stract_b200/synth.py, csrc/synth.cu): kind 0 = uniform
+    (configs[0]), 1 = R-MAT (configs[1]).  Returns dict(from_lo, from_hi, to_lo, to_hi, rel_flags)."""
+    a = [np.empty(n_edges, np.uint64) for _ in range(5)]
+    lib().orc_synth_edges(kind, n_nodes, first, n_edges, seed, scale, *a, threads)
+    return dict(from_lo=a[0], from_hi=a[1], to_lo=a[2], to_hi=a[3], rel_flags=a[4])
 
 
 def harmonic_ranks(ids_lo, ids_hi, values, ties_desc=False):

@@ -24,6 +24,9 @@ class KernelProf(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_uint64), ("ms", C.c_double), ("alg_bytes", C.c_double)]
 
 
+IPC_BLOB_BYTES = 384  # SB200_IPC_BLOB_BYTES
+
+
 class IterStats(C.Structure):
     _fields_ = [("t", C.c_uint32), ("mode", C.c_uint32), ("n_changed", C.c_uint64),
                 ("edges_active", C.c_uint64), ("ms", C.c_float)]
@@ -77,6 +80,10 @@ def declare(L):
     f("sb200_hyperball_ipc_export", i32, vp, vp)
     f("sb200_hyperball_ipc_import", i32, vp, vp)
     f("sb200_hyperball_p2p_enable", i32, vp, i32)
+    f("sb200_hyperball_run_sharded", i32, vp, u32, C.POINTER(u32), C.POINTER(IterStats), u32)
+    f("sb200_hyperball_group_link", i32, C.POINTER(vp), i32)
+    f("sb200_hyperball_group_run", i32, C.POINTER(vp), i32, u32, C.POINTER(u32), C.POINTER(IterStats), u32)
+    f("sb200_graph_ownership", i32, vp, vp, vp)
     f("sb200_hyperball_state_bytes", i32, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
     f("sb200_hyperball_bind_state", i32, vp, vp, vp, vp, vp)
     f("sb200_hyperball_set_publish_targets", i32, vp, i32, vp, vp, vp, vp)

@@ -16,6 +16,17 @@ void set_error(const char* fmt, ...) {
 int hb_alloc_state(sb200_graph* g);
 int hb_reset(sb200_graph* g);
 int hb_step(sb200_graph* g, sb200_iter_stats* st);
+int hb_step_launch(sb200_graph* g, bool with_barrier);
+int hb_step_finish(sb200_graph* g, sb200_iter_stats* st);
+int hb_barrier(sb200_graph* g);
+__global__ void k_owned_flags(const uint32_t* __restrict__ inv, const uint32_t* __restrict__ sub, uint64_t N, uint32_t world, uint32_t rank,
+                              uint8_t* owned, uint32_t* sub_out) {
+  const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;   // r = position in ascending-id order
+  if (r >= N) return;
+  const uint32_t v = inv[r];
+  if (owned) owned[r] = (world <= 1 || ((v >> 5) % world) == rank) ? 1 : 0;
+  if (sub_out) sub_out[r] = sub ? sub[v] : (world <= 1 ? 1u : 0xFFFFFFFFu >> (32 - world));
+}
 int hb_result(sb200_graph* g, uint64_t* id_lo, uint64_t* id_hi, double* cent, uint64_t cap, uint64_t* len);
 int hb_registers(sb200_graph* g, uint64_t first, uint64_t count, uint8_t* out);
 int hb_ranked(sb200_graph* g, int ties_desc, uint64_t* id_lo, uint64_t* id_hi, double* cent, uint64_t cap, uint64_t* len);
@@ -27,7 +38,7 @@ uint64_t sb200_graph::hbm_bytes() const {
   return id_lo.bytes() + id_hi.bytes() + perm.bytes() + inv.bytes() + row_ptr.bytes() + col.bytes() + fwd_ptr.bytes() +
          fwd_dst.bytes() + item_row.bytes() + item_start.bytes() + partial.bytes() + regs[0].bytes() + regs[1].bytes() +
          bm[0].bytes() + bm[1].bytes() + size_cache.bytes() + kahan_sum.bytes() + kahan_err.bytes() +
-         frontier_list.bytes() + frontier_off.bytes() + cub_tmp.bytes() + counters.bytes();
+         frontier_list.bytes() + frontier_off.bytes() + cub_tmp.bytes() + counters.bytes() + sub_mask.bytes() + sync_page.bytes();
 }
 
 extern "C" {
@@ -101,6 +112,8 @@ void sb200_graph_destroy(sb200_graph* g) {
     if (g->peer_regs[i][p]) cudaIpcCloseMemHandle(g->peer_regs[i][p]);
     if (g->peer_bm[i][p]) cudaIpcCloseMemHandle(g->peer_bm[i][p]);
   }
+  if (g->peers_ipc) for (int p = 0; p < g->n_peers; p++) if (g->peer_sync[p]) cudaIpcCloseMemHandle(g->peer_sync[p]);
+  if (g->l2_window_bytes) cudaCtxResetPersistingL2Cache();  // hand the pinned hub lines back to the normal L2
   if (g->h_counters) cudaFreeHost(g->h_counters);
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
@@ -224,32 +237,43 @@ int sb200_graph_row_ranges(sb200_graph* g, uint64_t* begins) {
   return SB200_OK;
 }
 // ---- fused exchange over NVLink peer memory (CUDA IPC between the per-GPU processes) ----------------------
-int sb200_hyperball_ipc_export(sb200_graph* g, uint8_t* out /* 4 x 64 bytes */) {
+int sb200_hyperball_ipc_export(sb200_graph* g, uint8_t* out /* SB200_IPC_BLOB_BYTES */) {
   SB_ENTER(g);
   if (!out) SB_FAIL(SB200_EINVAL, "out is NULL");
-  void* ptrs[4] = {g->regs[0].p, g->regs[1].p, g->bm[0].p, g->bm[1].p};
-  for (int i = 0; i < 4; i++) {
+  if (g->world < 2 || !g->sync_page.p) SB_FAIL(SB200_ESTATE, "only sharded handles (world_size > 1) export their state");
+  memset(out, 0, SB200_IPC_BLOB_BYTES);
+  void* ptrs[5] = {g->regs[0].p, g->regs[1].p, g->bm[0].p, g->bm[1].p, g->sync_page.p};
+  for (int i = 0; i < 5; i++) {
     cudaIpcMemHandle_t h;
     SB_CUDA(cudaIpcGetMemHandle(&h, ptrs[i]));
     static_assert(sizeof(h) == SB200_IPC_HANDLE_BYTES, "IPC handle size");
     memcpy(out + (size_t)i * SB200_IPC_HANDLE_BYTES, &h, sizeof(h));
   }
+  const uint32_t tail[2] = {(uint32_t)g->rank, (uint32_t)g->world};
+  memcpy(out + 5 * SB200_IPC_HANDLE_BYTES, tail, sizeof(tail));
   return SB200_OK;
 }
-int sb200_hyperball_ipc_import(sb200_graph* g, const uint8_t* handles) {
+int sb200_hyperball_ipc_import(sb200_graph* g, const uint8_t* blob) {
   SB_ENTER(g);
-  if (!handles) SB_FAIL(SB200_EINVAL, "handles is NULL");
+  if (!blob) SB_FAIL(SB200_EINVAL, "blob is NULL");
   if (!g->peers_ipc) SB_FAIL(SB200_ESTATE, "publish targets were set by address; IPC import cannot be mixed in");
   if (g->n_peers >= sb200::MAX_PEERS) SB_FAIL(SB200_ERANGE, "more than %d peers", sb200::MAX_PEERS);
-  void* opened[4];
-  for (int i = 0; i < 4; i++) {
+  uint32_t tail[2];
+  memcpy(tail, blob + 5 * SB200_IPC_HANDLE_BYTES, sizeof(tail));
+  if ((int)tail[1] != g->world || (int)tail[0] >= g->world || (int)tail[0] == g->rank)
+    SB_FAIL(SB200_EINVAL, "blob of rank %u / world %u does not fit this handle (rank %d / world %d)", tail[0], tail[1], g->rank, g->world);
+  for (int p = 0; p < g->n_peers; p++) if (g->peer_rank[p] == (int)tail[0]) SB_FAIL(SB200_ESTATE, "rank %u imported twice", tail[0]);
+  void* opened[5];
+  for (int i = 0; i < 5; i++) {
     cudaIpcMemHandle_t h;
-    memcpy(&h, handles + (size_t)i * SB200_IPC_HANDLE_BYTES, sizeof(h));
+    memcpy(&h, blob + (size_t)i * SB200_IPC_HANDLE_BYTES, sizeof(h));
     SB_CUDA(cudaIpcOpenMemHandle(&opened[i], h, cudaIpcMemLazyEnablePeerAccess));
   }
   const int p = g->n_peers++;
   g->peer_regs[0][p] = opened[0]; g->peer_regs[1][p] = opened[1];
   g->peer_bm[0][p] = opened[2]; g->peer_bm[1][p] = opened[3];
+  g->peer_sync[p] = opened[4];
+  g->peer_rank[p] = (int)tail[0];
   return SB200_OK;
 }
 int sb200_hyperball_p2p_enable(sb200_graph* g, int on) {
@@ -299,6 +323,116 @@ int sb200_hyperball_set_publish_targets(sb200_graph* g, int n_targets, const uin
     g->peer_bm[0][p] = on ? (void*)(uintptr_t)bitmap0[p] : nullptr; g->peer_bm[1][p] = on ? (void*)(uintptr_t)bitmap1[p] : nullptr;
   }
   g->n_peers = n_targets; g->peers_ipc = false; g->p2p = n_targets > 0;
+  // world_size-1 unicast targets are taken in rank order (own rank left out); any other count (e.g. the single
+  // multicast mapping) reaches every replica at once, so the subscriber filter is off
+  if (n_targets == g->world - 1) { for (int p = 0; p < n_targets; p++) g->peer_rank[p] = p < g->rank ? p : p + 1; g->publish_all = env_flag("SB200_PUBLISH_ALL", false); }
+  else g->publish_all = true;
+  return SB200_OK;
+}
+
+// ---- the round loop behind the ABI ---------------------------------------------------------------------------
+// (a) one process, n handles (n GPUs of one box, or -- for tests -- several ranks on one GPU): link wires every
+//     handle's publish targets to the other handles' arrays by address, run drives the rounds.
+int sb200_hyperball_group_link(sb200_graph** hs, int n) {
+  if (!hs || n < 1) SB_FAIL(SB200_EINVAL, "bad group");
+  for (int i = 0; i < n; i++) {
+    if (!hs[i]) SB_FAIL(SB200_EINVAL, "NULL handle %d", i);
+    if (hs[i]->world != n || hs[i]->rank != i) SB_FAIL(SB200_EINVAL, "handle %d has rank %d / world %d; expected rank %d / world %d", i, hs[i]->rank, hs[i]->world, i, n);
+    if (hs[i]->N != hs[0]->N || hs[i]->E_kept != hs[0]->E_kept) SB_FAIL(SB200_EINVAL, "handle %d was staged from a different graph", i);
+    if (hs[i]->n_peers) SB_FAIL(SB200_ESTATE, "handle %d already has publish targets", i);
+  }
+  if (n == 1) return SB200_OK;
+  if (n - 1 > sb200::MAX_PEERS) SB_FAIL(SB200_ERANGE, "more than %d peers", sb200::MAX_PEERS);
+  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) {
+    if (i == j || hs[i]->device == hs[j]->device) continue;
+    int can = 0;
+    SB_CUDA(cudaDeviceCanAccessPeer(&can, hs[i]->device, hs[j]->device));
+    if (!can) SB_FAIL(SB200_ESTATE, "device %d cannot access device %d", hs[i]->device, hs[j]->device);
+    SB_CUDA(cudaSetDevice(hs[i]->device));
+    const cudaError_t e = cudaDeviceEnablePeerAccess(hs[j]->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) SB_CUDA(e);
+    cudaGetLastError();
+  }
+  for (int i = 0; i < n; i++) {
+    sb200_graph* g = hs[i];
+    int p = 0;
+    for (int j = 0; j < n; j++) {
+      if (j == i) continue;
+      g->peer_regs[0][p] = hs[j]->regs[0].p; g->peer_regs[1][p] = hs[j]->regs[1].p;
+      g->peer_bm[0][p] = hs[j]->bm[0].p; g->peer_bm[1][p] = hs[j]->bm[1].p;
+      g->peer_sync[p] = hs[j]->sync_page.p; g->peer_rank[p] = j;
+      p++;
+    }
+    g->n_peers = n - 1; g->peers_ipc = false; g->p2p = true;
+  }
+  return SB200_OK;
+}
+
+int sb200_hyperball_group_run(sb200_graph** hs, int n, uint32_t max_iters, uint32_t* iters_done, sb200_iter_stats* per_iter, uint32_t cap) {
+  if (!hs || n < 1) SB_FAIL(SB200_EINVAL, "bad group");
+  for (int i = 0; i < n; i++) if (!hs[i] || hs[i]->world != n || hs[i]->rank != i) SB_FAIL(SB200_EINVAL, "handle %d does not belong to a group of %d", i, n);
+  for (int i = 0; i < n; i++) if (n > 1 && (!hs[i]->p2p || hs[i]->n_peers != n - 1)) SB_FAIL(SB200_ESTATE, "call sb200_hyperball_group_link first");
+  for (int i = 0; i < n; i++) { SB_CUDA(cudaSetDevice(hs[i]->device)); SB_CUDA(cudaStreamSynchronize(hs[i]->stream)); }  // every replica initialised
+  uint32_t t = 0;
+  bool changes = hs[0]->N > 0 && hs[0]->has_changes;
+  // coordinator.rs:151-213: rounds until one leaves Meta.round_had_changes unset
+  while (changes && (max_iters == 0 || t < max_iters)) {
+    if (t >= 100000) SB_FAIL(SB200_ESTATE, "HyperBall did not converge within 100000 iterations");
+    for (int i = 0; i < n; i++) { SB_CUDA(cudaSetDevice(hs[i]->device)); SB_TRY(hb_step_launch(hs[i], false)); }
+    uint64_t total = 0;
+    for (int i = 0; i < n; i++) {
+      sb200_iter_stats st;
+      SB_CUDA(cudaSetDevice(hs[i]->device));
+      SB_TRY(hb_step_finish(hs[i], &st));
+      total += st.n_changed;
+      if (per_iter && t < cap) per_iter[(size_t)i * cap + t] = st;
+    }
+    for (int i = 0; i < n; i++) { hs[i]->n_changed_prev = total; hs[i]->has_changes = total != 0; hs[i]->exchange_pending = false; }
+    changes = total != 0;
+    t++;
+  }
+  if (iters_done) *iters_done = t;
+  return SB200_OK;
+}
+
+// (b) one process per GPU: every rank calls this at the same time after the IPC blobs have been exchanged and
+//     sb200_hyperball_p2p_enable.  No host-side collective is involved: the ranks meet in k_barrier_count.
+int sb200_hyperball_run_sharded(sb200_graph* g, uint32_t max_iters, uint32_t* iters_done, sb200_iter_stats* per_iter, uint32_t cap) {
+  SB_ENTER(g);
+  if (g->world < 2) return sb200_hyperball_run(g, max_iters, iters_done, per_iter, cap);
+  if (!g->p2p || g->n_peers != g->world - 1) SB_FAIL(SB200_ESTATE, "exchange the IPC blobs of all %d peers and enable p2p first", g->world - 1);
+  SB_CUDA(cudaEventRecord(g->ev_run0, g->stream));
+  SB_TRY(hb_barrier(g));
+  uint32_t n = 0;
+  while (g->has_changes && (max_iters == 0 || g->t < max_iters)) {
+    if (g->t >= 100000) SB_FAIL(SB200_ESTATE, "HyperBall did not converge within 100000 iterations");
+    sb200_iter_stats st;
+    SB_TRY(hb_step_launch(g, true));
+    SB_TRY(hb_step_finish(g, &st));
+    if (per_iter && n < cap) per_iter[n] = st;
+    n++;
+  }
+  SB_CUDA(cudaEventRecord(g->ev_run1, g->stream));
+  SB_CUDA(cudaStreamSynchronize(g->stream));
+  cudaEventElapsedTime(&g->last_run_ms, g->ev_run0, g->ev_run1);
+  if (iters_done) *iters_done = g->t;
+  return SB200_OK;
+}
+
+// which nodes this rank owns / which ranks read each node's row, in ascending-id order (parity checks of sharded handles)
+int sb200_graph_ownership(sb200_graph* g, uint8_t* owned /* nullable, n_nodes */, uint32_t* subscribers /* nullable, n_nodes */) {
+  SB_ENTER(g);
+  const uint64_t N = g->N;
+  if (!N) return SB200_OK;
+  DevBuf<uint8_t> o; DevBuf<uint32_t> m;
+  if (owned) SB_TRY(o.alloc(N));
+  if (subscribers) SB_TRY(m.alloc(N));
+  SB_LAUNCH(k_owned_flags, div_up(N, 256), 256, 0, g->stream, g->inv.p, (g->publish_all || !g->sub_mask.p) ? (const uint32_t*)nullptr : g->sub_mask.p, N,
+            (uint32_t)g->world, (uint32_t)g->rank, owned ? o.p : (uint8_t*)nullptr, subscribers ? m.p : (uint32_t*)nullptr);
+  SB_CHECK_LAUNCH();
+  if (owned) SB_CUDA(cudaMemcpyAsync(owned, o.p, N, cudaMemcpyDefault, g->stream));
+  if (subscribers) SB_CUDA(cudaMemcpyAsync(subscribers, m.p, N * 4, cudaMemcpyDefault, g->stream));
+  SB_CUDA(cudaStreamSynchronize(g->stream));
   return SB200_OK;
 }
 

@@ -20,7 +20,7 @@ static Arena* g_arena[64] = {nullptr};
 static std::mutex g_arena_mu;
 
 bool arena_enabled() {
-  static const bool on = [] { const char* e = getenv("SB200_ARENA"); return e && *e && *e != '0'; }();
+  static const bool on = env_flag("SB200_ARENA", true);  // default since round 2 (SB200_ARENA=0: the driver's stream-ordered pool)
   return on;
 }
 static Arena* arena_of(int dev, bool create) {

@@ -792,14 +792,14 @@ static int run_batch(sb200_segment* g, const sb200_bm25_batch* b, int mode, cons
     if (kmode == 2) SB_TRY(launch_topk<2>(P, nq, s));
     else if (kmode == 0) SB_TRY(launch_topk<0>(P, nq, s));
     else SB_TRY(launch_topk<1>(P, nq, s));
-  } else if (kmode == 0 && getenv("SB200_BM25_AND3") != nullptr && [&] {
+  } else if (kmode == 0 && env_flag("SB200_BM25_AND3", true) && [&] {
                // a single-clause "intersection" makes every posting a hit: its candidate list is the whole posting list and
                // the select pass would crawl through it chunk by chunk; the threshold-pruning kernel handles those batches
                for (uint32_t slot = 0; slot < nq; slot++)
                  if (nterms[slot] == 1 && g->h_df[terms[(size_t)slot * nt]] > 65536u) return false;
                return true;
              }()) {
-    SB_TRY(run_and3(g, P, terms, nterms, nq, nt, k, s));  // unit-based intersection (bm25_and3.cuh), opt-in
+    SB_TRY(run_and3(g, P, terms, nterms, nq, nt, k, s));  // unit-based intersection (bm25_and3.cuh); SB200_BM25_AND3=0: k_topk_warp<AND>
   } else {
     SB_TRY(ensure(g->g_khi, (size_t)n_items * cap)); SB_TRY(ensure(g->g_klo, (size_t)n_items * cap));
     WParams W;
@@ -811,7 +811,7 @@ static int run_batch(sb200_segment* g, const sb200_bm25_batch* b, int mode, cons
     W.k1p1 = P.k1p1; W.coeff_text = P.coeff_text; W.sig = P.sig; W.n_cols = P.n_cols; W.coeffs = P.coeffs; W.max_docs = P.max_docs;
     W.g_khi = g->g_khi.p; W.g_klo = g->g_klo.p;
     W.o_docs = P.o_docs; W.o_scores = P.o_scores; W.o_totals = P.o_totals; W.o_n = P.o_n; W.counters = P.counters;
-    const bool use_or3 = kmode != 0 && W.max_docs == 0 && getenv("SB200_BM25_OR3") != nullptr;  // opt-in, bm25_or3.cuh
+    const bool use_or3 = kmode != 0 && W.max_docs == 0 && env_flag("SB200_BM25_OR3", true);  // bm25_or3.cuh; SB200_BM25_OR3=0: k_topk_warp
     if (use_or3) { if (kmode == 2) SB_TRY(launch_or3<2>(W, s)); else SB_TRY(launch_or3<1>(W, s)); }
     else if (kmode == 2) SB_TRY(launch_topk_warp<2>(W, s));
     else if (kmode == 0) SB_TRY(launch_topk_warp<0>(W, s));

@@ -129,6 +129,12 @@ int copy_in(void* dst_dev, const void* src_any, size_t bytes, cudaStream_t strea
 bool is_device_ptr(const void* p);
 
 static inline unsigned div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+// switch from the environment: unset -> dflt, "0"/"" -> off, anything else -> on
+static inline bool env_flag(const char* name, bool dflt) {
+  const char* e = getenv(name);
+  if (!e) return dflt;
+  return *e && *e != '0';
+}
 
 // ---- device helpers --------------------------------------------------------------------------
 // Byte-wise unsigned max of 4 packed bytes, valid when every byte is < 128 -- which holds for HyperLogLog<64>

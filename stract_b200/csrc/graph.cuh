@@ -16,7 +16,14 @@
 
 namespace sb200 {
 constexpr int MAX_PEERS = 15;
-struct PeerOut { uint4* newr[MAX_PEERS]; uint32_t* bmc[MAX_PEERS]; int n; uint32_t world, rank; };
+// publish targets of a sharded handle, by value in the kernel parameters.  `sub` (nullable) is the subscriber mask
+// of every row: bit r is set iff rank r has an in-edge from that node, i.e. ever reads its row; with it a produced
+// row is stored only into the replicas that will gather it (prank[p] = rank behind target p).
+struct PeerOut { uint4* newr[MAX_PEERS]; uint32_t* bmc[MAX_PEERS]; const uint32_t* sub; int n; uint32_t world, rank; uint8_t prank[MAX_PEERS + 1]; };
+// device-side barrier + changed-count sum between the ranks of one box (k_barrier_count): every rank owns a page of
+// 2 x 64 slots (epoch parity x writer rank) that all peers map
+constexpr int SYNC_SLOTS = 128;
+struct SyncView { unsigned long long* local; unsigned long long* peer[MAX_PEERS]; int n; uint32_t world, rank; };
 }
 
 struct sb200_graph {
@@ -68,6 +75,16 @@ struct sb200_graph {
   bool peers_ipc = true;  // peer mappings came from cudaIpcOpenMemHandle (closed at destroy); false: caller-owned addresses
   void* peer_regs[2][sb200::MAX_PEERS] = {{nullptr}};
   void* peer_bm[2][sb200::MAX_PEERS] = {{nullptr}};
+  int peer_rank[sb200::MAX_PEERS] = {0};   // rank behind publish target p
+  bool publish_all = false;                // one multicast target / SB200_PUBLISH_ALL=1: no subscriber filtering
+  sb200::DevBuf<uint32_t> sub_mask;        // [N] subscriber mask per row (internal order), sharded handles only
+  uint64_t n_subscribed = 0;               // sum over owned rows of the number of remote subscribers (profile: NVLink rows per dense iteration)
+  // device-side inter-rank barrier (sb200_hyperball_run_sharded)
+  sb200::DevBuf<unsigned long long> sync_page;
+  void* peer_sync[sb200::MAX_PEERS] = {nullptr};
+  uint64_t sync_epoch = 0;
+  bool step_in_flight = false, step_with_barrier = false;
+  int step_mode = 0;
   double dense_frac = 0.35, push_div = 48.0;  // mode policy (see hb_step)
   int force_mode = -1;
   uint64_t l2_window_bytes = 0;  // SB200_L2_PERSIST_MB: persisting-L2 access window over the hot prefix of the `old` register array

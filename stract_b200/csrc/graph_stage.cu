@@ -267,6 +267,38 @@ __global__ void k_owned_edges(const uint32_t* __restrict__ row_ptr, uint64_t n, 
   for (int o = 16; o; o >>= 1) d += __shfl_down_sync(0xffffffffu, d, o);
   if ((threadIdx.x & 31) == 0 && d) atomicAdd(out, d);
 }
+// Subscriber masks (sharded handles): bit r of sub[u] is set iff some row owned by rank r has an in-edge from u, i.e.
+// rank r gathers u's counter.  The test before the atomic keeps the ~E updates of a power-law graph from piling up on
+// the hubs' words: once a bit is set, later edges only read it.
+__device__ __forceinline__ void sub_mark(uint32_t* sub, uint32_t u, uint32_t bit) {
+  if ((__ldg(sub + u) & bit) == 0u) atomicOr(sub + u, bit);
+}
+__global__ void k_sub_items(uint64_t n_items, const uint32_t* __restrict__ item_row, const uint32_t* __restrict__ item_start,
+                            uint32_t warp_row_begin, const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col, int chunk,
+                            uint32_t world, uint32_t* sub) {
+  const uint64_t item = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  if (item >= n_items) return;
+  const uint32_t lane = threadIdx.x & 31, row = item_row[item];
+  const uint32_t bit = 1u << ((row >> 5) % world);
+  const uint32_t c = (uint32_t)item - item_start[row - warp_row_begin];
+  const uint32_t e0 = row_ptr[row] + c * (uint32_t)chunk, e1 = min(e0 + (uint32_t)chunk, row_ptr[row + 1]);
+  for (uint32_t e = e0 + lane; e < e1; e += 32) sub_mark(sub, col[e], bit);
+}
+__global__ void k_sub_rows(uint64_t row_begin, uint64_t row_end, const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col,
+                           uint32_t world, uint32_t* sub) {
+  const uint64_t row = row_begin + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (row >= row_end) return;
+  const uint32_t bit = 1u << ((uint32_t)(row >> 5) % world);
+  for (uint32_t e = row_ptr[row]; e < row_ptr[row + 1]; e++) sub_mark(sub, col[e], bit);
+}
+// remote subscribers of the rows this rank owns (the number of 64-B rows one dense iteration sends over NVLink)
+__global__ void k_sub_count(const uint32_t* __restrict__ sub, uint64_t n, uint32_t world, uint32_t rank, unsigned long long* out) {
+  const uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  unsigned long long d = 0;
+  if (v < n && ((v >> 5) % world) == rank) d = __popc(sub[v] & ~(1u << rank));
+  for (int o = 16; o; o >>= 1) d += __shfl_down_sync(0xffffffffu, d, o);
+  if ((threadIdx.x & 31) == 0 && d) atomicAdd(out, d);
+}
 __global__ void k_row_chunks(const uint32_t* __restrict__ row_ptr, uint64_t row0, uint64_t nrows, int chunk,
                              uint32_t* nchunks) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -590,8 +622,8 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
   pt.mark("3b remap + sort (dst CSR)");
   // destination-major CSR in internal ids
   DevBuf<uint32_t> col_full; SB_TRY(col_full.alloc(E));
-  if (E && getenv("SB200_STAGE_ROWPERM") != nullptr && !(g->world == 1 && getenv("SB200_EAGER_FWD") != nullptr)) {
-    // experiment switch: move the rows as blocks instead of re-sorting every edge (see k_row_permute)
+  if (E && env_flag("SB200_STAGE_ROWPERM", true) && !(g->world == 1 && getenv("SB200_EAGER_FWD") != nullptr)) {
+    // move the rows as blocks instead of re-sorting every edge (see k_row_permute); SB200_STAGE_ROWPERM=0: second radix sort
     DevBuf<uint32_t> rank_ptr; SB_TRY(rank_ptr.alloc(N + 1));
     SB_LAUNCH(k_offsets_from_sorted, div_up(E + 1, TPB), TPB, 0, s, k, E, N, rank_ptr.p); SB_CHECK_LAUNCH();
     SB_LAUNCH(k_row_permute, div_up(E, TPB), TPB, 0, s, k, E, rank_ptr.p, g->inv.p, g->row_ptr.p, col_full.p); SB_CHECK_LAUNCH();
@@ -685,6 +717,28 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
     SB_CHECK_LAUNCH();
     SB_TRY(g->partial.alloc((size_t)std::max<uint64_t>(1, g->n_multi_items) * 4));
     SB_CUDA(cudaStreamSynchronize(s));
+  }
+  if (g->world > 1 && N) {
+    // every rank holds the full CSR, so it derives the subscriber mask of every node itself (no exchange needed)
+    pt.mark("5 subscriber masks");
+    SB_TRY(g->sub_mask.alloc(N));
+    SB_CUDA(cudaMemsetAsync(g->sub_mask.p, 0, N * 4, s));
+    if (g->n_items) {
+      SB_LAUNCH(k_sub_items, div_up(g->n_items * 32, TPB), TPB, 0, s, g->n_items, g->item_row.p, g->item_start.p,
+                (uint32_t)g->warp_row_begin, g->row_ptr.p, g->col.p, CHUNK_EDGES, (uint32_t)g->world, g->sub_mask.p);
+      SB_CHECK_LAUNCH();
+    }
+    if (g->quad_row_end > g->quad_row_begin) {
+      SB_LAUNCH(k_sub_rows, div_up(g->quad_row_end - g->quad_row_begin, TPB), TPB, 0, s, g->quad_row_begin, g->quad_row_end,
+                g->row_ptr.p, g->col.p, (uint32_t)g->world, g->sub_mask.p);
+      SB_CHECK_LAUNCH();
+    }
+    SB_CUDA(cudaMemsetAsync(ctr.p, 0, sizeof(unsigned long long), s));
+    SB_LAUNCH(k_sub_count, div_up(N, TPB), TPB, 0, s, g->sub_mask.p, N, (uint32_t)g->world, (uint32_t)g->rank, ctr.p);
+    SB_CHECK_LAUNCH();
+    SB_CUDA(cudaMemcpyAsync(h_ctr, ctr.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    g->n_subscribed = h_ctr[0];
   }
   pt.mark(nullptr);
   SB_CUDA(cudaEventRecord(g->ev1, s));

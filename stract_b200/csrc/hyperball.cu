@@ -168,13 +168,17 @@ __global__ void k_bm_fill(uint32_t* bm, uint64_t N, uint64_t words) {
 __device__ __forceinline__ bool owned_row(const PeerOut& o, uint32_t row) {
   return o.world <= 1u || ((row >> 5) % o.world) == o.rank;
 }
-template <bool HINT = false>
+// Subscriber filter: a peer that has no in-edge from `row` never gathers it, so the row is stored only into the
+// replicas of the ranks named in its subscriber mask (at C2 size 69 % / 55 % / 42 % of the (row, peer) pairs at
+// 2 / 4 / 8 ranks).  A non-subscriber's copy of the row simply stays at its initial value and is never read.
 __device__ __forceinline__ void publish_row(uint4* __restrict__ newr, uint32_t* __restrict__ bm_cur, const PeerOut& peers,
-                                            uint32_t row, uint32_t sub, uint4 acc, bool write, bool changed, uint64_t pol = 0) {
-  if (write) { if (HINT) st_hint_u4(newr + (uint64_t)row * 4 + sub, acc, pol); else newr[(uint64_t)row * 4 + sub] = acc; }
+                                            uint32_t row, uint32_t sub, uint4 acc, bool write, bool changed) {
+  if (write) newr[(uint64_t)row * 4 + sub] = acc;
   if (changed && sub == 0) atomicOr(bm_cur + (row >> 5), 1u << (row & 31));
+  if (!write || peers.n == 0) return;
+  const uint32_t want = peers.sub ? __ldg(peers.sub + row) : 0xFFFFFFFFu;
   for (int p = 0; p < peers.n; p++) {
-    if (write) peers.newr[p][(uint64_t)row * 4 + sub] = acc;
+    if ((want >> peers.prank[p]) & 1u) peers.newr[p][(uint64_t)row * 4 + sub] = acc;
     // the changed bit is NOT pushed per row: a 32-row block has one owner, so k_publish_bitmap copies the owner's
     // finished bitmap words to the peers with plain stores (3.5 M remote atomics per peer and iteration measured
     // as the bottleneck of the 8-GPU run)
@@ -186,7 +190,7 @@ __device__ __forceinline__ bool bm_test(const uint32_t* __restrict__ bm, uint32_
 }
 
 // ---- pull, short rows: 4 lanes per destination row ----------------------------------------------------
-template <bool FRONTIER, bool HINT = false>
+template <bool FRONTIER>
 __global__ void __launch_bounds__(256, 7) k_pull_quad(uint64_t row_begin, uint64_t row_end,
     const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col, uint32_t col_base,
     const uint4* __restrict__ oldr, uint4* __restrict__ newr,
@@ -200,18 +204,17 @@ __global__ void __launch_bounds__(256, 7) k_pull_quad(uint64_t row_begin, uint64
   live = live && owned_row(peers, (uint32_t)row);
   if (__ballot_sync(0xffffffffu, live) == 0u) return;  // none of this warp's rows belongs to this rank
   const uint32_t e0 = live ? row_ptr[row] - col_base : 0u, e1 = live ? row_ptr[row + 1] - col_base : 0u;
-  const uint64_t pol = HINT ? l2_policy_evict_first() : 0ull;
-  const uint4 own = HINT ? ld_hint_u4(oldr + row * 4 + sub, pol) : oldr[row * 4 + sub];
+  const uint4 own = oldr[row * 4 + sub];
   uint4 acc = own;
   // lane `sub` fetches source index e+sub (one 16-B request per quad per 4 edges, prefetched one step ahead)
   // and the quad shares the four indices by shuffle; an out-of-range or (FRONTIER) unchanged source is
   // redirected to the row itself, which is a no-op under max and hits L1.
   const unsigned qmask = 0xFu << (lane & ~3u);
   const uint32_t self = (uint32_t)row;
-  uint32_t nxt = (e0 + sub < e1) ? (HINT ? ld_stream_hint_u32(col + e0 + sub, pol) : ld_stream_u32(col + e0 + sub)) : self;
+  uint32_t nxt = (e0 + sub < e1) ? ld_stream_u32(col + e0 + sub) : self;
   for (uint32_t e = e0; e < e1; e += 4) {
     uint32_t mine = nxt;
-    nxt = (e + 4 + sub < e1) ? (HINT ? ld_stream_hint_u32(col + e + 4 + sub, pol) : ld_stream_u32(col + e + 4 + sub)) : self;
+    nxt = (e + 4 + sub < e1) ? ld_stream_u32(col + e + 4 + sub) : self;
     if (FRONTIER) mine = bm_test(bm_prev, mine) ? mine : self;
     const uint32_t i0 = __shfl_sync(qmask, mine, 0, 4);
     const uint32_t i1 = __shfl_sync(qmask, mine, 1, 4);
@@ -226,11 +229,11 @@ __global__ void __launch_bounds__(256, 7) k_pull_quad(uint64_t row_begin, uint64
   const unsigned ball = __ballot_sync(0xffffffffu, ne_u4(acc, own));
   const bool changed = ((ball >> (lane & ~3u)) & 0xFu) != 0u;
   if (!live) return;
-  publish_row<HINT>(newr, bm_cur, peers, (uint32_t)row, sub, acc, changed || bm_test(bm_prev, (uint32_t)row), changed, pol);
+  publish_row(newr, bm_cur, peers, (uint32_t)row, sub, acc, changed || bm_test(bm_prev, (uint32_t)row), changed);
 }
 
 // ---- pull, long rows: one warp per <=CHUNK_EDGES work item ---------------------------------------------
-template <bool FRONTIER, bool HINT = false>
+template <bool FRONTIER>
 // 8 CTAs/SM (<= 32 registers): at full scale the gathers are DRAM-latency bound and the kernel's speed tracks the
 // number of resident warps (36 registers = 7 CTAs measured 11 % slower than 32 registers = 8 CTAs)
 __global__ void __launch_bounds__(256, 8) k_pull_warp(uint64_t n_items, uint64_t first_multi_free_item,
@@ -248,13 +251,12 @@ __global__ void __launch_bounds__(256, 8) k_pull_warp(uint64_t n_items, uint64_t
   const uint32_t e0 = rs + chunk * (uint32_t)CHUNK_EDGES;
   const uint32_t e1 = min(e0 + (uint32_t)CHUNK_EDGES, re);
   uint4 acc = make_uint4(0, 0, 0, 0);
-  const uint64_t pol = HINT ? l2_policy_evict_first() : 0ull;
   // out-of-range lanes and (FRONTIER) unchanged sources are redirected to the row itself: merging one's own row
   // is a no-op under max and hits L1, so the gather loop is branch-free
-  uint32_t nxt = (e0 + lane < e1) ? (HINT ? ld_stream_hint_u32(col + e0 + lane, pol) : ld_stream_u32(col + e0 + lane)) : row;
+  uint32_t nxt = (e0 + lane < e1) ? ld_stream_u32(col + e0 + lane) : row;
   for (uint32_t base = e0; base < e1; base += 32) {
     uint32_t mine = nxt;
-    nxt = (base + 32 + lane < e1) ? (HINT ? ld_stream_hint_u32(col + base + 32 + lane, pol) : ld_stream_u32(col + base + 32 + lane)) : row;
+    nxt = (base + 32 + lane < e1) ? ld_stream_u32(col + base + 32 + lane) : row;
     if (FRONTIER) mine = bm_test(bm_prev, mine) ? mine : row;
     const uint32_t i0 = __shfl_sync(0xffffffffu, mine, q);
     const uint32_t i1 = __shfl_sync(0xffffffffu, mine, q + 8);
@@ -277,11 +279,11 @@ __global__ void __launch_bounds__(256, 8) k_pull_warp(uint64_t n_items, uint64_t
     if (q == 0) partial[item * 4 + sub] = acc;
     return;
   }
-  const uint4 own = HINT ? ld_hint_u4(oldr + (uint64_t)row * 4 + sub, pol) : oldr[(uint64_t)row * 4 + sub];
+  const uint4 own = oldr[(uint64_t)row * 4 + sub];
   acc = vmax_u8x16(acc, own);
   const unsigned ball = __ballot_sync(0xffffffffu, ne_u4(acc, own));
   const bool changed = (ball & 0xFu) != 0u;
-  if (q == 0) publish_row<HINT>(newr, bm_cur, peers, row, sub, acc, changed || bm_test(bm_prev, row), changed, pol);
+  if (q == 0) publish_row(newr, bm_cur, peers, row, sub, acc, changed || bm_test(bm_prev, row), changed);
 }
 
 // rows spanning several work items: one warp reduces the parked partials
@@ -349,7 +351,8 @@ __global__ void k_publish_rows(const uint32_t* __restrict__ bm_prev, const uint3
   if (row >= n_rows || !owned_row(peers, (uint32_t)row)) return;
   if (!(bm_test(bm_prev, (uint32_t)row) || bm_test(bm_cur, (uint32_t)row))) return;
   const uint4 v = newr[row * 4 + (gt & 3)];
-  for (int p = 0; p < peers.n; p++) peers.newr[p][row * 4 + (gt & 3)] = v;
+  const uint32_t want = peers.sub ? __ldg(peers.sub + row) : 0xFFFFFFFFu;
+  for (int p = 0; p < peers.n; p++) if ((want >> peers.prank[p]) & 1u) peers.newr[p][row * 4 + (gt & 3)] = v;
 }
 __global__ void __launch_bounds__(256) k_push(const uint32_t* __restrict__ list, const uint32_t* __restrict__ off,
     uint32_t n_front, uint64_t n_slots, const uint32_t* __restrict__ fwd_ptr, const uint32_t* __restrict__ fwd_dst,
@@ -486,12 +489,17 @@ int hb_alloc_state(sb200_graph* g) {
   SB_TRY(g->size_cache.alloc(std::max<uint64_t>(N, 1)));
   SB_TRY(g->kahan_sum.alloc(std::max<uint64_t>(N, 1))); SB_TRY(g->kahan_err.alloc(std::max<uint64_t>(N, 1)));
   SB_TRY(g->counters.alloc(8));
+  if (g->world > 1) {   // sync page of the device-side barrier (plain cudaMalloc: exported through CUDA IPC)
+    SB_TRY(g->sync_page.alloc(SYNC_SLOTS));
+    SB_CUDA(cudaMemset(g->sync_page.p, 0, SYNC_SLOTS * sizeof(unsigned long long)));
+    g->publish_all = env_flag("SB200_PUBLISH_ALL", false);
+  }
   if (!g->h_counters) SB_CUDA(cudaMallocHost((void**)&g->h_counters, 8 * sizeof(unsigned long long)));
-  // Experiment switch (off by default): rows are ordered by in-degree, so the head of the register array holds the
-  // hubs -- on a power-law graph also the most-gathered sources.  SB200_L2_PERSIST_MB=m pins the first m MB of the
-  // array being READ as persisting L2 lines for the pull kernels (stream access-policy window, re-pointed at the
-  // `old` array every iteration), so the streaming col/row traffic cannot evict them.
-  const double mb = env_f("SB200_L2_PERSIST_MB", 0.0);
+  // Rows are ordered by in-degree, so the head of the register array holds the hubs -- on a power-law graph also the
+  // most-gathered sources.  The first SB200_L2_PERSIST_MB (default 32; 0 = off) MB of the array being READ are pinned
+  // as persisting L2 lines for the pull kernels (stream access-policy window, re-pointed at the `old` array every
+  // iteration), so the streaming col/row traffic cannot evict them.
+  const double mb = env_f("SB200_L2_PERSIST_MB", 32.0);  // measured at C2: 0 -> 57.5, 32 -> 54.1, 64 -> 56.2, 96 -> 60.0 ms/step
   g->l2_window_bytes = 0;
   if (mb > 0) {
     cudaDeviceProp prop;
@@ -525,19 +533,32 @@ int hb_reset(sb200_graph* g) {
 #define PROF_END(g, fam, bytes) do { if ((g)->profiling) { SB_CUDA(cudaEventRecord((g)->prof_ev[fam][1], (g)->stream)); \
     (g)->prof_used[fam] = true; (g)->prof_step_bytes[fam] = (double)(bytes); } } while (0)
 
+// publish targets of the iteration being launched: the peers' copies of the `new` register array / `cur` bitmap
+static PeerOut make_peer_out(const sb200_graph* g, bool with_targets) {
+  PeerOut po;
+  memset(&po, 0, sizeof(po));
+  po.world = (uint32_t)g->world; po.rank = (uint32_t)g->rank;
+  if (with_targets && g->p2p) {
+    po.n = g->n_peers;
+    po.sub = (g->publish_all || !g->sub_mask.p) ? nullptr : g->sub_mask.p;
+    for (int p = 0; p < g->n_peers; p++) {
+      po.newr[p] = (uint4*)g->peer_regs[g->cur ^ 1][p]; po.bmc[p] = (uint32_t*)g->peer_bm[g->bcur ^ 1][p];
+      po.prank[p] = (uint8_t)g->peer_rank[p];
+    }
+  }
+  return po;
+}
+
 template <bool FRONTIER>
 static int launch_pull(sb200_graph* g, const uint4* oldr, uint4* newr, const uint32_t* bmp, uint32_t* bmc) {
   cudaStream_t s = g->stream;
-  PeerOut po; po.n = 0; po.world = (uint32_t)g->world; po.rank = (uint32_t)g->rank;
-  if (g->p2p) { po.n = g->n_peers; for (int p = 0; p < g->n_peers; p++) { po.newr[p] = (uint4*)g->peer_regs[g->cur ^ 1][p]; po.bmc[p] = (uint32_t*)g->peer_bm[g->bcur ^ 1][p]; } }
+  const PeerOut po = make_peer_out(g, true);
   const int FW = FRONTIER ? sb200_graph::F_PULL_WARP_FRONT : sb200_graph::F_PULL_WARP_DENSE;
   const int FQ = FRONTIER ? sb200_graph::F_PULL_QUAD_FRONT : sb200_graph::F_PULL_QUAD_DENSE;
   const double per_edge = FRONTIER ? 4.0 : 68.0;  // col index (+ the 64-B gather when every source is read)
-  static const bool hints = getenv("SB200_L2_HINTS") != nullptr;  // experiment switch, see common.cuh
   if (g->n_items) {
     PROF_BEGIN(g, FW);
-    auto kw = hints ? k_pull_warp<FRONTIER, true> : k_pull_warp<FRONTIER, false>;
-    SB_LAUNCH(kw, div_up(g->n_items * 32, 256), 256, 0, s, g->n_items, g->n_multi_items,
+    SB_LAUNCH(k_pull_warp<FRONTIER>, div_up(g->n_items * 32, 256), 256, 0, s, g->n_items, g->n_multi_items,
               g->item_row.p, g->item_start.p, (uint32_t)g->warp_row_begin, g->row_ptr.p, g->col.p, g->col_base, oldr, newr,
               g->partial.p, bmp, bmc, po);
     SB_CHECK_LAUNCH();
@@ -553,8 +574,7 @@ static int launch_pull(sb200_graph* g, const uint4* oldr, uint4* newr, const uin
   const uint64_t nq = g->quad_row_end - g->quad_row_begin;
   if (nq) {
     PROF_BEGIN(g, FQ);
-    auto kq = hints ? k_pull_quad<FRONTIER, true> : k_pull_quad<FRONTIER, false>;
-    SB_LAUNCH(kq, div_up(nq * 4, 256), 256, 0, s, g->quad_row_begin, g->quad_row_end, g->row_ptr.p,
+    SB_LAUNCH(k_pull_quad<FRONTIER>, div_up(nq * 4, 256), 256, 0, s, g->quad_row_begin, g->quad_row_end, g->row_ptr.p,
               g->col.p, g->col_base, oldr, newr, bmp, bmc, po);
     SB_CHECK_LAUNCH();
     PROF_END(g, FQ, g->own_frac * (per_edge * (double)g->E_quad + 68.0 * (double)nq));
@@ -597,8 +617,7 @@ static int run_push(sb200_graph* g, const uint4* oldr, uint4* newr, const uint32
     PROF_END(g, sb200_graph::F_PUSH, 132.0 * (double)slots);
   }
   if (g->p2p && g->n_peers > 0) {
-    PeerOut po; po.n = g->n_peers; po.world = (uint32_t)g->world; po.rank = (uint32_t)g->rank;
-    for (int p = 0; p < g->n_peers; p++) { po.newr[p] = (uint4*)g->peer_regs[g->cur ^ 1][p]; po.bmc[p] = nullptr; }
+    const PeerOut po = make_peer_out(g, true);
     SB_LAUNCH(k_publish_rows, div_up(N * 4, 256), 256, 0, s, bmp, bmc, N, (const uint4*)newr, po);
     SB_CHECK_LAUNCH();
   }
@@ -626,11 +645,102 @@ __global__ void k_frontier_out_edges(const uint32_t* __restrict__ bm, uint64_t w
   if ((threadIdx.x & 31) == 0 && acc) atomicAdd(counter, acc);
 }
 
-int hb_step(sb200_graph* g, sb200_iter_stats* st) {
+// ---- device-side barrier + changed-count sum across the ranks of one box ------------------------------------------------
+// One warp.  Lane p stores (epoch, count) into slot [epoch & 1][my rank] of peer p's sync page (release, system scope,
+// after a system fence that orders this rank's earlier peer stores -- the rows and bitmap words of the iteration --
+// before the flag); lane r then spins (acquire) on slot [epoch & 1][r] of the LOCAL page until rank r's flag of this
+// epoch has arrived, and the warp sums the counts.  Two parities: a rank can be at most one barrier ahead of the
+// slowest one, so the slot of epoch e is rewritten (epoch e + 2) only after everybody has left barrier e + 1, i.e. has
+// long read it.  A watchdog (globaltimer) turns a missing peer into an error instead of a hung GPU.
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+#ifndef SB200_EMU
+  asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+#else
+  *(volatile unsigned long long*)p = v;
+#endif
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+#ifndef SB200_EMU
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+#else
+  return *(const volatile unsigned long long*)p;
+#endif
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+#ifndef SB200_EMU
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+#else
+  return 0ull;
+#endif
+}
+constexpr unsigned long long SYNC_COUNT_MASK = (1ull << 40) - 1;
+__global__ void __launch_bounds__(32) k_barrier_count(const SyncView sv, unsigned long long epoch, const unsigned long long* __restrict__ count_in,
+                                                      unsigned long long* out /* [0] total, [1] timed-out ranks */, unsigned long long timeout_ns) {
+  const int lane = threadIdx.x;
+  const unsigned long long e24 = epoch & 0xFFFFFFull;
+  const unsigned long long cnt = count_in ? (*count_in & SYNC_COUNT_MASK) : 0ull;
+  const unsigned long long val = (e24 << 40) | cnt;
+  const uint32_t slot = (uint32_t)(epoch & 1ull) * 64u + sv.rank;
+  __threadfence_system();
+  if (lane < sv.n) st_release_sys_u64(sv.peer[lane] + slot, val);
+  if (lane == sv.n) st_release_sys_u64(sv.local + slot, val);
+  unsigned long long got = 0;
+  bool ok = true;
+  if (lane < (int)sv.world) {
+    const unsigned long long* p = sv.local + (uint32_t)(epoch & 1ull) * 64u + lane;
+    const unsigned long long t0 = global_ns();
+    for (;;) {
+      got = ld_acquire_sys_u64(p);
+      if ((got >> 40) == e24) break;
+      if (global_ns() - t0 > timeout_ns) { ok = false; got = 0; break; }
+#ifdef SB200_EMU
+      ok = false; got = 0; break;  // the emulator runs one rank at a time: a peer's flag cannot arrive while we wait
+#endif
+    }
+  }
+  unsigned long long sum = (lane < (int)sv.world && ok) ? (got & SYNC_COUNT_MASK) : 0ull;
+  for (int o = 16; o; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+  const unsigned bad = __ballot_sync(0xffffffffu, !ok);
+  if (lane == 0) { out[0] = sum; out[1] = (unsigned long long)__popc(bad); }
+}
+
+static SyncView make_sync_view(const sb200_graph* g) {
+  SyncView sv;
+  memset(&sv, 0, sizeof(sv));
+  sv.local = g->sync_page.p; sv.n = g->n_peers; sv.world = (uint32_t)g->world; sv.rank = (uint32_t)g->rank;
+  for (int p = 0; p < g->n_peers; p++) sv.peer[p] = (unsigned long long*)g->peer_sync[p];
+  return sv;
+}
+// stand-alone barrier (before the first step of a run: every replica must be initialised before a peer may write into it)
+int hb_barrier(sb200_graph* g) {
+  cudaStream_t s = g->stream;
+  if (!g->sync_page.p || g->n_peers != g->world - 1) SB_FAIL(SB200_ESTATE, "device barrier needs the sync pages of all %d peers", g->world - 1);
+  for (int p = 0; p < g->n_peers; p++) if (!g->peer_sync[p]) SB_FAIL(SB200_ESTATE, "peer %d exported no sync page", p);
+  g->sync_epoch++;
+  SB_LAUNCH(k_barrier_count, 1, 32, 0, s, make_sync_view(g), (unsigned long long)g->sync_epoch, (const unsigned long long*)nullptr,
+            g->counters.p + 5, 20000000000ull);
+  SB_CHECK_LAUNCH();
+  SB_CUDA(cudaMemcpyAsync(g->h_counters + 5, g->counters.p + 5, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  SB_CUDA(cudaStreamSynchronize(s));
+  if (g->h_counters[6]) SB_FAIL(SB200_ESTATE, "inter-rank barrier timed out: %llu rank(s) did not arrive", (unsigned long long)g->h_counters[6]);
+  return SB200_OK;
+}
+
+// One iteration = launch (everything queued on the handle's stream, nothing waited for) + finish (wait, read the
+// counters, flip the ping-pong).  hb_step does both; the group / sharded run loops launch all ranks before they wait.
+// with_barrier: the changed counts are summed across the ranks on the device (k_barrier_count) and the step finishes
+// with the global count already applied (no sb200_hyperball_exchange_done needed).
+int hb_step_launch(sb200_graph* g, bool with_barrier) {
   cudaStream_t s = g->stream;
   const uint64_t N = g->N, words = (N + 31) / 32;
+  if (g->step_in_flight) SB_FAIL(SB200_ESTATE, "the previous step has not been finished");
   if (g->exchange_pending) SB_FAIL(SB200_ESTATE, "sb200_hyperball_exchange_done() must be called between steps of a sharded handle");
-  if (N == 0) { g->has_changes = false; if (st) memset(st, 0, sizeof(*st)); return SB200_OK; }
+  g->step_with_barrier = with_barrier; g->step_mode = 0;
+  if (N == 0) { g->step_in_flight = true; return SB200_OK; }
   const uint4* oldr = (const uint4*)g->regs[g->cur].p;
   uint4* newr = (uint4*)g->regs[g->cur ^ 1].p;
   const uint32_t* bmp = g->bm[g->bcur].p;
@@ -662,16 +772,15 @@ int hb_step(sb200_graph* g, sb200_iter_stats* st) {
     }
   } else {
     // sharded handles: the same lazy rule for the source-major CSR (of the owned rows); every rank sees the same
-    // global changed count, so all ranks switch together
-    // (checked on the CPU emulator with 2 and 3 ranks, both exchanges; the automatic switch stays opt-in --
-    // SB200_SHARDED_PUSH=1 -- until it has run on a multi-GPU box; force_mode == 2 always works)
-    static const bool auto_push = getenv("SB200_SHARDED_PUSH") != nullptr;
+    // global changed count, so all ranks switch together (SB200_SHARDED_PUSH=0 keeps them on the pull kernels)
+    static const bool auto_push = env_flag("SB200_SHARDED_PUSH", true);
     const bool tiny = (double)g->n_changed_prev * 64.0 <= (double)N;
     if (!g->has_fwd && ((auto_push && g->reuse > 0 && g->t > 0 && tiny) || force_mode == 2)) SB_TRY(build_fwd_csr(g));
     if (g->has_fwd && tiny) mode = 2;
     else mode = ((double)g->n_changed_prev >= 0.25 * (double)N) ? 0 : 1;
   }
   if (force_mode >= 0 && (force_mode < 2 || g->has_fwd)) mode = force_mode;
+  g->step_mode = mode;
   SB_CUDA(cudaEventRecord(g->ev0, s));
   // peers write their changed bits straight into this rank's bitmap, so with the fused exchange it is cleared
   // at the END of the previous step (before the inter-step barrier), never at the start of this one
@@ -689,8 +798,7 @@ int hb_step(sb200_graph* g, sb200_iter_stats* st) {
   else if (mode == 1) SB_TRY(launch_pull<true>(g, oldr, newr, bmp, bmc));
   else SB_TRY(run_push(g, oldr, newr, bmp, bmc));
   if (g->p2p && g->n_peers > 0) {
-    PeerOut po; po.n = g->n_peers; po.world = (uint32_t)g->world; po.rank = (uint32_t)g->rank;
-    for (int p = 0; p < g->n_peers; p++) { po.newr[p] = nullptr; po.bmc[p] = (uint32_t*)g->peer_bm[g->bcur ^ 1][p]; }
+    const PeerOut po = make_peer_out(g, true);
     SB_LAUNCH(k_publish_bitmap, div_up(words, 256), 256, 0, s, bmc, words, po);
     SB_CHECK_LAUNCH();
   }
@@ -704,8 +812,24 @@ int hb_step(sb200_graph* g, sb200_iter_stats* st) {
     PROF_END(g, sb200_graph::F_FINALIZE, 0.25 * (double)nrows);  // 2 bitmap bits/row; + 112 B per changed row below
   }
   if (g->p2p) SB_CUDA(cudaMemsetAsync((void*)bmp, 0, (words + 1) * 4, s));  // next step's `cur` bitmap
-  SB_CUDA(cudaMemcpyAsync(g->h_counters, g->counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  if (with_barrier) {
+    if (!g->sync_page.p || g->n_peers != g->world - 1) SB_FAIL(SB200_ESTATE, "device barrier needs the sync pages of all %d peers", g->world - 1);
+    g->sync_epoch++;
+    SB_LAUNCH(k_barrier_count, 1, 32, 0, s, make_sync_view(g), (unsigned long long)g->sync_epoch, (const unsigned long long*)g->counters.p,
+              g->counters.p + 5, 20000000000ull);
+    SB_CHECK_LAUNCH();
+  }
+  SB_CUDA(cudaMemcpyAsync(g->h_counters, g->counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   SB_CUDA(cudaEventRecord(g->ev1, s));
+  g->step_in_flight = true;
+  return SB200_OK;
+}
+
+int hb_step_finish(sb200_graph* g, sb200_iter_stats* st) {
+  cudaStream_t s = g->stream;
+  if (!g->step_in_flight) SB_FAIL(SB200_ESTATE, "no step in flight");
+  g->step_in_flight = false;
+  if (g->N == 0) { g->has_changes = false; if (st) memset(st, 0, sizeof(*st)); return SB200_OK; }
   SB_CUDA(cudaStreamSynchronize(s));
   float ms = 0; cudaEventElapsedTime(&ms, g->ev0, g->ev1);
   if (g->profiling) {
@@ -717,7 +841,7 @@ int hb_step(sb200_graph* g, sb200_iter_stats* st) {
     }
   }
   if (st) {
-    st->t = g->t; st->mode = (uint32_t)mode; st->n_changed = g->h_counters[0];
+    st->t = g->t; st->mode = (uint32_t)g->step_mode; st->n_changed = g->h_counters[0];
     st->edges_active = g->frontier_edges_prev; st->ms = ms;
   }
   g->cur ^= 1; g->bcur ^= 1; g->t += 1;
@@ -725,11 +849,20 @@ int hb_step(sb200_graph* g, sb200_iter_stats* st) {
     g->n_changed_prev = g->h_counters[0];
     g->frontier_edges_prev = g->h_counters[1];
     g->has_changes = g->h_counters[0] != 0;
+  } else if (g->step_with_barrier) {
+    if (g->h_counters[6]) SB_FAIL(SB200_ESTATE, "inter-rank barrier timed out in iteration %u: %llu rank(s) did not arrive", g->t - 1, (unsigned long long)g->h_counters[6]);
+    g->n_changed_prev = g->h_counters[5];   // the global count, summed on the device
+    g->has_changes = g->h_counters[5] != 0;
   } else {
     g->n_changed_prev = g->h_counters[0];
     g->exchange_pending = true;
   }
   return SB200_OK;
+}
+
+int hb_step(sb200_graph* g, sb200_iter_stats* st) {
+  SB_TRY(hb_step_launch(g, false));
+  return hb_step_finish(g, st);
 }
 
 int hb_result(sb200_graph* g, uint64_t* id_lo, uint64_t* id_hi, double* cent, uint64_t cap, uint64_t* len) {

@@ -239,14 +239,14 @@ class DeviceGraph:
         """Fused exchange: swap CUDA IPC handles with every other rank and let the pull kernels store produced rows
         straight into the peers' replicas over NVLink (sb200_hyperball_ipc_*)."""
         import torch.distributed as dist
-        mine = (C.c_uint8 * 256)()
+        mine = (C.c_uint8 * _lib.IPC_BLOB_BYTES)()
         check(self._L.sb200_hyperball_ipc_export(self._h, mine))
         allh = [None] * self.world_size
         dist.all_gather_object(allh, bytes(mine), group=group)
         for r, h in enumerate(allh):
             if r == self.rank:
                 continue
-            buf = (C.c_uint8 * 256).from_buffer_copy(h)
+            buf = (C.c_uint8 * _lib.IPC_BLOB_BYTES).from_buffer_copy(h)
             check(self._L.sb200_hyperball_ipc_import(self._h, buf))
         check(self._L.sb200_hyperball_p2p_enable(self._h, 1))
         dist.barrier(group=group)
@@ -283,6 +283,23 @@ class DeviceGraph:
         self.p2p = True
         return "multicast" if use_mc else "unicast"
 
+    def run_sharded(self, max_iters=0, cap=256):
+        """The whole round loop behind the ABI (sb200_hyperball_run_sharded): all ranks call it together after
+        enable_p2p(); the ranks meet in a device-side barrier that also sums the changed counts (no NCCL)."""
+        done = C.c_uint32(0)
+        arr = (IterStats * cap)()
+        check(self._L.sb200_hyperball_run_sharded(self._h, max_iters, C.byref(done), arr, cap))
+        n = min(done.value, cap)
+        return done.value, [{k: getattr(arr[i], k) for k, _ in IterStats._fields_} for i in range(n)]
+
+    def ownership(self):
+        """(owned uint8[N], subscribers uint32[N]) in ascending-id order (sb200_graph_ownership)."""
+        n = self.info()["n_nodes"]
+        o = np.zeros(n, np.uint8); m = np.zeros(n, np.uint32)
+        if n:
+            check(self._L.sb200_graph_ownership(self._h, o.ctypes.data, m.ctypes.data))
+        return o, m
+
     def exchange_done(self, global_n_changed):
         check(self._L.sb200_hyperball_exchange_done(self._h, int(global_n_changed)))
 
@@ -297,6 +314,41 @@ class DeviceGraph:
             self.close()
         except Exception:
             pass
+
+
+class DeviceGroup:
+    """n ranks of the sharded path driven by ONE process (sb200_hyperball_group_link / _group_run): the n GPUs of a
+    box, or -- `devices` repeating an index -- several ranks on one GPU (how the 1-GPU test box exercises the fused
+    exchange).  Replaces the AMPC coordinator + workers + DHT of entrypoint/ampc/harmonic_centrality/."""
+
+    def __init__(self, graph, devices, skipped_rel=SKIPPED_REL):
+        self.world = len(devices)
+        self.ranks = [DeviceGraph(graph, device=d, rank=r, world_size=self.world, skipped_rel=skipped_rel) for r, d in enumerate(devices)]
+        self._L = lib()
+        self._arr = (C.c_void_p * self.world)(*[h._h for h in self.ranks])
+        check(self._L.sb200_hyperball_group_link(self._arr, self.world))
+
+    def reset(self):
+        for h in self.ranks:
+            h.reset()
+
+    def run(self, max_iters=0, cap=256):
+        done = C.c_uint32(0)
+        arr = (IterStats * (cap * self.world))()
+        check(self._L.sb200_hyperball_group_run(self._arr, self.world, max_iters, C.byref(done), arr, cap))
+        n = min(done.value, cap)
+        return done.value, [[{k: getattr(arr[r * cap + i], k) for k, _ in IterStats._fields_} for i in range(n)] for r in range(self.world)]
+
+    def result(self):
+        """The union of the ranks' owned results in ascending id order (what HarmonicCentrality.iter() yields)."""
+        parts = [h.result() for h in self.ranks]
+        lo = np.concatenate([p[0] for p in parts]); hi = np.concatenate([p[1] for p in parts]); c = np.concatenate([p[2] for p in parts])
+        order = np.lexsort((lo, hi))
+        return lo[order], hi[order], c[order]
+
+    def close(self):
+        for h in self.ranks:
+            h.close()
 
 
 class HarmonicCentrality:
@@ -437,7 +489,10 @@ class ShardedHarmonicCentrality:
                     dg.exchange_kind = dg.enable_symmetric(group, multicast=(exchange == "multicast"))
                 elif p2p or exchange == "p2p":
                     dg.enable_p2p(group)
-            t, stats = run_sharded_loop(dg, world_size, group, max_iters)
+            if world_size > 1 and getattr(dg, "p2p", False) and exchange not in ("symm", "multicast"):
+                t, stats = dg.run_sharded(max_iters)          # round loop + device-side barrier behind the ABI
+            else:
+                t, stats = run_sharded_loop(dg, world_size, group, max_iters)
             lo, hi, c = dg.result()
             info = dg.info()
             return HarmonicCentrality(lo, hi, c, info["n_nodes"], t, stats, info)

@@ -98,6 +98,9 @@ static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 template <class T> static inline cudaError_t cudaMemcpyToSymbol(T& sym, const void* src, size_t n) { memcpy((void*)&sym, src, n); return cudaSuccess; }
 struct cudaIpcMemHandle_t { char reserved[64]; };
 static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return 1; }
+static const cudaError_t cudaErrorPeerAccessAlreadyEnabled = 704;
+static inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 1; return cudaSuccess; }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return 1; }
 static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 typedef void* cudaMemPool_t;
@@ -107,6 +110,7 @@ static inline cudaError_t cudaMemPoolTrimTo(cudaMemPool_t, size_t) { return cuda
 struct cudaDeviceProp { int persistingL2CacheMaxSize; int accessPolicyMaxWindowSize; };
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->persistingL2CacheMaxSize = 0; p->accessPolicyMaxWindowSize = 0; return cudaSuccess; }
 static inline cudaError_t cudaDeviceSetLimit(int, size_t) { return cudaSuccess; }
+static inline cudaError_t cudaCtxResetPersistingL2Cache() { return cudaSuccess; }
 struct cudaAccessPolicyWindow { void* base_ptr; size_t num_bytes; float hitRatio; cudaAccessProperty hitProp, missProp; };
 union cudaStreamAttrValue { cudaAccessPolicyWindow accessPolicyWindow; int pad[16]; };
 static inline cudaError_t cudaStreamSetAttribute(cudaStream_t, int, const cudaStreamAttrValue*) { return cudaSuccess; }

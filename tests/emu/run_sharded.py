@@ -1,8 +1,10 @@
 """Several ranks of the sharded HyperBall path inside ONE emulated process: every rank is its own handle, the register
 arrays and bitmaps are caller-owned numpy buffers handed over with sb200_hyperball_bind_state, and each rank's publish
 targets are the other ranks' buffers by address (sb200_hyperball_set_publish_targets) -- the same calls the NVSwitch
-multicast / symmetric-memory set-up makes, with unicast targets.  After every iteration all replicas must be identical
-and equal to the oracle's registers.  Started by tests/test_hyperball_emulated.py."""
+multicast / symmetric-memory set-up makes, with unicast targets.  After every iteration every replica must equal the
+oracle's registers on the rows its rank owns or reads (with the fused exchange a row is stored only into the replicas of
+its subscribers; the collective exchange replicates everything).  The second half drives the same ranks through the
+single-process group API (sb200_hyperball_group_link / _group_run).  Started by tests/test_hyperball_emulated.py."""
 import ctypes as C
 import os
 import sys
@@ -45,6 +47,11 @@ def run(world, fused, force_mode, reuse):
             check(L.sb200_hyperball_set_publish_targets(hs[r]._h, len(peers), *cols))
     for h in hs:
         h.set_policy(force_mode=force_mode)
+    own = [h.ownership() for h in hs]
+    need = [(o.astype(bool) | (((m >> r) & 1) == 1)) if fused else np.ones(len(o), bool) for r, (o, m) in enumerate(own)]
+    assert np.array_equal(np.sum([o for o, _ in own], axis=0), np.ones(len(own[0][0]), np.uint8)), "every node has exactly one owner"
+    if fused and world > 2:
+        assert any(not n_.all() for n_ in need), "the subscriber filter should leave some rows out at world > 2"
     f = hyperball_faithful(d["from_lo"], d["from_hi"], d["to_lo"], d["to_hi"], d["rel_flags"])
     modes_seen = set()
     for rep in range(2 if reuse else 1):
@@ -65,8 +72,9 @@ def run(world, fused, force_mode, reuse):
             for h in hs: h.exchange_done(total)
             ch = ref.step(); t += 1
             regs = [h.registers() for h in hs]
-            assert all(np.array_equal(regs[0], x) for x in regs[1:]), ("replicas differ", world, fused, force_mode, t)
-            assert np.array_equal(regs[0], ref.registers()), ("registers differ from the oracle", world, fused, force_mode, t)
+            want = ref.registers()
+            for r in range(world):
+                assert np.array_equal(regs[r][need[r]], want[need[r]]), ("replica differs from the oracle on a row it owns or reads", world, r, fused, force_mode, t)
             assert (total == 0) == (not ch), (t, total, ch)
             if total == 0: break
         res = [h.result() for h in hs]
@@ -78,6 +86,28 @@ def run(world, fused, force_mode, reuse):
     return modes_seen
 
 
+def run_group(world, force_mode):
+    """The round loop behind the ABI, single-process form: link + run, then the union of the owned results."""
+    from stract_b200.webgraph import DeviceGroup
+    d = synth.rmat_graph(3000, 40000, seed=7)
+    g = Webgraph.from_arrays(d["from_lo"], d["from_hi"], d["to_lo"], d["to_hi"], d["rel_flags"])
+    f = hyperball_faithful(d["from_lo"], d["from_hi"], d["to_lo"], d["to_hi"], d["rel_flags"])
+    grp = DeviceGroup(g, [0] * world)
+    for h in grp.ranks:
+        h.set_policy(force_mode=force_mode)
+    for rep in range(2):
+        if rep:
+            grp.reset()
+        t, stats = grp.run()
+        lo, hi, c = grp.result()
+        assert t == f["iters"] and np.array_equal(lo, f["ids_lo"]) and np.array_equal(hi, f["ids_hi"]) and np.array_equal(c, f["centrality"]), (world, force_mode, rep)
+    grp.close()
+    print("group world", world, "force_mode", force_mode, "ok", flush=True)
+
+
+for world in (2, 4, 8):
+    run_group(world, -1)
+run_group(3, 2)
 for world in (2, 3):
     for fused in (True, False):
         run(world, fused, -1, False)
