@@ -113,6 +113,47 @@ typedef struct {
 SB200_API int sb200_signal_topk_batch(sb200_segment* seg, const sb200_signal_batch* batch, uint32_t* docs, double* totals,
                                       uint32_t* n_out, sb200_bm25_stats* stats);
 
+/* Path B over SEVERAL text fields of one segment: the recall-stage signal set of
+ * SignalComputeOrder::compute (core/src/ranking/computer/order.rs:17-135) evaluated per candidate exactly as
+ * InitialSegmentScoreTweaker::score sums it (core/src/ranking/initial.rs:79-93):
+ *     total = sum over the ops, in the order given, of coeff * score            (f64)
+ * A field is one sb200_segment (the same tantivy segment opened per field: equal max_doc).  A query gives every field
+ * its terms as SLOTS in query order -- slot_field[q][x] = field index (0xFF pads), slot_term = the term's ordinal in that
+ * field's segment or SB200_NO_TERM when the segment does not hold it (SegmentPostings::empty(): the slot still counts in
+ * num_query_terms), slot_idf = MultiBm25Weight's idf (core/src/ranking/bm25.rs:52-92), slot_idf_f = MultiBm25FWeight's
+ * (doc_freq of the AllBody field, core/src/ranking/bm25f.rs:40-45,88-131).  Op kinds (computer/mod.rs:66-163):
+ *   SB200_OP_BM25      TextFieldData::bm25 of `field`      f32 sum over its slots of idf*((tf*(k1+1))/(tf+cache[id])), tf=0 -> 0
+ *   SB200_OP_BM25F     Bm25F: f64 sum over the fields (in field order) of TextFieldData::bm25f -- the same saturation
+ *                      with slot_idf_f and tf scaled by the field's bm25f_coefficient as f32 (bm25f.rs:167-180)
+ *   SB200_OP_COVERAGE  matching slots / num_query_terms of `field` (f64)
+ *   SB200_OP_IDF_SUM   f32 sum of slot_idf over the matching slots of `field`
+ *   SB200_OP_NUMERIC   column `col` of the signal table
+ * chain != 0 marks the members of an n-gram group in the reference's order (largest n first; 1 = first member):
+ * score *= 0.4^hits and hits += (score > 0) (NGRAM_DAMPENING, computer/order.rs:95-135).
+ * Candidates are the union of all slots' postings; top-k by (total desc, doc asc).  Limits: <= 6 fields, <= 16 slots per
+ * query, <= 32 ops.  Optic rule boosts (computer/mod.rs:471-497) are not applied. */
+#define SB200_OP_BM25 0u
+#define SB200_OP_BM25F 1u
+#define SB200_OP_COVERAGE 2u
+#define SB200_OP_IDF_SUM 3u
+#define SB200_OP_NUMERIC 4u
+typedef struct { sb200_segment* seg; const float* tf_cache256; float k1; float bm25f_coefficient; } sb200_signal_field;
+typedef struct { uint32_t kind, field, chain, col; double coeff; } sb200_signal_op;
+typedef struct {
+  uint32_t n_queries, n_slots;        /* slots per query (row width of the four arrays below) */
+  const uint8_t* slot_field;          /* [n_queries*n_slots] */
+  const uint32_t* slot_term;          /* [n_queries*n_slots] */
+  const float* slot_idf;              /* [n_queries*n_slots] */
+  const float* slot_idf_f;            /* [n_queries*n_slots] */
+  uint32_t n_fields, n_ops;
+  const sb200_signal_field* fields;   /* [n_fields], in TextFieldEnum order */
+  const sb200_signal_op* ops;         /* [n_ops], in SignalComputeOrder order */
+  const sb200_signals* signals;       /* nullable unless an op is SB200_OP_NUMERIC */
+  uint32_t k, _pad;
+} sb200_multi_signal_batch;
+SB200_API int sb200_multi_signal_topk_batch(const sb200_multi_signal_batch* batch, uint32_t* docs, double* totals, uint32_t* n_out,
+                                            sb200_bm25_stats* stats);
+
 /* Host-side writer of tantivy-format posting lists (PostingsSerializer for IndexRecordOption::WithFreqs,
  * tantivy/src/postings/serializer.rs:343-462), used to build synthetic / test segments.  Terms are given
  * CSR-style: term t owns docs[term_off[t]..term_off[t+1]) (ascending) and the matching tfs (>= 1).

@@ -636,6 +636,111 @@ ORC_API uint32_t orc_signal_topk(void* seg, const uint32_t* terms, const float* 
   return (uint32_t)v.size();
 }
 
+// Stract recall stage over SEVERAL text fields (first slice): what InitialSegmentScoreTweaker::score
+// (initial.rs:79-93) computes from SignalComputeOrder::compute (computer/order.rs:17-135) with the TextFieldData methods of
+// computer/mod.rs:66-163.  A field f holds its query terms as "slots" in query order (a term the segment does not know is
+// SegmentPostings::empty(): it still counts in num_query_terms and keeps its weights); every method re-seeks the field's
+// own cursors (posting_contains, mod.rs:61-63).
+//   bm25(f)      f32 sum over the slots of idf * ((tf*(k1+1)) / (tf + cache[fieldnorm_id])), tf = 0 -> 0        (bm25.rs:97-150)
+//   bm25f(f)     the same with idf_f (AllBody doc_freq, bm25f.rs:40-45) and tf scaled by the field's signal coefficient
+//                as f32 before the saturation (bm25f.rs:167-180)
+//   coverage(f)  (number of slots containing the doc as f64) / num_query_terms                                  (mod.rs:91-107)
+//   idf_sum(f)   f32 sum of idf over the slots containing the doc                                               (mod.rs:126-143)
+// ops are evaluated in the order given (the host mirror derives it like SignalComputeOrder::new): kind 0 bm25(field),
+// 1 Bm25F = f64 sum over the fields of bm25f, 2 coverage(field), 3 idf_sum(field), 4 numeric column.  chain != 0 marks an
+// n-gram group (largest n first): chain == 1 starts it; score *= 0.4^hits, hits += score > 0 (order.rs:95-135).
+// total = f64 sum of coefficient * score in op order.  Candidates = union of all slots' postings, ascending docs.
+ORC_API uint32_t orc_multi_signal_topk(uint32_t n_fields, void* const* segs, const float* const* caches, const float* k1s,
+                                       const float* coefs, uint32_t n_slots, const uint8_t* slot_field, const uint32_t* slot_term,
+                                       const float* slot_idf, const float* slot_idf_f, uint32_t n_ops, const uint32_t* op_kind,
+                                       const uint32_t* op_field, const uint32_t* op_chain, const uint32_t* op_col,
+                                       const double* op_coeff, const double* const* signals, uint32_t k, uint32_t* docs,
+                                       double* totals, uint64_t* scored) {
+  if (k == 0) return 0;
+  struct Field { const Segment* seg; std::vector<Postings> post; std::vector<float> idf, idf_f; const float* cache; float k1, coef; };
+  std::vector<Field> F(n_fields);
+  std::vector<Postings> cand;
+  cand.reserve(n_slots);
+  for (uint32_t f = 0; f < n_fields; f++) { F[f].seg = (const Segment*)segs[f]; F[f].cache = caches[f]; F[f].k1 = k1s[f]; F[f].coef = coefs[f]; }
+  auto open = [](Postings& p, const Segment* s, uint32_t term) {
+    if (term == 0xFFFFFFFFu || term >= s->terms.size()) {   // SegmentPostings::empty()
+      p.seg = s; p.df = 0; p.skip.reset(nullptr, 0, s->record);
+      for (int q = 0; q < BLOCK; q++) { p.docs[q] = TERMINATED; p.tfs[q] = 0; }
+      p.block_len = 0; p.loaded = true; p.cur = 0;
+    } else p.open(s, term);
+  };
+  for (uint32_t x = 0; x < n_slots; x++) {
+    Field& fd = F[slot_field[x]];
+    fd.post.emplace_back(); open(fd.post.back(), fd.seg, slot_term[x]);
+    fd.idf.push_back(slot_idf[x]); fd.idf_f.push_back(slot_idf_f[x]);
+    cand.emplace_back(); open(cand.back(), fd.seg, slot_term[x]);
+  }
+  auto contains = [](Postings& p, uint32_t d) { return p.doc() == d || (p.doc() < d && p.seek(d) == d); };
+  const double DAMP[3] = {1.0, 0.4, 0.4 * 0.4};   // NGRAM_DAMPENING.powi(hits), hits <= 2 (three n-gram sizes per field)
+  TopN<double> top(k);
+  uint64_t nscored = 0;
+  for (;;) {
+    uint32_t d = TERMINATED;
+    for (auto& c : cand) d = std::min(d, c.doc());
+    if (d == TERMINATED) break;
+    for (auto& c : cand) if (c.doc() == d) c.advance();
+    double total = 0.0;
+    int hits = 0;
+    for (uint32_t o = 0; o < n_ops; o++) {
+      double sc = 0.0;
+      const uint32_t kind = op_kind[o];
+      if (kind == 4) sc = signals[op_col[o]][d];
+      else if (kind == 1) {
+        for (auto& fd : F) {                      // text_fields.values_mut().map(bm25f).sum::<f64>()
+          if (fd.post.empty()) continue;          // a field without query terms is not in the map
+          const uint8_t id = fd.seg->fieldnorm_ids[d];
+          float b = 0.0f;
+          for (size_t i = 0; i < fd.post.size(); i++) {
+            const uint32_t tf = contains(fd.post[i], d) ? fd.post[i].term_freq() : 0u;
+            float part = 0.0f;
+            if (tf != 0) { const float t = (float)tf * fd.coef; part = fd.idf_f[i] * ((t * (fd.k1 + 1.0f)) / (t + fd.cache[id])); }
+            b += part;
+          }
+          sc += (double)b;
+        }
+      } else {
+        Field& fd = F[op_field[o]];
+        if (!fd.post.empty()) {
+          if (kind == 0) {
+            const uint8_t id = fd.seg->fieldnorm_ids[d];
+            float b = 0.0f;
+            for (size_t i = 0; i < fd.post.size(); i++) {
+              const uint32_t tf = contains(fd.post[i], d) ? fd.post[i].term_freq() : 0u;
+              b += stract_score(fd.idf[i], fd.cache, fd.k1, id, tf);
+            }
+            sc = (double)b;
+          } else if (kind == 2) {
+            double n = 0.0;
+            for (auto& p : fd.post) n += contains(p, d) ? 1.0 : 0.0;
+            sc = n / (double)fd.post.size();
+          } else if (kind == 3) {
+            float b = 0.0f;
+            for (size_t i = 0; i < fd.post.size(); i++) if (contains(fd.post[i], d)) b += fd.idf[i];
+            sc = (double)b;
+          }
+        }
+      }
+      if (op_chain[o]) {
+        if (op_chain[o] == 1) hits = 0;
+        sc *= DAMP[hits > 2 ? 2 : hits];
+        if (sc > 0.0) hits++;
+      }
+      total += op_coeff[o] * sc;
+    }
+    nscored++;
+    top.push(total, d);
+  }
+  auto v = top.into_sorted();
+  for (size_t i = 0; i < v.size(); i++) { docs[i] = v[i].doc; totals[i] = v[i].feature; }
+  if (scored) *scored = nscored;
+  return (uint32_t)v.size();
+}
+
 // batch drivers: one query per thread across all host threads (the reference runs a query on one
 // thread, tantivy/src/index/index.rs:416, and many queries concurrently)
 ORC_API void orc_bm25_topk_batch(void* seg, const uint32_t* terms /*n_q*n_terms*/, const float* weights, const float* caches,

@@ -26,6 +26,20 @@ class SignalBatch(C.Structure):
                 ("coeffs", C.c_void_p), ("max_docs", C.c_uint32), ("_pad", C.c_uint32)]
 
 
+class SignalField(C.Structure):
+    _fields_ = [("seg", C.c_void_p), ("tf_cache256", C.c_void_p), ("k1", C.c_float), ("bm25f_coefficient", C.c_float)]
+
+
+class SignalOp(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("field", C.c_uint32), ("chain", C.c_uint32), ("col", C.c_uint32), ("coeff", C.c_double)]
+
+
+class MultiSignalBatch(C.Structure):
+    _fields_ = [("n_queries", C.c_uint32), ("n_slots", C.c_uint32), ("slot_field", C.c_void_p), ("slot_term", C.c_void_p),
+                ("slot_idf", C.c_void_p), ("slot_idf_f", C.c_void_p), ("n_fields", C.c_uint32), ("n_ops", C.c_uint32),
+                ("fields", C.c_void_p), ("ops", C.c_void_p), ("signals", C.c_void_p), ("k", C.c_uint32), ("_pad", C.c_uint32)]
+
+
 def proto(L, f):
     vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
     f("sb200_segment_create", i32, vp, u64, vp, u32, vp, u32, i32, i32, C.POINTER(vp))
@@ -36,6 +50,7 @@ def proto(L, f):
     f("sb200_bm25_topk_batch", i32, vp, C.POINTER(Bm25Batch), vp, vp, vp, C.POINTER(Bm25Stats))
     f("sb200_bm25_topk", i32, vp, vp, vp, u32, vp, i32, u32, vp, vp, vp)
     f("sb200_signal_topk_batch", i32, vp, C.POINTER(SignalBatch), vp, vp, vp, C.POINTER(Bm25Stats))
+    f("sb200_multi_signal_topk_batch", i32, C.POINTER(MultiSignalBatch), vp, vp, vp, C.POINTER(Bm25Stats))
     f("sb200_postings_encode", i32, vp, vp, vp, u32, vp, u32, C.c_float, vp, u64, C.POINTER(u64), vp, i32)
     f("sb200_term_info_store_decode", i32, vp, u64, i32, vp, u64, C.POINTER(u64))
     f("sb200_postings_encode_ex", i32, vp, vp, vp, u32, vp, u32, C.c_float, i32, vp, u64, C.POINTER(u64), vp, i32)

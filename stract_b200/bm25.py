@@ -404,37 +404,143 @@ class SignalSearcher:
         return out_seg, out_doc, out_t, out_n
 
 
-def smoke():
-    """One small invocation of path 2 on cuda:0 checked against the CPU oracle (called by __graft_entry__.smoke)."""
-    import oracle  # test infrastructure; only smoke()/tests/bench may import it
-    rng = np.random.default_rng(3)
-    max_doc = 20_000
-    lens = np.maximum(1, rng.lognormal(4.0, 0.8, max_doc)).astype(np.uint32)
-    ids = fieldnorms_to_ids(lens)
-    oseg = oracle.Segment(ids)
-    td, tt = [], []
-    for df in [int(x) for x in np.geomspace(50, 8000, 24)]:
-        d = np.sort(rng.choice(max_doc, df, replace=False)).astype(np.uint32)
-        t = np.minimum(rng.geometric(0.6, df), 255).astype(np.uint32)
-        td.append(d); tt.append(t); oseg.add_term(d, t)
-    data, infos = encode_postings(td, tt, ids, oseg.avg_fieldnorm)
-    assert np.array_equal(data, oseg.postings_bytes())
-    seg = SegmentReader(data, infos, ids)
-    nq = 32
-    terms = np.stack([rng.choice(24, 2, replace=False) for _ in range(nq)]).astype(np.uint32)
-    cache = compute_tf_cache(seg.average_fieldnorm)
-    w = np.array([[Bm25Weight.for_one_term(int(seg.doc_freq[t]), max_doc, seg.average_fieldnorm).weight for t in row] for row in terms], np.float32)
-    od, os_, on, _ = oseg.topk_batch(terms, w, np.tile(cache, (nq * 2, 1)), 0, 100, threads=4)
-    gd, gs, gn = TopDocs.with_limit(100).search_batch(seg, terms, MODE_AND)
-    assert np.array_equal(gn, on)
-    for q in range(nq):
-        assert np.array_equal(gd[q, :gn[q]], od[q, :on[q]]) and np.array_equal(gs[q, :gn[q]], os_[q, :on[q]])
-    cols = [rng.random(max_doc), rng.random(max_doc) ** 4]
-    comp = SignalComputer(seg, SignalTable(cols), [2.0, 0.02], coeff_text=0.005)
-    t5 = np.stack([rng.choice(24, 5, replace=False) for _ in range(8)]).astype(np.uint32)
-    w5 = np.array([[StractBm25Weight.for_one_term(int(seg.doc_freq[t]), max_doc, seg.average_fieldnorm).weight for t in row] for row in t5], np.float32)
-    od, ot, on, _ = oseg.signal_topk_batch(t5, w5, np.tile(cache, (40, 1)), 1.2, 0.005, cols, [2.0, 0.02], 50, threads=4)
-    gd, gt, gn = comp.top_docs_batch(t5, 50)
-    assert np.array_equal(gd, od) and np.array_equal(gt, ot) and np.array_equal(gn, on)
-    seg.close()
-    print(f"smoke path2 ok: {nq} AND queries + 8 signal queries bit-exact against the oracle")
+# ---- multi-field recall-stage signals ------------------------------------------------------------
+OP_BM25, OP_BM25F, OP_COVERAGE, OP_IDF_SUM, OP_NUMERIC = 0, 1, 2, 3, 4
+
+# The text signals of CoreSignalEnum in declaration order (core/src/ranking/signals/mod.rs:182-206) with what
+# SignalComputeOrder::new and prepare_textfields need to know about each: the op kind, its text field (as_field), whether it
+# has sibling n-gram signals, and the default coefficient (core/src/ranking/signals/core/text.rs).
+CORE_SIGNALS = [
+    # name,                                  kind,        field,                              sibling n-grams, default coefficient
+    ("Bm25F",                                OP_BM25F,    None,                               False, 0.1),
+    ("Bm25Title",                            OP_BM25,     "Title",                            True,  0.0063),
+    ("TitleCoverage",                        OP_COVERAGE, "Title",                            False, 0.01),
+    ("Bm25TitleBigrams",                     OP_BM25,     "TitleBigrams",                     True,  0.005),
+    ("Bm25TitleTrigrams",                    OP_BM25,     "TitleTrigrams",                    True,  0.005),
+    ("Bm25CleanBody",                        OP_BM25,     "CleanBody",                        True,  0.005),
+    ("CleanBodyCoverage",                    OP_COVERAGE, "CleanBody",                        False, 0.01),
+    ("Bm25CleanBodyBigrams",                 OP_BM25,     "CleanBodyBigrams",                 True,  0.005),
+    ("Bm25CleanBodyTrigrams",                OP_BM25,     "CleanBodyTrigrams",                True,  0.005),
+    ("Bm25StemmedTitle",                     OP_BM25,     "StemmedTitle",                     False, 0.003),
+    ("Bm25StemmedCleanBody",                 OP_BM25,     "StemmedCleanBody",                 False, 0.001),
+    ("Bm25AllBody",                          OP_BM25,     "AllBody",                          False, 0.0),
+    ("Bm25Keywords",                         OP_BM25,     "Keywords",                         False, 0.001),
+    ("Bm25BacklinkText",                     OP_BM25,     "BacklinkText",                     False, 0.003),
+    ("IdfSumUrl",                            OP_IDF_SUM,  "Url",                              False, 0.0006),
+    ("IdfSumSite",                           OP_IDF_SUM,  "SiteWithout",                      False, 0.00015),
+    ("IdfSumDomain",                         OP_IDF_SUM,  "Domain",                           False, 0.0003),
+    ("IdfSumSiteNoTokenizer",                OP_IDF_SUM,  "SiteNoTokenizer",                  False, 0.00015),
+    ("IdfSumDomainNoTokenizer",              OP_IDF_SUM,  "DomainNoTokenizer",                False, 0.0036),
+    ("IdfSumDomainNameNoTokenizer",          OP_IDF_SUM,  "DomainNameNoTokenizer",            False, 0.0002),
+    ("IdfSumDomainIfHomepage",               OP_IDF_SUM,  "DomainIfHomepage",                 False, 0.0004),
+    ("IdfSumDomainNameIfHomepageNoTokenizer", OP_IDF_SUM, "DomainNameIfHomepageNoTokenizer",  False, 0.0036),
+    ("IdfSumDomainIfHomepageNoTokenizer",    OP_IDF_SUM,  "DomainIfHomepageNoTokenizer",      False, 0.0036),
+    ("IdfSumTitleIfHomepage",                OP_IDF_SUM,  "TitleIfHomepage",                  False, 0.001),
+]
+# n-gram size and monogram field of the n-gram text fields (core/src/schema/text_field.rs:1267-1403)
+NGRAM_FIELDS = {"TitleBigrams": (2, "Title"), "TitleTrigrams": (3, "Title"), "CleanBodyBigrams": (2, "CleanBody"), "CleanBodyTrigrams": (3, "CleanBody")}
+# TextFieldEnum declaration order (text_field.rs:161-199), the iteration order of every EnumMap<TextFieldEnum, _>
+TEXT_FIELD_ORDER = ["Title", "CleanBody", "StemmedTitle", "StemmedCleanBody", "AllBody", "Url", "UrlNoTokenizer", "UrlForSiteOperator",
+                    "SiteWithout", "Domain", "SiteNoTokenizer", "DomainNoTokenizer", "DomainNameNoTokenizer", "SiteIfHomepageNoTokenizer",
+                    "DomainIfHomepage", "DomainNameIfHomepageNoTokenizer", "DomainIfHomepageNoTokenizer", "TitleIfHomepage", "BacklinkText",
+                    "Description", "DmozDescription", "SchemaOrgJson", "FlattenedSchemaOrgJson", "CleanBodyBigrams", "TitleBigrams",
+                    "CleanBodyTrigrams", "TitleTrigrams", "MicroformatTags", "SafetyClassification", "InsertionTimestamp",
+                    "RecipeFirstIngredientTagId", "Keywords"]
+
+
+class SignalComputeOrder:
+    """`SignalComputeOrder::new` (core/src/ranking/computer/order.rs:33-62): text signals with sibling n-gram signals are
+    grouped per monogram field in an EnumMap (iterated in TextFieldEnum order), each group ordered by descending n-gram
+    size (NGramComputeOrder::push re-sorts on every insert); every other signal follows in CoreSignalEnum order.
+    `enabled` restricts the list to the signals the caller has fields for; numeric signals (which sit behind the text
+    signals in CoreSignalEnum) are appended through `numeric` = [(name, column, coefficient)] in the order given."""
+
+    def __init__(self, enabled, numeric=()):
+        groups, others = {}, []
+        for name, kind, field, sibling, coef in CORE_SIGNALS:
+            if name not in enabled:
+                continue
+            if sibling:
+                ngram, mono = NGRAM_FIELDS.get(field, (1, field))
+                groups.setdefault(mono, []).append((ngram, name, kind, field, coef))
+                groups[mono].sort(key=lambda e: -e[0])   # sort_unstable_by(b.cmp(a)) on distinct sizes
+            else:
+                others.append((name, kind, field, coef))
+        self.entries = []   # (name, kind, field, chain, col, default coefficient)
+        for mono in sorted(groups, key=TEXT_FIELD_ORDER.index):
+            for i, (_n, name, kind, field, coef) in enumerate(groups[mono]):
+                self.entries.append((name, kind, field, 1 if i == 0 else 2, 0, coef))
+        for name, kind, field, coef in others:
+            self.entries.append((name, kind, field, 0, 0, coef))
+        for name, col, coef in numeric:
+            self.entries.append((name, OP_NUMERIC, None, 0, int(col), coef))
+
+
+class MultiFieldSignalComputer:
+    """The recall-stage SignalComputer over several text fields of one segment (core/src/ranking/computer/mod.rs:300-389,
+    order.rs): `fields` = {TextField name: SegmentReader} in TextFieldEnum order, every reader opened over the same docs.
+    `coefficients` overrides the default coefficient per signal name (SignalComputer::coefficient)."""
+
+    def __init__(self, fields, enabled, signals=None, numeric=(), coefficients=None, k1=K1, b=B_):
+        self.names = sorted(fields.keys(), key=TEXT_FIELD_ORDER.index)   # EnumMap<TextFieldEnum, TextFieldData> order
+        self.readers = [fields[n] for n in self.names]
+        self.signals = signals
+        self.order = SignalComputeOrder(set(enabled), numeric)
+        self.coefficients = dict(coefficients or {})
+        self.k1, self.b = np.float32(k1), np.float32(b)
+        self._L = lib()
+
+    def coefficient(self, name, default):
+        return float(self.coefficients.get(name, default))
+
+    def field_coefficient(self, field):
+        """TextFieldData.signal_coefficient (mod.rs:372): prepare_textfields walks CoreSignalEnum::all() and INSERTS the
+        field's data once per signal that names it, so the entry that survives carries the coefficient of the LAST such
+        signal (Title ends up with TitleCoverage's, CleanBody with CleanBodyCoverage's)."""
+        c = 0.0
+        for name, _kind, f, _sib, coef in CORE_SIGNALS:
+            if f == field:
+                c = self.coefficient(name, coef)
+        return c
+
+    def top_docs_batch(self, slot_field, slot_term, k, doc_freq_all_body=None, return_stats=False):
+        """slot_field / slot_term [n_queries, n_slots]: field index into `self.names` (TextFieldEnum order; 0xFF pads) and the term's ordinal in that
+        field's reader (NO_TERM = the segment does not hold it).  idf comes from the field's own doc_freq
+        (MultiBm25Weight::for_terms), the Bm25F idf from `doc_freq_all_body` [n_queries, n_slots] (WeightCache: the AllBody
+        doc_freq of the token), defaulting to the field's own."""
+        sf = np.ascontiguousarray(slot_field, np.uint8); st = np.ascontiguousarray(slot_term, np.uint32)
+        nq, ns = sf.shape
+        idf1 = np.zeros((nq, ns), np.float32); idf2 = np.zeros((nq, ns), np.float32)
+        for q in range(nq):
+            for x in range(ns):
+                f = int(sf[q, x])
+                if f == 0xFF:
+                    continue
+                r = self.readers[f]
+                df = int(r.doc_freq[st[q, x]]) if st[q, x] != NO_TERM and st[q, x] < r.n_terms else 0
+                idf1[q, x] = idf(df, r.max_doc)
+                dfa = df if doc_freq_all_body is None else int(doc_freq_all_body[q][x])
+                idf2[q, x] = idf(dfa, r.max_doc)
+        caches = [np.ascontiguousarray(compute_tf_cache(r.average_fieldnorm, self.k1, self.b)) for r in self.readers]
+        farr = (B.SignalField * len(self.readers))()
+        for i, (n_, r) in enumerate(zip(self.names, self.readers)):
+            farr[i].seg = r._h; farr[i].tf_cache256 = caches[i].ctypes.data
+            farr[i].k1 = float(self.k1); farr[i].bm25f_coefficient = float(np.float32(self.field_coefficient(n_)))
+        ops = (B.SignalOp * len(self.order.entries))()
+        for i, (name, kind, field, chain, col, coef) in enumerate(self.order.entries):
+            ops[i].kind = kind; ops[i].field = self.names.index(field) if field is not None else 0
+            ops[i].chain = chain; ops[i].col = col; ops[i].coeff = self.coefficient(name, coef)
+        docs = host_out((nq, k), np.uint32); totals = host_out((nq, k), np.float64); n_out = np.zeros(nq, np.uint32)
+        mb = B.MultiSignalBatch()
+        mb.n_queries, mb.n_slots = nq, ns
+        mb.slot_field, mb.slot_term, mb.slot_idf, mb.slot_idf_f = _p(sf), _p(st), _p(idf1), _p(idf2)
+        mb.n_fields, mb.n_ops = len(self.readers), len(self.order.entries)
+        mb.fields = C.cast(farr, C.c_void_p); mb.ops = C.cast(ops, C.c_void_p)
+        mb.signals = self.signals._h if self.signals is not None else None
+        mb.k = k
+        stt = B.Bm25Stats()
+        check(self._L.sb200_multi_signal_topk_batch(C.byref(mb), _p(docs), _p(totals), _p(n_out), C.byref(stt)))
+        self.last_inputs = dict(idf=idf1, idf_f=idf2, caches=caches)
+        if return_stats:
+            return docs, totals, n_out, {k_: getattr(stt, k_) for k_, _ in B.Bm25Stats._fields_ if not k_.startswith("_")}
+        return docs, totals, n_out

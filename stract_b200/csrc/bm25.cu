@@ -70,6 +70,9 @@ struct sb200_segment {
   sb200::DevBuf<uint4> a3_units;            // AUnit records
   sb200::DevBuf<uint64_t> a3_off;           // per query slot: start of its candidate list
   sb200::DevBuf<uint32_t> a3_cnt, a3_key, a3_doc;
+  // scratch of the multi-field signal path (bm25_multi.cuh); lives in the FIRST field's handle
+  sb200::DevBuf<uint8_t> m_fields, m_ops, m_slot_field;
+  sb200::DevBuf<float> m_idf_f;
 };
 
 namespace sb200 {
@@ -602,7 +605,184 @@ static int launch_topk_warp(const WParams& P, cudaStream_t s) {
 }  // namespace sb200
 #include "bm25_and3.cuh"
 #include "bm25_or3.cuh"
+#include "bm25_multi.cuh"
 namespace sb200 {
+
+static void seg_view(const sb200_segment* g, SegView& S) {
+  S.p32 = (const uint32_t*)g->postings.p; S.postings_len = g->postings_len; S.fieldnorm = g->fieldnorm.p; S.max_doc = g->max_doc;
+  S.t_data_off = g->t_data_off.p; S.t_end_off = g->t_end_off.p; S.t_df = g->t_df.p; S.t_first = g->t_first.p;
+  S.b_last = g->b_last.p; S.b_off = g->b_off.p; S.b_bits = g->b_bits.p; S.record = g->record;
+}
+
+// Work items of a batch whose query slots are ordered by decreasing work: a query much larger than the average is cut
+// into <= 16 doc ranges (W*k <= 16384 for the merge); their partial top-k lists are merged by k_merge_topk.
+struct ItemPlan {
+  std::vector<uint32_t> q, lo, hi, out;
+  std::vector<MergeJob> jobs;
+  uint32_t extra = 0, capm = 0;
+};
+static void plan_items(const std::vector<uint64_t>& work, const std::vector<uint32_t>& order, uint32_t k, uint32_t max_doc, bool can_split, ItemPlan& pl) {
+  const uint32_t nq = (uint32_t)work.size();
+  uint64_t total = 0;
+  for (uint64_t w : work) total += w;
+  const uint64_t target = std::max<uint64_t>(32768, total / std::max<uint32_t>(nq, 1));
+  const uint32_t wmax = std::max<uint32_t>(1, std::min<uint32_t>(16, 16384 / k));
+  for (uint32_t slot = 0; slot < nq; slot++) {
+    uint32_t W = can_split ? (uint32_t)std::min<uint64_t>(wmax, (work[slot] + target - 1) / target) : 1;
+    if (W < 1) W = 1;
+    if (W == 1) { pl.q.push_back(slot); pl.lo.push_back(0); pl.hi.push_back(0xFFFFFFFFu); pl.out.push_back(order[slot]); continue; }
+    MergeJob j; j.first_slot = nq + pl.extra; j.n_slots = W; j.out_slot = order[slot]; j._pad = 0;
+    pl.jobs.push_back(j);
+    for (uint32_t c = 0; c < W; c++) {
+      pl.q.push_back(slot);
+      pl.lo.push_back((uint32_t)((uint64_t)max_doc * c / W));
+      pl.hi.push_back(c + 1 == W ? 0xFFFFFFFFu : (uint32_t)((uint64_t)max_doc * (c + 1) / W));
+      pl.out.push_back(nq + pl.extra + c);
+    }
+    pl.extra += W;
+  }
+  if (!pl.jobs.empty()) { pl.capm = 1024; while (pl.capm < wmax * k) pl.capm <<= 1; }
+}
+
+template <int TMAX>
+static int launch_multi(const MParams& P, cudaStream_t s) {
+  const size_t sm = m_cta_smem<TMAX>();
+  static bool configured = false;
+  if (!configured) { SB_CUDA(cudaFuncSetAttribute(k_sig_multi<TMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); configured = true; }
+  SB_LAUNCH(k_sig_multi<TMAX>, div_up(P.n_items, WQ), WQ * 32, sm, s, P);
+  SB_CHECK_LAUNCH();
+  return SB200_OK;
+}
+
+static int run_multi(const sb200_multi_signal_batch* b, uint32_t* docs, double* totals, uint32_t* n_out, sb200_bm25_stats* stats) {
+  if (!b || !b->fields || !b->ops || !b->slot_field || !b->slot_term || !b->slot_idf || !b->slot_idf_f || !docs || !totals || !n_out)
+    SB_FAIL(SB200_EINVAL, "NULL argument");
+  const uint32_t nq = b->n_queries, SM = b->n_slots, k = b->k, NF = b->n_fields, NO = b->n_ops;
+  if (NF == 0 || NF > (uint32_t)M_MAX_FIELDS) SB_FAIL(SB200_ERANGE, "n_fields %u outside [1,%d]", NF, M_MAX_FIELDS);
+  if (NO == 0 || NO > (uint32_t)M_MAX_OPS) SB_FAIL(SB200_ERANGE, "n_ops %u outside [1,%d]", NO, M_MAX_OPS);
+  if (SM == 0 || SM > 16) SB_FAIL(SB200_ERANGE, "n_slots %u outside [1,16]", SM);
+  if (k == 0 || k > SB200_MAX_K) SB_FAIL(SB200_ERANGE, "k %u outside [1,%d]", k, SB200_MAX_K);
+  sb200_segment* g = b->fields[0].seg;
+  if (!g) SB_FAIL(SB200_EINVAL, "field 0 has no segment");
+  SB_CUDA(cudaSetDevice(g->device));
+  cudaStream_t s = g->stream;
+  for (uint32_t f = 0; f < NF; f++) {
+    const sb200_segment* x = b->fields[f].seg;
+    if (!x || !b->fields[f].tf_cache256) SB_FAIL(SB200_EINVAL, "field %u: NULL segment or cache", f);
+    if (x->device != g->device || x->max_doc != g->max_doc) SB_FAIL(SB200_EINVAL, "field %u is not a field of the same segment (device / max_doc differ)", f);
+  }
+  uint32_t n_cols = 0;
+  for (uint32_t o = 0; o < NO; o++) {
+    const sb200_signal_op& op = b->ops[o];
+    if (op.kind > 4u) SB_FAIL(SB200_EINVAL, "op %u: kind %u", o, op.kind);
+    if (op.kind != 4u && op.kind != 1u && op.field >= NF) SB_FAIL(SB200_EINVAL, "op %u: field %u >= %u", o, op.field, NF);
+    if (op.kind == 4u) {
+      if (!b->signals || op.col >= b->signals->n_cols) SB_FAIL(SB200_EINVAL, "op %u: numeric column %u not in the signal table", o, op.col);
+      n_cols = b->signals->n_cols;
+    }
+  }
+  if (n_cols && b->signals->max_doc < g->max_doc) SB_FAIL(SB200_EINVAL, "signal table covers %u docs, segment has %u", b->signals->max_doc, g->max_doc);
+  if (nq == 0) return SB200_OK;
+  // planning: slots keep their query order (the f32 sums depend on it); padding slots (field 0xFF) are dropped
+  std::vector<uint8_t> sf((size_t)nq * SM, 0);
+  std::vector<uint32_t> st((size_t)nq * SM, SB200_NO_TERM), ns(nq, 0), order(nq);
+  std::vector<float> w1((size_t)nq * SM, 0.f), w2((size_t)nq * SM, 0.f);
+  std::vector<uint64_t> work(nq, 0), work_sorted(nq, 0);
+  unsigned long long postings = 0;
+  for (uint32_t q = 0; q < nq; q++) {
+    order[q] = q;
+    for (uint32_t x = 0; x < SM; x++) {
+      const uint8_t f = b->slot_field[(size_t)q * SM + x];
+      if (f == 0xFF) continue;
+      if (f >= NF) SB_FAIL(SB200_EINVAL, "query %u slot %u: field %u >= %u", q, x, (unsigned)f, NF);
+      const uint32_t ord = b->slot_term[(size_t)q * SM + x];
+      if (ord != SB200_NO_TERM && ord < b->fields[f].seg->n_terms) work[q] += b->fields[f].seg->h_df[ord];
+    }
+    postings += work[q];
+  }
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) { return work[a] > work[c]; });
+  for (uint32_t slot = 0; slot < nq; slot++) {
+    const uint32_t q = order[slot];
+    uint32_t c = 0;
+    for (uint32_t x = 0; x < SM; x++) {
+      const uint8_t f = b->slot_field[(size_t)q * SM + x];
+      if (f == 0xFF) continue;
+      const size_t o = (size_t)slot * SM + c;
+      sf[o] = f; st[o] = b->slot_term[(size_t)q * SM + x]; w1[o] = b->slot_idf[(size_t)q * SM + x]; w2[o] = b->slot_idf_f[(size_t)q * SM + x];
+      c++;
+    }
+    ns[slot] = c; work_sorted[slot] = work[q];
+  }
+  ItemPlan pl;
+  plan_items(work_sorted, order, k, g->max_doc, getenv("SB200_BM25_NOSPLIT") == nullptr, pl);
+  const uint32_t n_items = (uint32_t)pl.q.size();
+  const size_t n_slots_out = (size_t)nq + pl.extra;
+  uint32_t cap = 1024; while (cap < k + SM * 128u) cap <<= 1;
+  // device copies
+  std::vector<MField> hf(NF);
+  for (uint32_t f = 0; f < NF; f++) {
+    memset(&hf[f], 0, sizeof(MField));
+    const sb200_segment* x = b->fields[f].seg;
+    seg_view(x, hf[f].S); hf[f].a128 = x->a_post.p; hf[f].t_aoff = x->t_aoff.p;
+    memcpy(hf[f].cache, b->fields[f].tf_cache256, 256 * 4);
+    hf[f].k1p1 = b->fields[f].k1 + 1.0f; hf[f].coef = b->fields[f].bm25f_coefficient; hf[f].n_terms = x->n_terms;
+  }
+  std::vector<MOp> ho(NO);
+  for (uint32_t o = 0; o < NO; o++) { ho[o].kind = b->ops[o].kind; ho[o].field = b->ops[o].field; ho[o].chain = b->ops[o].chain; ho[o].col = b->ops[o].col; ho[o].coeff = b->ops[o].coeff; }
+  SB_TRY(ensure(g->m_fields, NF * sizeof(MField))); SB_TRY(ensure(g->m_ops, NO * sizeof(MOp))); SB_TRY(ensure(g->m_slot_field, (size_t)nq * SM));
+  SB_TRY(ensure(g->q_terms, (size_t)nq * SM)); SB_TRY(ensure(g->q_weights, (size_t)nq * SM)); SB_TRY(ensure(g->m_idf_f, (size_t)nq * SM));
+  SB_TRY(ensure(g->q_nterms, nq)); SB_TRY(ensure(g->q_orig, nq)); SB_TRY(ensure(g->o_docs, n_slots_out * k)); SB_TRY(ensure(g->o_n, n_slots_out));
+  SB_TRY(ensure(g->o_totals, n_slots_out * k)); SB_TRY(ensure(g->counters, 4));
+  SB_TRY(ensure(g->q_items, (size_t)4 * n_items)); SB_TRY(ensure(g->q_jobs, pl.jobs.size() + 1));
+  SB_TRY(ensure(g->g_khi, (size_t)n_items * cap)); SB_TRY(ensure(g->g_klo, (size_t)n_items * cap));
+  SB_CUDA(cudaEventRecord(g->ev0, s));
+  SB_CUDA(cudaMemcpyAsync(g->m_fields.p, hf.data(), NF * sizeof(MField), cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(g->m_ops.p, ho.data(), NO * sizeof(MOp), cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(g->m_slot_field.p, sf.data(), sf.size(), cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(g->q_terms.p, st.data(), st.size() * 4, cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(g->q_weights.p, w1.data(), w1.size() * 4, cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(g->m_idf_f.p, w2.data(), w2.size() * 4, cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(g->q_nterms.p, ns.data(), ns.size() * 4, cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(g->q_orig.p, order.data(), (size_t)nq * 4, cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(g->q_items.p, pl.q.data(), (size_t)n_items * 4, cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(g->q_items.p + n_items, pl.lo.data(), (size_t)n_items * 4, cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(g->q_items.p + 2 * (size_t)n_items, pl.hi.data(), (size_t)n_items * 4, cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(g->q_items.p + 3 * (size_t)n_items, pl.out.data(), (size_t)n_items * 4, cudaMemcpyHostToDevice, s));
+  if (!pl.jobs.empty()) SB_CUDA(cudaMemcpyAsync(g->q_jobs.p, pl.jobs.data(), pl.jobs.size() * sizeof(MergeJob), cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemsetAsync(g->counters.p, 0, 4 * sizeof(unsigned long long), s));
+  MParams P;
+  memset(&P, 0, sizeof(P));
+  P.fields = (const MField*)g->m_fields.p; P.n_fields = NF; P.max_doc = g->max_doc;
+  P.ops = (const MOp*)g->m_ops.p; P.n_ops = NO;
+  P.q_slot_field = g->m_slot_field.p; P.q_slot_term = g->q_terms.p; P.q_idf = g->q_weights.p; P.q_idf_f = g->m_idf_f.p; P.q_nslots = g->q_nterms.p;
+  P.q_orig = g->q_orig.p; P.n_queries = nq; P.n_slots_max = SM; P.k = k; P.cap = cap;
+  P.n_items = n_items; P.item_q = g->q_items.p; P.item_lo = g->q_items.p + n_items; P.item_hi = g->q_items.p + 2 * (size_t)n_items; P.item_out = g->q_items.p + 3 * (size_t)n_items;
+  if (n_cols) { P.sig = b->signals->rows.p; P.n_cols = n_cols; }
+  P.g_khi = g->g_khi.p; P.g_klo = g->g_klo.p; P.o_docs = g->o_docs.p; P.o_totals = g->o_totals.p; P.o_n = g->o_n.p; P.counters = g->counters.p;
+  SB_CUDA(cudaEventRecord(g->evk0, s));
+  if (SM <= 8) SB_TRY(launch_multi<8>(P, s)); else SB_TRY(launch_multi<16>(P, s));
+  if (!pl.jobs.empty()) {
+    const size_t msm = (size_t)pl.capm * 12;
+    static size_t mconf = 0;
+    if (msm > 48 * 1024 && mconf < msm) { SB_CUDA(cudaFuncSetAttribute(k_merge_topk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm)); mconf = msm; }
+    SB_LAUNCH(k_merge_topk<2>, (unsigned)pl.jobs.size(), 256, msm, s, g->q_jobs.p, k, pl.capm, P.o_docs, (float*)nullptr, P.o_totals, P.o_n);
+    SB_CHECK_LAUNCH();
+  }
+  SB_CUDA(cudaEventRecord(g->evk1, s));
+  SB_CUDA(cudaMemcpyAsync(docs, g->o_docs.p, (size_t)nq * k * 4, cudaMemcpyDefault, s));
+  SB_CUDA(cudaMemcpyAsync(totals, g->o_totals.p, (size_t)nq * k * 8, cudaMemcpyDefault, s));
+  SB_CUDA(cudaMemcpyAsync(n_out, g->o_n.p, (size_t)nq * 4, cudaMemcpyDefault, s));
+  unsigned long long h[4] = {0, 0, 0, 0};
+  SB_CUDA(cudaMemcpyAsync(h, g->counters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  SB_CUDA(cudaEventRecord(g->ev1, s));
+  SB_CUDA(cudaStreamSynchronize(s));
+  if (h[2]) SB_FAIL(SB200_EFORMAT, "%llu queries hit the decode watchdog (inconsistent posting data)", h[2]);
+  if (stats) {
+    float ms = 0; cudaEventElapsedTime(&ms, g->ev0, g->ev1);
+    stats->postings_scored = postings; stats->docs_scored = h[0]; stats->blocks_decoded = h[1]; stats->ms = ms; cudaEventElapsedTime(&stats->kernel_ms, g->evk0, g->evk1);
+  }
+  return SB200_OK;
+}
 
 // union modes through k_or3, instantiated for the smallest term-count bound that covers the batch
 template <int MODE>
@@ -1081,6 +1261,10 @@ int sb200_bm25_topk(sb200_segment* seg, const uint32_t* term_ords, const float* 
   return sb200_bm25_topk_batch(seg, &b, docs, scores, n_out, nullptr);
 }
 
+int sb200_multi_signal_topk_batch(const sb200_multi_signal_batch* batch, uint32_t* docs, double* totals, uint32_t* n_out,
+                                  sb200_bm25_stats* stats) {
+  return run_multi(batch, docs, totals, n_out, stats);
+}
 int sb200_signal_topk_batch(sb200_segment* seg, const sb200_signal_batch* batch, uint32_t* docs, double* totals, uint32_t* n_out,
                             sb200_bm25_stats* stats) {
   if (!seg) SB_FAIL(SB200_EINVAL, "NULL segment handle");

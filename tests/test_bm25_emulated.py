@@ -98,3 +98,9 @@ def test_union_kernel_matches_default_kernel(emulated, monkeypatch):
     T.test_or_queries_bit_exact_up_to_two_terms()
     T.test_or_three_plus_terms_canonical_order()
     T.test_signal_combine_bit_exact()
+
+
+def test_multi_field_signals_against_oracle(emulated):
+    import test_multi_signal_gpu as M
+    M.test_multi_field_signals_bit_exact()
+    M.test_signal_compute_order_mirror()

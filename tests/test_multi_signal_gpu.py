@@ -1,0 +1,95 @@
+"""Multi-field recall-stage signals through the C ABI against the CPU oracle: BM25 per field, Bm25F over
+the fields, coverage, idf_sum, numeric columns, n-gram dampening chains, in SignalComputeOrder order; f64 totals and doc
+order bit-exact.  Also the host-side order / coefficient quirks of the reference (computer/order.rs, mod.rs:300-389)."""
+import numpy as np
+import pytest
+
+import oracle
+from stract_b200 import bm25
+from stract_b200.bm25 import NO_TERM, MultiFieldSignalComputer, SignalComputeOrder, SignalTable
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ["Title", "CleanBody", "Url", "TitleBigrams", "TitleTrigrams"]
+ENABLED = {"Bm25F", "Bm25Title", "TitleCoverage", "Bm25TitleBigrams", "Bm25TitleTrigrams", "Bm25CleanBody", "CleanBodyCoverage", "IdfSumUrl"}
+
+
+def _field_index(seed, max_doc, dfs, mean_len):
+    import test_bm25_gpu as T
+    rng = np.random.default_rng(seed)
+    lens = np.maximum(1, rng.lognormal(mean_len, 0.7, max_doc)).astype(np.uint32)
+    td, tt = [], []
+    for df in dfs:
+        td.append(np.sort(rng.choice(max_doc, df, replace=False)).astype(np.uint32))
+        tt.append(np.minimum(rng.geometric(0.6, df), 255).astype(np.uint32))
+    return T.build(td, tt, lens)
+
+
+def make_segment(seed=5, max_doc=30_000):
+    dfs = {"Title": [40, 300, 129, 2500, 7], "CleanBody": [900, 6000, 128, 15000, 3000, 1], "Url": [20, 500, 4000],
+           "TitleBigrams": [30, 260, 1000], "TitleTrigrams": [12, 200]}
+    mean = {"Title": 2.0, "CleanBody": 5.0, "Url": 1.5, "TitleBigrams": 1.8, "TitleTrigrams": 1.6}
+    pairs = {f: _field_index(seed + i, max_doc, dfs[f], mean[f]) for i, f in enumerate(FIELDS)}
+    return pairs, dfs
+
+
+def random_queries(rng, dfs, names, nq, ns):
+    """Slots in the order prepare_textfields builds them per field; unknown terms mixed in, padding behind."""
+    sf = np.full((nq, ns), 0xFF, np.uint8); st = np.full((nq, ns), NO_TERM, np.uint32)
+    for q in range(nq):
+        x = 0
+        for fi, name in enumerate(names):
+            n_terms = int(rng.integers(0, 4))
+            for _ in range(n_terms):
+                if x >= ns:
+                    break
+                sf[q, x] = fi
+                st[q, x] = NO_TERM if rng.random() < 0.15 else int(rng.integers(0, len(dfs[name])))
+                x += 1
+    return sf, st
+
+
+def check_against_oracle(comp, pairs, cols, sf, st, k, numeric):
+    docs, totals, n_out = comp.top_docs_batch(sf, st, k)
+    names = comp.names
+    osegs = [pairs[n][0] for n in names]
+    caches = comp.last_inputs["caches"]
+    coefs = [np.float32(comp.field_coefficient(n)) for n in names]
+    ops = [(kind, names.index(field) if field is not None else 0, chain, col, comp.coefficient(name, coef))
+           for name, kind, field, chain, col, coef in comp.order.entries]
+    for q in range(sf.shape[0]):
+        od, ot = oracle.multi_signal_topk(osegs, caches, [1.2] * len(names), coefs, sf[q], st[q], comp.last_inputs["idf"][q],
+                                          comp.last_inputs["idf_f"][q], ops, cols, k)
+        n = int(n_out[q])
+        assert n == len(od), (q, n, len(od))
+        assert np.array_equal(docs[q, :n], od), (q, docs[q, :8], od[:8])
+        assert np.array_equal(totals[q, :n], ot), (q, totals[q, :4], ot[:4])
+
+
+def test_multi_field_signals_bit_exact():
+    pairs, dfs = make_segment()
+    max_doc = 30_000
+    rng = np.random.default_rng(11)
+    cols = [rng.random(max_doc) ** 6, 1.0 / (1.0 + rng.integers(0, 1000, max_doc).astype(np.float64))]
+    numeric = [("HostCentrality", 0, 2.5), ("FetchTimeMs", 1, 0.001)]
+    comp = MultiFieldSignalComputer({n: pairs[n][1] for n in FIELDS}, ENABLED, SignalTable(cols), numeric,
+                                    coefficients={"Bm25Title": 0.02, "Bm25F": 0.3})
+    assert comp.names == ["Title", "CleanBody", "Url", "TitleBigrams", "TitleTrigrams"]
+    # <= 8 slots -> TMAX 8 kernel; 9..16 slots -> TMAX 16 kernel
+    for ns, nq, k in ((8, 24, 50), (14, 16, 200)):
+        sf, st = random_queries(rng, dfs, comp.names, nq, ns)
+        check_against_oracle(comp, pairs, cols, sf, st, k, numeric)
+    # doc-range work items + merge: a batch dominated by one heavy query
+    sf = np.full((12, 6), 0xFF, np.uint8); st = np.full((12, 6), NO_TERM, np.uint32)
+    sf[0, :3] = [0, 1, 1]; st[0, :3] = [3, 3, 1]
+    for q in range(1, 12):
+        sf[q, :2] = [0, 2]; st[q, :2] = [4, 0]
+    check_against_oracle(comp, pairs, cols, sf, st, 100, numeric)
+
+
+def test_signal_compute_order_mirror():
+    """SignalComputeOrder::new and the signal_coefficient quirk of prepare_textfields, host side only."""
+    o = SignalComputeOrder(ENABLED | {"Bm25CleanBodyBigrams"}, numeric=[("HostCentrality", 0, 1.0)])
+    assert [e[0] for e in o.entries] == ["Bm25TitleTrigrams", "Bm25TitleBigrams", "Bm25Title", "Bm25CleanBodyBigrams", "Bm25CleanBody",
+                                         "Bm25F", "TitleCoverage", "CleanBodyCoverage", "IdfSumUrl", "HostCentrality"]
+    assert [e[3] for e in o.entries][:5] == [1, 2, 2, 1, 2]
