@@ -212,6 +212,30 @@ SB200_API int sb200_hyperball_set_publish_targets(sb200_graph* g, int n_targets,
 /* after the exchange: tell the library the global changed count so every rank picks the same mode */
 SB200_API int sb200_hyperball_exchange_done(sb200_graph* g, uint64_t global_n_changed);
 
+/* ---- other graph kernels over the resident CSR --------------------------------------------------
+ * All edge costs are 1, so the reference's dijkstra_multi (crates/core/src/webgraph/shortest_path.rs:57-105) is a
+ * breadth-first search; up to 64 searches run bit-parallel over the CSR the handle already holds.  Single-rank handles.
+ * The edge set is the handle's (unique, non-self-loop edges that pass skipped_rel_mask): create the handle with
+ * skipped_rel_mask = 0 for searches over every link, as ForwardlinksQuery / BacklinksQuery see them.
+ *
+ * sb200_graph_distances: raw_distances / raw_distances_with_max (forward, reversed = 0) and raw_reversed_distances(_with_max)
+ * (shortest_path.rs:122-214).  Source i belongs to search src_group[i] (NULL: its own search); a search with several
+ * sources reports the distance to the nearest one (dijkstra_multi's `sources` slice).  dist_out is [n_groups][n_nodes] in
+ * ascending-id order, 255 = not reached.  max_dist = 0: unbounded; otherwise the reference's cut-off is reproduced: it
+ * returns when it POPS a node with cost > max_dist, so nodes at distance max_dist + 1 are still reported. */
+SB200_API int sb200_graph_distances(sb200_graph* g, const uint64_t* src_lo, const uint64_t* src_hi, const uint32_t* src_group,
+                                    uint32_t n_sources, uint32_t n_groups, uint32_t max_dist, int reversed, uint8_t* dist_out);
+/* ApproxHarmonic::build (crates/core/src/webgraph/centrality/approx_harmonic.rs:40-88) for a caller-chosen sample (the
+ * reference draws random page nodes with outgoing links; ceil(log2(n) / 0.3^2) of them): one forward search with
+ * max_dist (7 in the reference) per sample; every reached target at distance d >= 1 receives
+ * (1.0 / d as f32) * (num_nodes as f32 / (n_sources as f32 * (num_nodes as f32 - 1.0))).  num_nodes is the reference's
+ * HyperLogLog<2048> estimate of the node count (0: the exact count).  The reference accumulates the f32 terms in a
+ * DashMap from a rayon pool, i.e. in no defined order; here the same f32 terms are summed in f64.  Output: the nodes that
+ * were reached, ascending id; call with centrality == NULL for the length. */
+SB200_API int sb200_approx_harmonic(sb200_graph* g, const uint64_t* src_lo, const uint64_t* src_hi, uint32_t n_sources,
+                                    uint32_t max_dist, uint64_t num_nodes, uint64_t* id_lo, uint64_t* id_hi, double* centrality,
+                                    uint64_t cap, uint64_t* len);
+
 /* Device-memory arena diagnostics.  With SB200_ARENA=1 in the environment, staging temporaries, the CSR and the
  * state of single-rank handles are sub-allocated from large slabs that are kept for the life of the process
  * (deterministic, no driver call per allocation once warm) instead of the driver's stream-ordered pool.

@@ -76,6 +76,8 @@ def _proto(L):
     f("orc_hb_dense_reset", None, C.c_void_p)
     f("orc_hb_dense_num_self_loops", C.c_uint64, C.c_void_p)
     f("orc_hb_dense_registers_ptr", C.c_void_p, C.c_void_p)
+    f("orc_graph_distances", None, C.c_uint32, _u32p, _u32p, C.c_uint64, _u32p, _u32p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, _u8p)
+    f("orc_approx_harmonic", None, C.c_uint32, _u32p, _u32p, C.c_uint64, _u32p, C.c_uint32, C.c_int, C.c_uint64, _f32p, _f64p)
     f("orc_synth_edges", None, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int,
       _u64p, _u64p, _u64p, _u64p, _u64p, C.c_int)
     if hasattr(L, "orc_p2_proto_marker"):
@@ -245,6 +247,42 @@ def synth_edges(kind, n_nodes, n_edges, seed=42, scale=26, first=0, threads=1):
     a = [np.empty(n_edges, np.uint64) for _ in range(5)]
     lib().orc_synth_edges(kind, n_nodes, first, n_edges, seed, scale, *a, threads)
     return dict(from_lo=a[0], from_hi=a[1], to_lo=a[2], to_hi=a[3], rel_flags=a[4])
+
+
+def graph_links(from_lo, from_hi, to_lo, to_hi, rel, skip_mask=0):
+    """(ids_lo, ids_hi, from_rank, to_rank): the unique links that pass `skip_mask` (first occurrence decides, like the
+    Webgraph iterator) over dense node ranks -- the input of graph_distances / approx_harmonic.  numpy, test sizes only."""
+    flo = np.asarray(from_lo, np.uint64); fhi = np.asarray(from_hi, np.uint64); tlo = np.asarray(to_lo, np.uint64); thi = np.asarray(to_hi, np.uint64)
+    ids = np.unique(np.concatenate([np.stack([fhi, flo], 1), np.stack([thi, tlo], 1)]), axis=0)
+    order = {(int(h), int(l)): i for i, (h, l) in enumerate(ids)}
+    fr = np.array([order[(int(h), int(l))] for h, l in zip(fhi, flo)], np.uint32)
+    tr = np.array([order[(int(h), int(l))] for h, l in zip(thi, tlo)], np.uint32)
+    pair = fr.astype(np.uint64) << np.uint64(32) | tr.astype(np.uint64)
+    _, first = np.unique(pair, return_index=True)
+    first.sort()
+    keep = (np.asarray(rel, np.uint64)[first] & np.uint64(skip_mask)) == 0
+    first = first[keep]
+    return ids[:, 1].copy(), ids[:, 0].copy(), fr[first], tr[first]
+
+
+def graph_distances(n, from_rank, to_rank, sources, groups=None, max_dist=None, reversed=False):
+    """dijkstra_multi (webgraph/shortest_path.rs:57-105) per group of sources: uint8 [n_groups, n], 255 = not reached."""
+    fr = np.ascontiguousarray(from_rank, np.uint32); tr = np.ascontiguousarray(to_rank, np.uint32)
+    src = np.ascontiguousarray(sources, np.uint32)
+    grp = np.arange(src.size, dtype=np.uint32) if groups is None else np.ascontiguousarray(groups, np.uint32)
+    ng = int(grp.max()) + 1 if grp.size else 1
+    out = np.zeros((ng, n), np.uint8)
+    lib().orc_graph_distances(n, fr, tr, fr.size, src, grp, src.size, ng, -1 if max_dist is None else int(max_dist), 1 if reversed else 0, out.reshape(-1))
+    return out
+
+
+def approx_harmonic(n, from_rank, to_rank, sources, max_dist=7, num_nodes=None):
+    """ApproxHarmonic::build for a fixed sample: (f32 sums in source order, f64 sums of the same f32 terms), 0 = not reached."""
+    fr = np.ascontiguousarray(from_rank, np.uint32); tr = np.ascontiguousarray(to_rank, np.uint32)
+    src = np.ascontiguousarray(sources, np.uint32)
+    o32 = np.zeros(n, np.float32); o64 = np.zeros(n, np.float64)
+    lib().orc_approx_harmonic(n, fr, tr, fr.size, src, src.size, int(max_dist), int(n if num_nodes is None else num_nodes), o32, o64)
+    return o32, o64
 
 
 def harmonic_ranks(ids_lo, ids_hi, values, ties_desc=False):

@@ -169,6 +169,14 @@ class SegmentReader:
         check(self._L.sb200_segment_create(_p(postings), postings.size, term_infos, n_terms, _p(self.fieldnorm_ids), self.max_doc,
                                            record_option, device, C.byref(self._h)))
         if total_num_tokens is None:
+            # tantivy keeps the exact token count in the inverted index (InvertedIndexReader::total_num_tokens); a caller that
+            # opens a real segment must pass it.  The reconstruction from the quantised fieldnorm ids below is exact only for
+            # indexes written from those ids (the synthetic / test segments of this repo).
+            import warnings
+            if not getattr(SegmentReader, "_warned_tokens", False):
+                warnings.warn("SegmentReader: total_num_tokens not given; reconstructing it from the fieldnorm ids (exact only for "
+                              "segments written from those ids)", stacklevel=2)
+                SegmentReader._warned_tokens = True
             total_num_tokens = int(fieldnorm_table()[self.fieldnorm_ids].astype(np.uint64).sum())
         self.total_num_tokens = total_num_tokens
         # average_fieldnorm = total_num_tokens as f32 / total_num_docs as f32 (bm25.rs:112-114)

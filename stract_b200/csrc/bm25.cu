@@ -104,10 +104,11 @@ __global__ void k_build_directory(const uint8_t* __restrict__ postings, const sb
   if (off + len > postings_len) { if (lane == 0) *err = 1; return; }
   uint64_t skip_start = off, skip_len = 0;
   if (df >= 128) {  // split_into_skips_and_postings, block_segment_postings.rs:78-88
-    int sh = 0; uint64_t p = off;
-    for (int i = 0; i < 10; i++) { const uint8_t b = postings[p++]; skip_len |= (uint64_t)(b & 127u) << sh; if (b & 128u) break; sh += 7; }
+    // every read stays inside [off, off + len): the TermInfo is caller data and may be corrupt
+    int sh = 0; uint64_t p = off; bool closed = false;
+    for (int i = 0; i < 10 && p < off + len; i++) { const uint8_t b = postings[p++]; skip_len |= (uint64_t)(b & 127u) << sh; if (b & 128u) { closed = true; break; } sh += 7; }
     skip_start = p;
-    if (skip_len != (uint64_t)nfull * stride) { if (lane == 0) *err = 2; return; }
+    if (!closed || skip_len != (uint64_t)nfull * stride || skip_start + skip_len > off + len) { if (lane == 0) *err = 2; return; }
   }
   const uint64_t data_off = skip_start + skip_len;
   if (lane == 0) { t_data_off[t] = data_off; t_end_off[t] = off + len; t_df[t] = df; }

@@ -508,7 +508,9 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
     SB_CUDA(cudaStreamSynchronize(pipe.cs));
     if (!h_flags[0]) { n_keys = h_ctr[0]; has_max = h_flags[1] != 0; break; }
     cap <<= 2;  // load factor exceeded 1/2: grow and redo (still linear overall)
-    if (cap > (1ull << 32)) SB_FAIL(SB200_ENOMEM, "node hash set would exceed 2^32 slots");
+    // slots are recorded as u32 and 0xFFFFFFFF is the sentinel (all-ones id / overflow), so the table must stay below
+    // 2^32 slots: at most 2^31, i.e. <= 2^30 nodes at load factor 1/2 (n_edges < 2^32 keeps real inputs far below)
+    if (cap > (1ull << 31)) SB_FAIL(SB200_ERANGE, "node hash set would exceed 2^31 slots (more than 2^30 distinct nodes)");
   }
   for (int a = 0; a < 5; a++) for (int bsel = 0; bsel < 2; bsel++) stg[bsel][a].release();
   pt.mark("1b compact+sort ids");

@@ -300,6 +300,31 @@ class DeviceGraph:
             check(self._L.sb200_graph_ownership(self._h, o.ctypes.data, m.ctypes.data))
         return o, m
 
+    def distances(self, sources, groups=None, max_dist=0, reversed=False):
+        """dijkstra_multi with unit costs (webgraph/shortest_path.rs:57-105): `sources` = node ids (python ints), `groups[i]` =
+        the search source i belongs to (default: one search per source).  Returns uint8 [n_groups, n_nodes] in ascending-id
+        order, 255 = not reached; with max_dist > 0 distances up to max_dist + 1 are reported like the reference does."""
+        n = self.info()["n_nodes"]
+        lo = np.array([int(x) & _M64 for x in sources], np.uint64); hi = np.array([int(x) >> 64 for x in sources], np.uint64)
+        grp = np.arange(len(lo), dtype=np.uint32) if groups is None else np.ascontiguousarray(groups, np.uint32)
+        ng = int(grp.max()) + 1 if len(grp) else 1
+        out = np.full((ng, n), 255, np.uint8)
+        check(self._L.sb200_graph_distances(self._h, lo.ctypes.data, hi.ctypes.data, grp.ctypes.data, len(lo), ng, int(max_dist),
+                                            1 if reversed else 0, out.ctypes.data))
+        return out
+
+    def approx_harmonic(self, sources, max_dist=7, num_nodes=0):
+        """ApproxHarmonic::build for the given sample (webgraph/centrality/approx_harmonic.rs:40-88): (ids_lo, ids_hi, centrality)
+        of the reached nodes in ascending id order."""
+        n = self.info()["n_nodes"]
+        lo = np.array([int(x) & _M64 for x in sources], np.uint64); hi = np.array([int(x) >> 64 for x in sources], np.uint64)
+        ln = C.c_uint64(0)
+        olo = host_out(n, np.uint64); ohi = host_out(n, np.uint64); oc = host_out(n, np.float64)
+        check(self._L.sb200_approx_harmonic(self._h, lo.ctypes.data, hi.ctypes.data, len(lo), int(max_dist), int(num_nodes),
+                                            olo.ctypes.data if n else None, ohi.ctypes.data if n else None, oc.ctypes.data if n else None, n, C.byref(ln)))
+        k = ln.value
+        return olo[:k], ohi[:k], oc[:k]
+
     def exchange_done(self, global_n_changed):
         check(self._L.sb200_hyperball_exchange_done(self._h, int(global_n_changed)))
 

@@ -179,6 +179,8 @@ template <class A, class B> static inline typename std::common_type<A, B>::type 
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> (sh & 31u)); }
 static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
@@ -202,6 +204,7 @@ static inline __attribute__((always_inline)) void __syncthreads() { ::emu::block
 static inline __attribute__((always_inline)) void __syncwarp(unsigned mask = 0xffffffffu) { ::emu::warp_barrier(mask); }
 template <class T> static inline T atomicAdd(T* p, T v) { const T o = *p; *p = o + v; return o; }
 static inline unsigned atomicOr(unsigned* p, unsigned v) { const unsigned o = *p; *p = o | v; return o; }
+static inline unsigned long long atomicOr(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o | v; return o; }
 
 namespace emu {
 template <class T> static inline uint64_t pack(T v) { static_assert(sizeof(T) <= 8, "payload"); uint64_t r = 0; memcpy(&r, &v, sizeof(T)); return r; }

@@ -1,0 +1,66 @@
+"""The other graph kernels over the resident CSR: shortest-path distances (dijkstra_multi with unit
+costs, incl. its max_dist cut-off and reversed searches) exact against the oracle; ApproxHarmonic for a fixed sample against
+the oracle's f64 sums (identical f32 terms) and within f32 accumulation error of the reference-shaped f32 sums."""
+import numpy as np
+import pytest
+
+import oracle
+from stract_b200 import synth
+from stract_b200.webgraph import DeviceGraph, Webgraph
+
+pytestmark = pytest.mark.gpu
+
+
+def _graph(seed=3, nodes=4000, edges=30000):
+    d = synth.rmat_graph(nodes, edges, seed=seed)
+    a = (d["from_lo"], d["from_hi"], d["to_lo"], d["to_hi"], d["rel_flags"])
+    ids_lo, ids_hi, fr, tr = oracle.graph_links(*a, skip_mask=0)
+    keep = fr != tr          # a self-loop never shortens a path; the device CSR drops it
+    return a, ids_lo, ids_hi, fr[keep], tr[keep]
+
+
+def test_distances_match_dijkstra_multi():
+    a, ids_lo, ids_hi, fr, tr = _graph()
+    n = len(ids_lo)
+    dg = DeviceGraph(Webgraph.from_arrays(*a), skipped_rel=0)      # every link, as ForwardlinksQuery sees them
+    try:
+        assert dg.info()["n_nodes"] == n
+        rng = np.random.default_rng(1)
+        src = rng.choice(n, 70, replace=False).astype(np.uint32)
+        ids = [(int(ids_hi[s]) << 64) | int(ids_lo[s]) for s in src]
+        for reversed_ in (False, True):
+            for max_dist in (None, 2, 7):
+                for lo in (0, 64):       # 64 searches fill the bit word; the rest goes in a second call
+                    part = slice(lo, min(lo + 64, len(src)))
+                    want = oracle.graph_distances(n, fr, tr, src[part], None, max_dist, reversed_)
+                    got = dg.distances(ids[part], None, 0 if max_dist is None else max_dist, reversed_)
+                    assert np.array_equal(got, want), (reversed_, max_dist, lo)
+        # several sources per search (dijkstra_multi's `sources` slice) + an id that is not a node
+        groups = np.array([0, 0, 0, 1, 1, 2], np.uint32)
+        want = oracle.graph_distances(n, fr, tr, src[:6], groups, 3, False)
+        got = dg.distances(ids[:6] + [12345], np.concatenate([groups, [2]]).astype(np.uint32), 3, False)
+        assert np.array_equal(got, want)
+        assert (want[0] <= 4).sum() > 3 and want.max() == 255     # the cut-off reports distances up to max_dist + 1
+    finally:
+        dg.close()
+
+
+def test_approx_harmonic_fixed_sample():
+    a, ids_lo, ids_hi, fr, tr = _graph(seed=9, nodes=6000, edges=60000)
+    n = len(ids_lo)
+    dg = DeviceGraph(Webgraph.from_arrays(*a), skipped_rel=0)
+    try:
+        rng = np.random.default_rng(2)
+        outdeg = np.bincount(fr, minlength=n)
+        cand = np.flatnonzero(outdeg > 0)                       # random_page_nodes_with_outgoing
+        k = int(np.ceil(np.log2(n) / 0.3 ** 2))                 # approx_harmonic.rs:50
+        src = rng.choice(cand, k, replace=False).astype(np.uint32)
+        ids = [(int(ids_hi[s]) << 64) | int(ids_lo[s]) for s in src]
+        w32, w64 = oracle.approx_harmonic(n, fr, tr, src, 7, n)
+        lo, hi, c = dg.approx_harmonic(ids, 7, n)
+        reached = np.flatnonzero(w64 != 0.0)
+        assert np.array_equal(lo, ids_lo[reached]) and np.array_equal(hi, ids_hi[reached])
+        assert np.allclose(c, w64[reached], rtol=1e-12, atol=0.0)            # same f32 terms, f64 sums (order differs)
+        assert np.allclose(c, w32[reached].astype(np.float64), rtol=2e-5)    # the reference-shaped f32 accumulation
+    finally:
+        dg.close()

@@ -1,6 +1,7 @@
 """Pins the path-1 oracle against every known-answer test the reference holds for it
 (SURVEY.md 8c).  CPU only."""
 import math
+import os
 
 import numpy as np
 
@@ -188,3 +189,61 @@ def test_harmonic_rank_order_restatement():
     assert list(harmonic_ranks(lo, hi, c)) == want == [3, 0, 2, 1, 4]
     want_top = sorted(range(5), key=lambda i: (c[i], ids[i]), reverse=True)
     assert list(harmonic_ranks(lo, hi, c, ties_desc=True)) == want_top == [3, 2, 0, 4, 1]
+
+
+def test_hll64_bias_does_not_depend_on_the_std_binary_search():
+    """estimate_bias binary-searches the precision-5 raw table, which is not sorted (inversions at 127/128 and 130/131),
+    so the index it returns depends on the std implementation: Rust >= 1.82 (branch-free, what the oracle and the GPU
+    follow) and Rust 1.52-1.81 (three-way compare) can land on different neighbours.  The value that matters is the mean
+    bias of the 6 nearest entries, and a dense sweep over [20, 320] -- extra fine around the two inversions -- shows it is
+    the same under both searches, so HyperLogLog<64>::size() does not depend on the toolchain (ADVICE round 1)."""
+    import re
+    t = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "sb200_hll_tables.h")).read()
+
+    def arr(name):
+        m = re.search(name + r"\[\w*\]\s*=\s*\{(.*?)\};", t, re.S)
+        return np.array([float(x) for x in m.group(1).replace("\n", " ").split(",") if x.strip()])
+    raw, bias = arr("SB200_HLL_RAW_P5"), arr("SB200_HLL_BIAS_P5")
+    n = len(raw)
+    assert [i for i in range(n - 1) if raw[i] > raw[i + 1]] == [127, 130]
+
+    def new_search(e):
+        size, base = n, 0
+        while size > 1:
+            half = size // 2; mid = base + half
+            base = base if raw[mid] > e else mid
+            size -= half
+        r = base if raw[base] == e else base + (1 if raw[base] < e else 0)
+        return min(r, n - 1)
+
+    def old_search(e):
+        left, right, size = 0, n, n
+        while left < right:
+            mid = left + size // 2
+            if raw[mid] < e: left = mid + 1
+            elif raw[mid] > e: right = mid
+            else: return mid
+            size = right - left
+        return min(left, n - 1)
+
+    def mean_bias(idx, e):
+        il, ir, acc = idx, (idx + 1 if idx < n - 1 else -1), 0.0
+        for _ in range(6):
+            if il >= 0 and ir >= 0:
+                right = abs(raw[ir] - e) < abs(raw[il] - e)
+            else:
+                right = il < 0
+            i = ir if right else il
+            acc += bias[i]
+            if right: ir = i + 1 if i < n - 1 else -1
+            else: il = i - 1 if i > 0 else -1
+        return acc / 6.0
+    sweep = np.concatenate([np.linspace(20, 320, 60001), np.linspace(128.2, 128.5, 60001), np.linspace(130.9, 131.2, 60001),
+                            raw, np.nextafter(raw, 0), np.nextafter(raw, 1e9)])
+    differing_index = 0
+    for e in sweep:
+        a, b = new_search(e), old_search(e)
+        if a != b:
+            differing_index += 1
+            assert mean_bias(a, e) == mean_bias(b, e), e
+    assert differing_index > 0     # the searches do disagree on the index somewhere -- just never on the result
