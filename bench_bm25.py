@@ -19,7 +19,8 @@ def synth_index(max_doc, df_scale, n_ranks=10_000, seed=1234, threads=16):
     lens = np.minimum(np.maximum(1, rng.lognormal(5.5, 0.8, max_doc)), 2e9).astype(np.uint32)
     ids = bm25.fieldnorms_to_ids(lens)
     del lens
-    avg = np.float32(np.float32(bm25.fieldnorm_table()[ids].astype(np.uint64).sum()) / np.float32(max_doc))
+    total_tokens = int(bm25.fieldnorm_table()[ids].astype(np.uint64).sum())   # the index is written from the quantised lengths
+    avg = np.float32(np.float32(total_tokens) / np.float32(max_doc))
     ranks = np.arange(1, n_ranks + 1)
     target = np.minimum(np.maximum(1, np.round(df_scale / ranks)), max_doc // 2).astype(np.int64)
     docs_l, off = [], np.zeros(n_ranks + 1, np.uint64)
@@ -34,7 +35,7 @@ def synth_index(max_doc, df_scale, n_ranks=10_000, seed=1234, threads=16):
     del docs_l
     tfs = np.minimum(rng.geometric(0.6, docs.size), 255).astype(np.uint32)
     data, infos = bm25.encode_postings_csr(docs, tfs, off, ids, avg, threads=threads)
-    return dict(postings=data, infos=infos, fieldnorm_ids=ids, avg=avg, n_postings=int(docs.size), off=off)
+    return dict(postings=data, infos=infos, fieldnorm_ids=ids, avg=avg, n_postings=int(docs.size), off=off, total_num_tokens=total_tokens)
 
 
 def log_uniform_queries(n_queries, n_terms, lo=10, hi=10_000, seed=1):
@@ -57,7 +58,7 @@ def run_and(device, peaks, max_doc=10_000_000, df_scale=2.0e6, n_queries=10_000,
     t0 = time.perf_counter()
     ix = synth_index(max_doc, df_scale)
     gen_s = time.perf_counter() - t0
-    seg = bm25.SegmentReader(ix["postings"], ix["infos"], ix["fieldnorm_ids"], device=device)
+    seg = bm25.SegmentReader(ix["postings"], ix["infos"], ix["fieldnorm_ids"], device=device, total_num_tokens=ix["total_num_tokens"])
     terms = log_uniform_queries(n_queries, 2)
     top = bm25.TopDocs.with_limit(k)
     for _ in range(warmup):
@@ -140,7 +141,7 @@ def run_signal(device, peaks, max_doc=100_000_000, df_scale=2.0e7, n_queries=10_
     del rank
     coeffs = [2.0, 0.02, 2.0, 0.001]
     gen_s = time.perf_counter() - t0
-    seg = bm25.SegmentReader(ix["postings"], ix["infos"], ix["fieldnorm_ids"], device=device)
+    seg = bm25.SegmentReader(ix["postings"], ix["infos"], ix["fieldnorm_ids"], device=device, total_num_tokens=ix["total_num_tokens"])
     table = bm25.SignalTable(cols, device=device)
     comp = bm25.SignalComputer(seg, table, coeffs, coeff_text=0.005)
     terms = log_uniform_queries(n_queries, 5, seed=2)

@@ -586,6 +586,7 @@ template <class T>
 static int ensure(DevBuf<T>& b, size_t n) { if (b.n < n) return b.alloc(n + (n >> 2) + 16); return SB200_OK; }
 
 }  // namespace sb200
+#include "tma.cuh"
 #include "bm25_warp.cuh"
 namespace sb200 {
 
@@ -992,6 +993,7 @@ static int run_batch(sb200_segment* g, const sb200_bm25_batch* b, int mode, cons
     W.k1p1 = P.k1p1; W.coeff_text = P.coeff_text; W.sig = P.sig; W.n_cols = P.n_cols; W.coeffs = P.coeffs; W.max_docs = P.max_docs;
     W.g_khi = g->g_khi.p; W.g_klo = g->g_klo.p;
     W.o_docs = P.o_docs; W.o_scores = P.o_scores; W.o_totals = P.o_totals; W.o_n = P.o_n; W.counters = P.counters;
+    W.use_tma = env_flag("SB200_BM25_TMA", true) ? 1u : 0u;
     const bool use_or3 = kmode != 0 && W.max_docs == 0 && env_flag("SB200_BM25_OR3", true);  // bm25_or3.cuh; SB200_BM25_OR3=0: k_topk_warp
     if (use_or3) { if (kmode == 2) SB_TRY(launch_or3<2>(W, s)); else SB_TRY(launch_or3<1>(W, s)); }
     else if (kmode == 2) SB_TRY(launch_topk_warp<2>(W, s));

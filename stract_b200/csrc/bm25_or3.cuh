@@ -20,6 +20,8 @@
 
 namespace sb200 {
 
+constexpr uint32_t O3_STAGE_BYTES = 256;   // a staged block: (doc bits + tf bits) * 16 B <= 256, i.e. <= 16 bits per posting
+constexpr uint32_t O3_NONE = 0xFFFFFFFFu;
 struct OTerm { uint64_t adata, tail_off, end_off; uint32_t first, nfull, df; float weight; };  // per (warp, term), shared
 static_assert(sizeof(OTerm) == 40, "OTerm layout");
 
@@ -52,8 +54,9 @@ __device__ __forceinline__ uint32_t o3_dir_search(const uint32_t* __restrict__ l
 // Decode block `blk` of a term (full block, or the vint tail when blk == nfull) into docs/tfs[128] and rebuild its
 // presence filter.  Every lane calls it; returns the number of postings (docs beyond it are TERMINATED) and the
 // last doc through `last`.
+// `staged` (nullable): the packed bytes of this block in shared memory, put there ahead of time by the TMA unit.
 __device__ uint32_t o3_decode(const SegView& S, const uint4* __restrict__ a128, const OTerm& c, uint32_t blk, uint32_t prev_last,
-                              uint32_t* docs, uint32_t* tfs, uint32_t* bloom, uint32_t lane, uint32_t& last) {
+                              uint32_t* docs, uint32_t* tfs, uint32_t* bloom, uint32_t lane, uint32_t& last, const uint4* staged = nullptr) {
   __syncwarp();
   if (lane < 16) bloom[lane] = 0;
   uint32_t n;
@@ -61,10 +64,16 @@ __device__ uint32_t o3_decode(const SegView& S, const uint4* __restrict__ a128, 
   if (blk < c.nfull) {
     const uint32_t idx = c.first + blk;
     const uint32_t bits = S.b_bits[idx], db = bits & 0x3fu, strict = (bits >> 6) & 1u, tb = bits >> 8;
-    const uint4* base = a128 + c.adata + (S.b_off[idx] >> 4);
-    d = unpack4(base, db, lane);
     uint4 f = make_uint4(1, 1, 1, 1);
-    if (S.record >= 1) { f = unpack4(base + db, tb, lane); f.x += strict; f.y += strict; f.z += strict; f.w += strict; }
+    if (staged) {
+      d = unpack4<true>(staged, db, lane);
+      if (S.record >= 1) f = unpack4<true>(staged + db, tb, lane);
+    } else {
+      const uint4* base = a128 + c.adata + (S.b_off[idx] >> 4);
+      d = unpack4(base, db, lane);
+      if (S.record >= 1) f = unpack4(base + db, tb, lane);
+    }
+    if (S.record >= 1) { f.x += strict; f.y += strict; f.z += strict; f.w += strict; }
     d.x += strict; d.y += d.x + strict; d.z += d.y + strict; d.w += d.z + strict;
     const uint32_t incl = warp_scan_incl(d.w, lane);
     const uint32_t before = incl - d.w + ((strict && prev_last == 0) ? 0xFFFFFFFFu : prev_last);  // offset 0 == None
@@ -129,6 +138,11 @@ __global__ void __launch_bounds__(WQ * 32) k_or3(const WParams P) {
   __shared__ uint32_t s_bloom[WQ][TMAX * 16];
   __shared__ OTerm s_tc[WQ][TMAX];
   __shared__ uint32_t s_misc[WQ][32];
+  // TMA staging: while a term's current block is being consumed, the bytes of its NEXT block travel from HBM/L2 into this
+  // buffer (one cp.async.bulk per block, completion on the term's mbarrier), so the next refill unpacks from shared
+  // memory instead of waiting for two dependent global loads.  Blocks wider than O3_STAGE_BYTES take the direct path.
+  __shared__ __align__(16) unsigned char s_stage[WQ][TMAX][O3_STAGE_BYTES];
+  __shared__ __align__(8) uint64_t s_bar[WQ][TMAX];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (uint32_t i = threadIdx.x; i < 256; i += WQ * 32) cache[i] = P.cache[i];
   __syncthreads();  // the only block barrier
@@ -151,6 +165,14 @@ __global__ void __launch_bounds__(WQ * 32) k_or3(const WParams P) {
   // ---- cursors: lane t owns term t
   uint32_t my_pos = 0, my_len = 0, my_last = 0, my_cur = 0, my_prev = 0;
   bool my_done = true, my_tail_done = false;
+  uint32_t my_pf = O3_NONE, my_phase = 0;   // block whose bytes are (being) staged for this lane's term; parity to wait for
+  const bool use_tma = P.use_tma != 0;
+  uint64_t* bar = s_bar[warp];
+  if (use_tma) {
+    if (lane < TMAX) mbar_init(bar + lane, 1);
+    mbar_fence_init();
+    __syncwarp();
+  }
   unsigned long long budget = 64;
   if (lane < T) {
     OTerm c;
@@ -200,8 +222,31 @@ __global__ void __launch_bounds__(WQ * 32) k_or3(const WParams P) {
           continue;
         }
         uint32_t last;
-        const uint32_t n = o3_decode(S, P.a128, c, cur, prev, docs + s * 128, tfs + s * 128, bloom + s * 16, lane, last);
+        const uint4* staged = nullptr;
+        if (use_tma) {
+          const uint32_t pf = __shfl_sync(0xffffffffu, my_pf, s), ph = __shfl_sync(0xffffffffu, my_phase, s);
+          if (pf != O3_NONE) {               // an outstanding copy is always waited for before its buffer / barrier is reused
+            mbar_wait(bar + s, ph);
+            if (pf == cur) staged = (const uint4*)s_stage[warp][s];
+            if (lane == (uint32_t)s) { my_pf = O3_NONE; my_phase ^= 1u; }
+          }
+        }
+        const uint32_t n = o3_decode(S, P.a128, c, cur, prev, docs + s * 128, tfs + s * 128, bloom + s * 16, lane, last, staged);
         my_blocks++;
+        if (use_tma && cur + 1 < c.nfull) {  // o3_decode ended with a warp barrier: every lane is done with the staging buffer
+          uint32_t issued = 0;
+          if (lane == 0) {
+            const uint32_t idx = c.first + cur + 1, bits = S.b_bits[idx];
+            const uint32_t bytes = ((bits & 0x3fu) + (bits >> 8)) * 16u;
+            if (bytes != 0 && bytes <= O3_STAGE_BYTES) {
+              mbar_expect_tx(bar + s, bytes);
+              tma_load_1d(s_stage[warp][s], P.a128 + c.adata + (S.b_off[idx] >> 4), bytes, bar + s);
+              issued = 1;
+            }
+          }
+          issued = __shfl_sync(0xffffffffu, issued, 0);
+          if (issued && lane == (uint32_t)s) my_pf = cur + 1;
+        }
         if (lane == (uint32_t)s) {
           my_len = n; my_pos = 0; my_last = last; my_prev = last; my_cur = cur + 1;
           if (cur >= c.nfull) my_tail_done = true;
@@ -322,6 +367,7 @@ __global__ void __launch_bounds__(WQ * 32) k_or3(const WParams P) {
     }
     __syncwarp();
   }
+  if (use_tma && my_pf != O3_NONE) mbar_wait(bar + lane, my_phase);   // no copy may still be in flight when the warp leaves
   __threadfence_block();
   __syncwarp();
   w_sort_prefix_desc(khi, klo, *s_count, P.cap, lane);

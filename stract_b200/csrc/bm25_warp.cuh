@@ -41,6 +41,7 @@ struct WParams {
   float k1p1; double coeff_text; const double* sig; uint32_t n_cols; const double* coeffs; uint32_t max_docs;
   uint64_t* g_khi; uint32_t* g_klo;   // [n_queries][cap] candidate buffers
   uint32_t* o_docs; float* o_scores; double* o_totals; uint32_t* o_n; unsigned long long* counters;
+  uint32_t use_tma;   // k_or3: stage the next posting block of every term with cp.async.bulk (SB200_BM25_TMA=0 turns it off)
 };
 
 __device__ __forceinline__ uint32_t warp_scan_incl(uint32_t x, uint32_t lane) {
@@ -49,13 +50,15 @@ __device__ __forceinline__ uint32_t warp_scan_incl(uint32_t x, uint32_t lane) {
   return x;
 }
 
-// four consecutive values (k = 4*slot .. 4*slot+3) of a 128-value BitPacker4x stream stored at `base` (uint4 units)
+// four consecutive values (k = 4*slot .. 4*slot+3) of a 128-value BitPacker4x stream stored at `base` (uint4 units);
+// STAGED: `base` points into shared memory (a block the TMA unit copied there), so plain loads instead of ld.global.nc
+template <bool STAGED = false>
 __device__ __forceinline__ uint4 unpack4(const uint4* __restrict__ base, uint32_t nb, uint32_t slot) {
   if (nb == 0) return make_uint4(0, 0, 0, 0);
   const uint32_t bit = slot * nb, w = bit >> 5, sh = bit & 31u;
-  const uint4 lo = __ldg(base + w);
+  const uint4 lo = STAGED ? base[w] : __ldg(base + w);
   uint4 hi = make_uint4(0, 0, 0, 0);
-  if (sh + nb > 32) hi = __ldg(base + w + 1);
+  if (sh + nb > 32) hi = STAGED ? base[w + 1] : __ldg(base + w + 1);
   const uint32_t mask = nb == 32 ? 0xFFFFFFFFu : ((1u << nb) - 1u);
   return make_uint4(__funnelshift_r(lo.x, hi.x, sh) & mask, __funnelshift_r(lo.y, hi.y, sh) & mask,
                     __funnelshift_r(lo.z, hi.z, sh) & mask, __funnelshift_r(lo.w, hi.w, sh) & mask);

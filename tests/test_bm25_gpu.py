@@ -20,7 +20,7 @@ def build(term_docs, term_tfs, lens, record_option=1):
         oseg.add_term(np.asarray(d, np.uint32), np.asarray(t, np.uint32))
     data, infos = bm25.encode_postings(term_docs, term_tfs, ids, oseg.avg_fieldnorm, record_option=record_option)
     assert np.array_equal(data, oseg.postings_bytes())
-    seg = SegmentReader(data, infos, ids, record_option=record_option)
+    seg = SegmentReader(data, infos, ids, record_option=record_option, total_num_tokens=int(bm25.fieldnorm_table()[ids].astype(np.uint64).sum()))
     assert seg.average_fieldnorm == np.float32(oseg.avg_fieldnorm)
     return oseg, seg
 

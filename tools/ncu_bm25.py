@@ -12,7 +12,7 @@ what = sys.argv[1]
 scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 if what == "and":
     ix = bench_bm25.synth_index(int(10_000_000 * scale), 2.0e6 * scale)
-    seg = bm25.SegmentReader(ix["postings"], ix["infos"], ix["fieldnorm_ids"])
+    seg = bm25.SegmentReader(ix["postings"], ix["infos"], ix["fieldnorm_ids"], total_num_tokens=ix["total_num_tokens"])
     terms = bench_bm25.log_uniform_queries(10_000, 2)
     top = bm25.TopDocs.with_limit(1000)
     for _ in range(2):
@@ -23,7 +23,7 @@ else:
     ix = bench_bm25.synth_index(max_doc, 2.0e7 * scale)
     rng = np.random.default_rng(99)
     cols = [rng.random(max_doc) ** 8, rng.random(max_doc), rng.random(max_doc), 1.0 / (1.0 + rng.integers(0, 1000, max_doc).astype(np.float64))]
-    seg = bm25.SegmentReader(ix["postings"], ix["infos"], ix["fieldnorm_ids"])
+    seg = bm25.SegmentReader(ix["postings"], ix["infos"], ix["fieldnorm_ids"], total_num_tokens=ix["total_num_tokens"])
     comp = bm25.SignalComputer(seg, bm25.SignalTable(cols), [2.0, 0.02, 2.0, 0.001], coeff_text=0.005)
     terms = bench_bm25.log_uniform_queries(10_000, 5, seed=2)
     for _ in range(2):
