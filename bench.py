@@ -147,7 +147,27 @@ def _i64(x):
 
 
 def host_threads():
-    return os.cpu_count() or 1
+    """Threads the CPU legs may use: the cores this process is allowed to run on (affinity mask, cgroup CPU quota), not the
+    machine's core count -- a GPU lease is often a slice of a bigger host."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, q // period))
+        except (OSError, ValueError, IndexError):
+            pass
+    return max(1, n)
 
 
 def _np_u64(t):

@@ -115,7 +115,8 @@ def cpu_and(ix, terms, k, seg, gpu_out, sample=2048, runs=3):
     uniq, inv = np.unique(df, return_inverse=True)
     w = np.array([bm25.Bm25Weight.for_one_term(int(x), seg.max_doc, seg.average_fieldnorm).weight for x in uniq], np.float32)[inv].reshape(t.shape)
     caches = np.tile(cache, (t.size, 1))
-    threads = os.cpu_count() or 1
+    from bench import host_threads
+    threads = host_threads()
     dts = []
     for _ in range(runs):
         t0 = time.perf_counter()
@@ -171,7 +172,8 @@ def run_signal(device, peaks, max_doc=100_000_000, df_scale=2.0e7, n_queries=10_
         infos = ix["infos"]; nt = len(infos)
         o.set_postings(ix["postings"], [infos[i].postings_off for i in range(nt)], [infos[i].postings_len for i in range(nt)],
                        [infos[i].doc_freq for i in range(nt)])
-        threads = os.cpu_count() or 1
+        from bench import host_threads
+        threads = host_threads()
         t = terms[:max(16 * threads, 256)]        # >= 16 queries per thread, dynamic schedule
         cache = bm25.compute_tf_cache(seg.average_fieldnorm)
         df = seg.doc_freq[t]

@@ -17,6 +17,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <thread>
@@ -84,6 +87,14 @@ ORC_API void* orc_hb_dense_create_mt(const uint64_t* flo, const uint64_t* fhi, c
   const int T = threads < 1 ? 1 : threads;
   g->threads = T;
   const uint64_t E = n_edges;
+  const bool timing = getenv("ORC_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[orc stage] %-28s %8.2f s\n", what, std::chrono::duration<double>(now - t_prev).count());
+    t_prev = now;
+  };
 
   // ---- 1. host_nodes(): distinct endpoints ------------------------------------------------------
   const int NB = 1 << ID_BUCKET_BITS;
@@ -102,6 +113,7 @@ ORC_API void* orc_hb_dense_create_mt(const uint64_t* flo, const uint64_t* fhi, c
     for (u128 k : s.slot) if (k) out[pos[id_bucket(k)]++] = k;
     local[t].swap(out); local_off[t].swap(cnt);
   });
+  mark("1a local endpoint sets");
   std::vector<std::vector<u128>> bucket(NB);
   par_for(NB, T, 8, [&](int64_t qb, int64_t qe, int) {
     for (int64_t q = qb; q < qe; q++) {
@@ -122,6 +134,7 @@ ORC_API void* orc_hb_dense_create_mt(const uint64_t* flo, const uint64_t* fhi, c
   bucket.clear(); bucket.shrink_to_fit();
   if (N > 0xFFFFFFFFull) { delete g; return nullptr; }
 
+  mark("1b bucket sort + concat");
   // ---- 2. rank directory -----------------------------------------------------------------------
   const uint64_t NI = 1ull << IDX_BITS;
   std::vector<uint64_t> dir(NI + 1, 0);
@@ -147,6 +160,7 @@ ORC_API void* orc_hb_dense_create_mt(const uint64_t* flo, const uint64_t* fhi, c
       tr[i] = a; fr[i] = f; cnt[t][a / rows_per]++;
     }
   });
+  mark("3a rank lookups");
   std::vector<uint64_t> tb_off(TB + 1, 0);
   {
     uint64_t run = 0;
@@ -165,6 +179,7 @@ ORC_API void* orc_hb_dense_create_mt(const uint64_t* flo, const uint64_t* fhi, c
     }
   });
   tr.reset(); fr.reset();
+  mark("3b scatter");
 
   // ---- 4. per bucket: sort, first-wins dedup, drop skipped, emit CSR pieces ---------------------------
   g->row_ptr.assign(N + 1, 0);
@@ -183,6 +198,7 @@ ORC_API void* orc_hb_dense_create_mt(const uint64_t* flo, const uint64_t* fhi, c
     }
   });
   ents.reset();
+  mark("4a bucket sort + dedup");
   for (uint64_t v = 0; v < N; v++) g->row_ptr[v + 1] += g->row_ptr[v];
   g->col.resize(g->row_ptr[N]);
   par_for(TB, T, 4, [&](int64_t qb, int64_t qe, int) {
@@ -193,6 +209,7 @@ ORC_API void* orc_hb_dense_create_mt(const uint64_t* flo, const uint64_t* fhi, c
   });
   colb.clear(); colb.shrink_to_fit();
 
+  mark("4b csr concat");
   // ---- 5. HyperBall state (harmonic.rs:53-73) ----------------------------------------------------
   g->old_r.assign(N * 64, 0);
   g->size_old.resize(N);
@@ -206,6 +223,7 @@ ORC_API void* orc_hb_dense_create_mt(const uint64_t* flo, const uint64_t* fhi, c
   g->changed.assign(N, 1);
   g->new_changed.assign(N, 0);
   g->cent.assign(N, Kahan());
+  mark("5 state init");
   return g;
 }
 
