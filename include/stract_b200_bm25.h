@@ -67,6 +67,10 @@ SB200_API void sb200_signals_destroy(sb200_signals* s);
 
 #define SB200_MODE_AND 0     /* all clauses Occur::Must  -> Intersection, score = left + right + sum(others) */
 #define SB200_MODE_OR 1      /* all clauses Occur::Should -> union, score = f32 sum over matching terms in query order */
+#define SB200_MODE_OR_WAND 2 /* the same union with tantivy's Block-Max WAND replayed step by step (block_wand.rs:148-214): the f32
+                               sum of a document's term scores then has the association the reference's pruning history gives it,
+                               so scores and doc order match the reference bit for bit for ANY number of terms.  10-100x slower
+                               than SB200_MODE_OR, whose sums are in query order (identical for <= 2 terms). */
 #define SB200_NO_TERM 0xFFFFFFFFu  /* padding for queries shorter than the batch arity */
 #define SB200_MAX_QUERY_TERMS 8
 #define SB200_MAX_K 4096
@@ -167,6 +171,9 @@ SB200_API int sb200_postings_encode(const uint32_t* docs, const uint32_t* tfs, c
 SB200_API int sb200_postings_encode_ex(const uint32_t* docs, const uint32_t* tfs, const uint64_t* term_off, uint32_t n_terms,
                                        const uint8_t* fieldnorm_ids, uint32_t max_doc, float avg_fieldnorm, int record_option,
                                        uint8_t* out, uint64_t out_cap, uint64_t* out_len, sb200_term_info* infos, int threads);
+/* idf(doc_freq, doc_count) = ln(1 + (N - n + 0.5) / (n + 0.5)) in f32 (tantivy/src/query/bm25.rs:52-56,
+ * core/src/ranking/bm25.rs:23-27) for an array of doc_freqs; tantivy_weight != 0 returns Bm25Weight.weight = idf * (1 + K1). */
+SB200_API int sb200_bm25_idf(const uint32_t* doc_freq, uint64_t n, uint64_t doc_count, int tantivy_weight, float* out);
 /* FIELD_NORMS_TABLE (tantivy/src/fieldnorm/code.rs:13-270) as the closed-form byte code it is tested against */
 SB200_API uint32_t sb200_fieldnorm_id_to_value(uint8_t id);
 SB200_API uint8_t sb200_fieldnorm_value_to_id(uint32_t fieldnorm);

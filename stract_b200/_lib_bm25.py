@@ -54,5 +54,6 @@ def proto(L, f):
     f("sb200_postings_encode", i32, vp, vp, vp, u32, vp, u32, C.c_float, vp, u64, C.POINTER(u64), vp, i32)
     f("sb200_term_info_store_decode", i32, vp, u64, i32, vp, u64, C.POINTER(u64))
     f("sb200_postings_encode_ex", i32, vp, vp, vp, u32, vp, u32, C.c_float, i32, vp, u64, C.POINTER(u64), vp, i32)
+    f("sb200_bm25_idf", i32, vp, u64, u64, i32, vp)
     f("sb200_fieldnorm_id_to_value", u32, C.c_uint8)
     f("sb200_fieldnorm_value_to_id", C.c_uint8, u32)

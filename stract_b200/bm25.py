@@ -23,7 +23,7 @@ from ._hostmem import host_out
 
 K1 = np.float32(1.2)
 B_ = np.float32(0.75)
-MODE_AND, MODE_OR = 0, 1
+MODE_AND, MODE_OR, MODE_OR_WAND = 0, 1, 2   # MODE_OR_WAND: block_wand replayed, bit-exact sums for >= 3 terms
 NO_TERM = 0xFFFFFFFF
 
 
@@ -63,6 +63,15 @@ _libm.logf.argtypes = [C.c_float]
 
 def _logf(x):
     return _libm.logf(float(x))
+
+
+def idf_array(doc_freq, doc_count, tantivy_weight=False):
+    """idf (or Bm25Weight.weight = idf * (1 + K1)) for an array of doc_freqs through the library's host helper: the same f32
+    expression and C-library logf as `idf`, without an interpreter round trip per value."""
+    df = np.ascontiguousarray(doc_freq, np.uint32)
+    out = np.empty(df.shape, np.float32)
+    check(lib().sb200_bm25_idf(df.ctypes.data, df.size, int(doc_count), 1 if tantivy_weight else 0, out.ctypes.data))
+    return out
 
 
 def compute_tf_cache(average_fieldnorm, k1=K1, b=B_):
@@ -252,10 +261,7 @@ class TopDocs:
         term_ords = np.ascontiguousarray(term_ords, np.uint32)
         nq, nt = term_ords.shape
         if weights is None:  # Bm25Weight::for_terms with the segment's own statistics (bm25.rs:98-134)
-            df = segment.doc_freq[np.minimum(term_ords, segment.n_terms - 1)]
-            uniq, inv = np.unique(df, return_inverse=True)  # one scalar idf per distinct doc_freq
-            w_u = np.array([np.float32(idf(int(d), segment.max_doc) * (np.float32(1.0) + K1)) for d in uniq], np.float32)
-            weights = w_u[inv].reshape(nq, nt)
+            weights = idf_array(segment.doc_freq[np.minimum(term_ords, segment.n_terms - 1)], segment.max_doc, tantivy_weight=True)
         weights = np.ascontiguousarray(weights, np.float32)
         cache = compute_tf_cache(segment.average_fieldnorm if average_fieldnorm is None else average_fieldnorm)
         k = self.limit + self.offset
@@ -352,10 +358,7 @@ class SignalComputer:
         term_ords = np.ascontiguousarray(term_ords, np.uint32)
         nq, nt = term_ords.shape
         if weights is None:
-            df = seg.doc_freq[np.minimum(term_ords, seg.n_terms - 1)]
-            uniq, inv = np.unique(df, return_inverse=True)  # one scalar idf per distinct doc_freq
-            w_u = np.array([idf(int(d), seg.max_doc) for d in uniq], np.float32)
-            weights = w_u[inv].reshape(nq, nt)
+            weights = idf_array(seg.doc_freq[np.minimum(term_ords, seg.n_terms - 1)], seg.max_doc)
         weights = np.ascontiguousarray(weights, np.float32)
         cache = compute_tf_cache(seg.average_fieldnorm if average_fieldnorm is None else average_fieldnorm, self.k1, self.b)
         docs = host_out((nq, k), np.uint32); totals = host_out((nq, k), np.float64); n_out = np.zeros(nq, np.uint32)

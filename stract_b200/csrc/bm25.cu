@@ -52,7 +52,7 @@ struct sb200_segment {
   sb200::DevBuf<uint64_t> t_data_off, t_end_off;
   sb200::DevBuf<uint32_t> t_df, t_first;
   sb200::DevBuf<uint32_t> b_last, b_off;
-  sb200::DevBuf<uint16_t> b_bits;
+  sb200::DevBuf<uint16_t> b_bits, b_bw;   // b_bw: the block-wand (fieldnorm id | tf << 8) pair of every skip entry
   std::vector<uint32_t> h_df;  // host copy (query planning: Intersection sorts by size_hint)
   // per-batch scratch (grown on demand)
   sb200::DevBuf<uint32_t> q_terms, q_nterms, o_docs, o_n, q_orig;
@@ -94,7 +94,7 @@ struct SegView {
 __global__ void k_build_directory(const uint8_t* __restrict__ postings, const sb200_term_info* __restrict__ terms,
                                   uint32_t n_terms, int stride, const uint32_t* __restrict__ t_first,
                                   uint64_t* t_data_off, uint64_t* t_end_off, uint32_t* t_df, uint32_t* b_last,
-                                  uint32_t* b_off, uint16_t* b_bits, uint64_t postings_len, int* err) {
+                                  uint32_t* b_off, uint16_t* b_bits, uint16_t* b_bw, uint64_t postings_len, int* err) {
   const uint32_t t = (blockIdx.x * (uint32_t)blockDim.x + threadIdx.x) >> 5;
   if (t >= n_terms) return;
   const uint32_t lane = threadIdx.x & 31;
@@ -115,7 +115,7 @@ __global__ void k_build_directory(const uint8_t* __restrict__ postings, const sb
   uint32_t run = 0;
   for (uint32_t base = 0; base < nfull; base += 32) {
     const uint32_t j = base + lane;
-    uint32_t size = 0, last = 0; uint16_t bits = 0;
+    uint32_t size = 0, last = 0; uint16_t bits = 0, bw = 0;
     if (j < nfull) {
       const uint8_t* e = postings + skip_start + (uint64_t)j * stride;  // skip.rs:186-238
       last = (uint32_t)e[0] | ((uint32_t)e[1] << 8) | ((uint32_t)e[2] << 16) | ((uint32_t)e[3] << 24);
@@ -123,15 +123,16 @@ __global__ void k_build_directory(const uint8_t* __restrict__ postings, const sb
       const uint32_t tb = (stride >= 8) ? e[5] : 0u;
       bits = (uint16_t)(db | (strict << 6) | (tb << 8));
       size = (db + tb) * 16u;
+      if (stride >= 8) { const int o = stride == 12 ? 10 : 6; bw = (uint16_t)(e[o] | ((uint32_t)e[o + 1] << 8)); }   // skip.rs:203-232
       if (db > 32 || tb > 32) *err = 3;
     }
     uint32_t incl = size;
     for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
-    if (j < nfull) { b_last[first + j] = last; b_bits[first + j] = bits; b_off[first + j] = run + incl - size; }
+    if (j < nfull) { b_last[first + j] = last; b_bits[first + j] = bits; b_bw[first + j] = bw; b_off[first + j] = run + incl - size; }
     run += __shfl_sync(0xffffffffu, incl, 31);
   }
   if (lane == 0) {
-    b_off[first + nfull] = run; b_last[first + nfull] = TERMINATED; b_bits[first + nfull] = 0;
+    b_off[first + nfull] = run; b_last[first + nfull] = TERMINATED; b_bits[first + nfull] = 0; b_bw[first + nfull] = 0;
     if (data_off + run > off + len) *err = 4;
   }
 }
@@ -608,6 +609,7 @@ static int launch_topk_warp(const WParams& P, cudaStream_t s) {
 #include "bm25_and3.cuh"
 #include "bm25_or3.cuh"
 #include "bm25_multi.cuh"
+#include "bm25_wand.cuh"
 namespace sb200 {
 
 static void seg_view(const sb200_segment* g, SegView& S) {
@@ -836,6 +838,7 @@ static int run_and3(sb200_segment* g, const Params& P, const std::vector<uint32_
     const uint32_t n_units = (uint32_t)units.size();
     SB_TRY(ensure(g->a3_key, (size_t)std::max<uint64_t>(entries, 1))); SB_TRY(ensure(g->a3_doc, (size_t)std::max<uint64_t>(entries, 1)));
     SB_TRY(ensure(g->a3_units, std::max<size_t>(n_units, 1)));
+    if (g0 == 0) SB_CUDA(cudaEventRecord(g->evk0, s));   // kernel_ms starts here: the unit list above is host planning
     SB_CUDA(cudaMemcpyAsync(g->a3_off.p + g0, off.data() + g0, (size_t)(g1 - g0) * 8, cudaMemcpyHostToDevice, s));
     SB_CUDA(cudaMemsetAsync(g->a3_cnt.p + g0, 0, (size_t)(g1 - g0) * 4, s));
     if (n_units) {
@@ -847,7 +850,10 @@ static int run_and3(sb200_segment* g, const Params& P, const std::vector<uint32_
       A.units = (const AUnit*)g->a3_units.p; A.n_units = n_units;
       A.cand_off = g->a3_off.p; A.cand_cnt = g->a3_cnt.p; A.c_key = g->a3_key.p; A.c_doc = g->a3_doc.p;
       A.counters = P.counters;
-      SB_LAUNCH(k_and3, div_up(n_units, A3_WARPS), A3_WARPS * 32, 0, s, A);
+      static const int occ = [] { const char* e = getenv("SB200_AND3_OCC"); return e ? atoi(e) : 5; }();
+      if (occ >= 8) SB_LAUNCH(k_and3<8>, div_up(n_units, A3_WARPS), A3_WARPS * 32, 0, s, A);
+      else if (occ >= 6) SB_LAUNCH(k_and3<6>, div_up(n_units, A3_WARPS), A3_WARPS * 32, 0, s, A);
+      else SB_LAUNCH(k_and3<5>, div_up(n_units, A3_WARPS), A3_WARPS * 32, 0, s, A);
       SB_CHECK_LAUNCH();
     }
     SB_LAUNCH(k_and3_select, g1 - g0, 256, sel_smem, s, g->a3_off.p, g->a3_cnt.p, g->a3_key.p, g->a3_doc.p, P.q_orig, g0, k,
@@ -904,7 +910,8 @@ static int run_batch(sb200_segment* g, const sb200_bm25_batch* b, int mode, cons
   std::vector<MergeJob> jobs;
   uint32_t extra = 0, capm = 0;
   {
-    const bool can_split = !(sb && sb->max_docs) && getenv("SB200_BM25_CTA") == nullptr && getenv("SB200_BM25_NOSPLIT") == nullptr;
+    const bool can_split = !(sb && sb->max_docs) && !(!sb && mode == SB200_MODE_OR_WAND) && getenv("SB200_BM25_CTA") == nullptr &&
+                           getenv("SB200_BM25_NOSPLIT") == nullptr;   // a replayed history cannot be cut into doc ranges
     const uint64_t target = std::max<uint64_t>(32768, postings / std::max<uint32_t>(nq, 1));
     const uint32_t wmax = std::max<uint32_t>(1, std::min<uint32_t>(16, 16384 / k));
     it_q.reserve(nq + 64); it_lo.reserve(nq + 64); it_hi.reserve(nq + 64); it_out.reserve(nq + 64);
@@ -967,7 +974,21 @@ static int run_batch(sb200_segment* g, const sb200_bm25_batch* b, int mode, cons
       P.sig = sb->signals->rows.p; P.n_cols = sb->signals->n_cols; P.coeffs = g->q_coeffs.p;
     }
   }
-  if (!sb && mode != SB200_MODE_AND && mode != SB200_MODE_OR) SB_FAIL(SB200_EINVAL, "mode %d", mode);
+  if (!sb && mode != SB200_MODE_AND && mode != SB200_MODE_OR && mode != SB200_MODE_OR_WAND) SB_FAIL(SB200_EINVAL, "mode %d", mode);
+  if (!sb && mode == SB200_MODE_OR_WAND) {
+    // block_wand replayed (bm25_wand.cuh): one warp per query slot, the reference's own pruning and summation order
+    if (g->record < 1) SB_FAIL(SB200_EINVAL, "Block-WAND needs term frequencies (record option WithFreqs or above)");
+    uint32_t wcap = 2; while (wcap < 2 * k) wcap <<= 1;
+    SB_TRY(ensure(g->g_khi, (size_t)nq * wcap)); SB_TRY(ensure(g->g_klo, (size_t)nq * wcap));
+    WandParams W;
+    memset(&W, 0, sizeof(W));
+    W.S = P.S; W.b_bw = g->b_bw.p; W.a128 = g->a_post.p; W.t_aoff = g->t_aoff.p;
+    W.q_terms = P.q_terms; W.q_nterms = P.q_nterms; W.q_weights = P.q_weights; W.cache = P.cache; W.q_orig = P.q_orig;
+    W.n_queries = nq; W.n_terms_max = nt; W.k = k; W.cap = wcap;
+    W.g_khi = g->g_khi.p; W.g_klo = g->g_klo.p; W.o_docs = P.o_docs; W.o_scores = P.o_scores; W.o_n = P.o_n; W.counters = P.counters;
+    SB_LAUNCH(k_wand, div_up(nq, WD_WARPS), WD_WARPS * 32, 0, s, W);
+    SB_CHECK_LAUNCH();
+  } else {
   const int kmode = sb ? 2 : mode;
   static const bool use_cta_kernel = getenv("SB200_BM25_CTA") != nullptr;  // the first-generation CTA-per-query kernel
   if (use_cta_kernel) {
@@ -1008,6 +1029,7 @@ static int run_batch(sb200_segment* g, const sb200_bm25_batch* b, int mode, cons
              SB_LAUNCH(k_merge_topk<0>, (unsigned)jobs.size(), 256, msm, s, g->q_jobs.p, k, capm, P.o_docs, P.o_scores, P.o_totals, P.o_n); }
       SB_CHECK_LAUNCH();
     }
+  }
   }
   SB_CUDA(cudaEventRecord(g->evk1, s));
   SB_CUDA(cudaMemcpyAsync(docs, g->o_docs.p, (size_t)nq * k * 4, cudaMemcpyDefault, s));
@@ -1141,7 +1163,7 @@ int sb200_segment_create(const uint8_t* postings_file, uint64_t postings_len, co
     first[n_terms] = (uint32_t)slots;
     g->n_blocks = slots - n_terms; g->n_postings = postings;
     SB_TRY(g->t_first.alloc(n_terms + 1)); SB_TRY(g->t_data_off.alloc(n_terms + 1)); SB_TRY(g->t_end_off.alloc(n_terms + 1)); SB_TRY(g->t_df.alloc(n_terms + 1));
-    SB_TRY(g->b_last.alloc(slots + 1)); SB_TRY(g->b_off.alloc(slots + 1)); SB_TRY(g->b_bits.alloc(slots + 1));
+    SB_TRY(g->b_last.alloc(slots + 1)); SB_TRY(g->b_off.alloc(slots + 1)); SB_TRY(g->b_bits.alloc(slots + 1)); SB_TRY(g->b_bw.alloc(slots + 1));
     SB_CUDA(cudaMemcpyAsync(g->t_first.p, first.data(), (size_t)(n_terms + 1) * 4, cudaMemcpyHostToDevice, s));
     DevBuf<sb200_term_info> d_terms; DevBuf<int> d_err;
     SB_TRY(d_terms.alloc(n_terms + 1)); SB_TRY(d_err.alloc(1));
@@ -1149,7 +1171,7 @@ int sb200_segment_create(const uint8_t* postings_file, uint64_t postings_len, co
     SB_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), s));
     if (n_terms) {
       SB_LAUNCH(k_build_directory, div_up((uint64_t)n_terms * 32, 256), 256, 0, s, g->postings.p, d_terms.p, n_terms, g->stride,
-                g->t_first.p, g->t_data_off.p, g->t_end_off.p, g->t_df.p, g->b_last.p, g->b_off.p, g->b_bits.p, postings_len, d_err.p);
+                g->t_first.p, g->t_data_off.p, g->t_end_off.p, g->t_df.p, g->b_last.p, g->b_off.p, g->b_bits.p, g->b_bw.p, postings_len, d_err.p);
       SB_CHECK_LAUNCH();
     }
     int h_err = 0;
@@ -1206,7 +1228,7 @@ int sb200_segment_get_info(const sb200_segment* g, sb200_segment_info* info) {
   if (!g || !info) SB_FAIL(SB200_EINVAL, "NULL argument");
   info->n_terms = g->n_terms; info->n_blocks = g->n_blocks; info->n_postings = g->n_postings; info->max_doc = g->max_doc; info->_pad = 0;
   info->hbm_bytes = g->postings.bytes() + g->fieldnorm.bytes() + g->t_first.bytes() + g->t_data_off.bytes() + g->t_end_off.bytes() +
-                    g->t_df.bytes() + g->b_last.bytes() + g->b_off.bytes() + g->b_bits.bytes();
+                    g->t_df.bytes() + g->b_last.bytes() + g->b_off.bytes() + g->b_bits.bytes() + g->b_bw.bytes();
   info->stage_ms = g->stage_ms;
   return SB200_OK;
 }

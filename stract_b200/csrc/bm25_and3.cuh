@@ -1,5 +1,5 @@
-// bm25_and3.cuh -- AND queries, third generation (opt-in: SB200_BM25_AND3=1; written without a GPU at hand, the
-// default stays k_topk_warp<AND> until this has been run through tests/test_bm25_gpu.py).
+// bm25_and3.cuh -- AND queries, third generation (the default AND kernel since round 2: bit-identical to
+// k_topk_warp<AND> on hardware and 2x faster on the C4 batch; SB200_BM25_AND3=0 switches back).
 //
 // Why: a CPU emulation of k_topk_warp<AND> on the C4 batch (10k 2-term queries) counts 4.1 M rounds of ~250 per
 // work item, evenly spread -- no tail -- yet the kernel needs 14 ms: ~12 us per round.  A round there is ~1500
@@ -161,7 +161,11 @@ __device__ __forceinline__ float a3_term_score(float weight, uint32_t tf, float 
   return __fmul_rn(weight, __fdiv_rn(t, __fadd_rn(t, norm)));   // Bm25Weight::score, bm25.rs:182-196
 }
 
-__global__ void __launch_bounds__(A3_WARPS * 32) k_and3(const A3Params P) {
+// MINB = resident CTAs per SM the register allocation aims for (5: 96 registers, no spill; 6: 80; 8: 64 with a small spill).
+// ncu on the C4 batch: 27 % warps active at 96 registers with the issue slots 47 % busy -- the kernel lives on latency
+// hiding, so the occupancy variants are kept selectable (SB200_AND3_OCC) until one is measured to win.
+template <int MINB>
+__global__ void __launch_bounds__(A3_WARPS * 32, MINB) k_and3(const A3Params P) {
   __shared__ float cache[256];
   __shared__ __align__(16) uint32_t s_docs[A3_WARPS][128];
   __shared__ __align__(16) uint32_t s_tfs[A3_WARPS][128];

@@ -119,6 +119,20 @@ extern "C" {
 uint32_t sb200_fieldnorm_id_to_value(uint8_t id) { return sb200::fieldnorm_value(id); }
 uint8_t sb200_fieldnorm_value_to_id(uint32_t v) { return sb200::fieldnorm_id(v); }
 
+// idf of tantivy/src/query/bm25.rs:52-56 == core/src/ranking/bm25.rs:23-27 for a whole array of doc_freqs, in f32 with the C
+// library's logf (what Rust's f32::ln lowers to on Linux); tantivy_weight != 0 multiplies by (1 + K1) like Bm25Weight
+// (bm25.rs:161-162).  Host code: a batch's weights no longer cost one interpreter round trip per distinct doc_freq.
+int sb200_bm25_idf(const uint32_t* doc_freq, uint64_t n, uint64_t doc_count, int tantivy_weight, float* out) {
+  if ((n && (!doc_freq || !out))) { sb200::set_error("NULL argument"); return SB200_EINVAL; }
+  for (uint64_t i = 0; i < n; i++) {
+    if (doc_freq[i] > doc_count) { sb200::set_error("doc_freq %u > doc_count %llu", doc_freq[i], (unsigned long long)doc_count); return SB200_EINVAL; }
+    const volatile float x = ((float)(doc_count - doc_freq[i]) + 0.5f) / ((float)doc_freq[i] + 0.5f);
+    const volatile float l = logf(1.0f + x);
+    out[i] = tantivy_weight ? l * (1.0f + 1.2f) : l;
+  }
+  return SB200_OK;
+}
+
 int sb200_postings_encode(const uint32_t* docs, const uint32_t* tfs, const uint64_t* term_off, uint32_t n_terms,
                           const uint8_t* fieldnorm_ids, uint32_t max_doc, float avg_fieldnorm, uint8_t* out,
                           uint64_t out_cap, uint64_t* out_len, sb200_term_info* infos, int threads) {

@@ -104,3 +104,7 @@ def test_multi_field_signals_against_oracle(emulated):
     import test_multi_signal_gpu as M
     M.test_multi_field_signals_bit_exact()
     M.test_signal_compute_order_mirror()
+
+
+def test_block_wand_replay_against_oracle(emulated):
+    emulated.test_or_wand_replay_matches_block_wand_bit_for_bit()

@@ -264,3 +264,41 @@ def test_or3_union_kernel_matches_default_kernel(monkeypatch):
         assert np.array_equal(an, bn)
         for q in range(80):
             assert np.array_equal(ad[q, :an[q]], bd[q, :bn[q]]) and np.array_equal(at[q, :an[q]], bt[q, :bn[q]]), (ncols, q)
+
+
+def test_or_wand_replay_matches_block_wand_bit_for_bit():
+    """SB200_MODE_OR_WAND: tantivy's block_wand replayed on the device -- docs, order and f32 score bits equal the oracle's
+    block_wand (mode 1) for 1..8 terms, small and large k, tie-heavy data (few distinct lengths / tfs)."""
+    from stract_b200.bm25 import MODE_OR_WAND
+    rng = np.random.default_rng(77)
+    max_doc = 50_000
+    lens = rng.choice([3, 5, 8, 13, 40], max_doc).astype(np.uint32)          # few fieldnorms: many exactly tied term scores
+    dfs = [1, 40, 127, 128, 129, 500, 2000, 2600, 9000, 20000, 30000]
+    td, tt = [], []
+    for df in dfs:
+        td.append(np.sort(rng.choice(max_doc, df, replace=False)).astype(np.uint32))
+        tt.append(rng.choice([1, 1, 1, 2, 3], df).astype(np.uint32))
+    oseg, seg = build(td, tt, lens)
+    flips = 0
+    for width, k in ((1, 10), (2, 25), (3, 10), (3, 300), (5, 10), (5, 1000), (8, 100)):
+        nq = 12
+        terms = np.stack([rng.choice(len(dfs), width, replace=False) for _ in range(nq)]).astype(np.uint32)
+        d, s, n = TopDocs.with_limit(k).search_batch(seg, terms, MODE_OR_WAND)
+        dx, sx, nx = TopDocs.with_limit(k).search_batch(seg, terms, MODE_OR)
+        for q in range(nq):
+            w, caches = weights_for(seg, terms[q])
+            od, os_, _ = oseg.topk(terms[q], w, caches, 1, k)      # oracle mode 1 = block_wand
+            m = int(n[q])
+            assert m == len(od), (width, k, q, m, len(od))
+            assert np.array_equal(d[q, :m], od), (width, k, q)
+            assert np.array_equal(s[q, :m], os_), (width, k, q)
+            flips += int(not np.array_equal(s[q, :m], sx[q, :m]))
+    # absent clauses are dropped like in the other modes
+    t = np.array([[10, NO_TERM, 9, 8], [NO_TERM, 7, 6, 5]], np.uint32)
+    d, s, n = TopDocs.with_limit(50).search_batch(seg, t, MODE_OR_WAND)
+    for q in range(2):
+        qq = [int(x) for x in t[q] if x != NO_TERM]
+        w, caches = weights_for(seg, qq)
+        od, os_, _ = oseg.topk(np.array(qq, np.uint32), w, caches, 1, 50)
+        assert np.array_equal(d[q, :n[q]], od) and np.array_equal(s[q, :n[q]], os_)
+    print("queries whose score bits differ between the replay and the query-order union:", flips)
