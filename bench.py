@@ -653,6 +653,9 @@ def main():
             for k in ("and_top1000_10M", "or5_signals_100M"):
                 if isinstance(line["bm25"].get(k), dict) and "parity" in line["bm25"][k]:
                     parity[k] = line["bm25"][k]["parity"]
+                md = (line["bm25"].get(k) or {}).get("max_docs_250k") if isinstance(line["bm25"].get(k), dict) else None
+                if md and "parity" in md:
+                    parity[k + ".max_docs_250k"] = md["parity"]
         print(json.dumps(line))
         greens = [v.get("green") for v in parity.values() if isinstance(v, dict)]
         if any(g is False for g in greens):

@@ -181,6 +181,17 @@ def run_signal(device, peaks, max_doc=100_000_000, df_scale=2.0e7, n_queries=10_
            "roofline": {"bound": "hbm", "kernel": "k_or3<SIGNAL,5>", "achieved": alg / (kern * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                         "unit": "GB/s", "frac": alg / (kern * 1e-3) / 1e9 / peaks["hbm_gbs"], "alg_bytes_per_launch": alg, **_ncu("k_or3", max_doc == 100_000_000)},
            "index_hbm_bytes": seg.info()["hbm_bytes"], "gen_s": round(gen_s, 1)}
+    # production-shaped variant: Stract stops a segment after max_docs_considered candidates in doc order
+    # (core/src/config/defaults.rs:38-40 = 250 000; ShortCircuitQuery, tantivy/src/query/shortcircuit.rs:100-133)
+    MAXD = 250_000
+    comp.top_docs_batch(terms, k, max_docs=MAXD)
+    kms2 = []
+    for _ in range(3):
+        d2, tot2, n2, st2 = comp.top_docs_batch(terms, k, max_docs=MAXD, return_stats=True)
+        kms2.append(st2["kernel_ms"])
+    out["max_docs_250k"] = {"kernel_ms_per_batch": float(np.median(kms2)), "docs_scored": st2["docs_scored"],
+                            "queries_per_s": n_queries / (float(np.median(kms2)) * 1e-3),
+                            "note": "every query stops after its first 250 000 candidate docs (ascending doc order), then top-k of those"}
     if cpu:
         import oracle
         o = oracle.Segment(ix["fieldnorm_ids"], avg_fieldnorm=ix["avg"])
@@ -208,6 +219,8 @@ def run_signal(device, peaks, max_doc=100_000_000, df_scale=2.0e7, n_queries=10_
                                          f"oracle union + per-term seek + Stract BM25 + f64 combine + TopNComputer"}
         out["parity"] = _compare("oracle union + Stract BM25 + f64 linear combine on the full-size index (docs and f64 total bits)",
                                  (d, tot, n), (od, ot, on), t.shape[0])
+        od2, ot2, on2, _sc2 = o.signal_topk_batch(t, w, np.tile(cache, (t.size, 1)), 1.2, 0.005, cols, coeffs, k, max_docs=MAXD, threads=threads)
+        out["max_docs_250k"]["parity"] = _compare("oracle with the same max_docs short-circuit", (d2, tot2, n2), (od2, ot2, on2), t.shape[0])
         o.close()
     table.close(); seg.close()
     return out
