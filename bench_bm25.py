@@ -60,7 +60,7 @@ def _ncu(kernel, same_workload):
         return {"traffic": None}
     if not same_workload:
         return {"traffic": None}
-    return {"traffic": c["dram_bytes_per_launch"], "traffic_source": cap["source"], "limiter": c.get("note"),
+    return {"traffic": c["dram_bytes_per_launch"], "traffic_source": c.get("source", cap["source"]), "limiter": c.get("note"),
             "ncu": {k: c[k] for k in ("l2_hit_rate_pct", "warps_active_pct", "issue_active_pct", "registers") if k in c}}
 
 

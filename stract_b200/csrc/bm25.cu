@@ -73,6 +73,9 @@ struct sb200_segment {
   // scratch of the multi-field signal path (bm25_multi.cuh); lives in the FIRST field's handle
   sb200::DevBuf<uint8_t> m_fields, m_ops, m_slot_field;
   sb200::DevBuf<float> m_idf_f;
+  // sparse result tables go to the host packed (copy_out_tables)
+  sb200::DevBuf<uint32_t> p_docs, p_scores; sb200::DevBuf<uint64_t> p_off;
+  uint32_t* h_pack = nullptr; size_t h_pack_words = 0;   // page-locked staging: [n counts | offsets (u64) | docs | scores]
 };
 
 namespace sb200 {
@@ -789,15 +792,90 @@ static int run_multi(const sb200_multi_signal_batch* b, uint32_t* docs, double* 
 }
 
 // union modes through k_or3, instantiated for the smallest term-count bound that covers the batch
-template <int MODE>
-static int launch_or3(const WParams& P, cudaStream_t s) {
+template <int MODE, int MINB>
+static int launch_or3_occ(const WParams& P, cudaStream_t s) {
   const unsigned grid = div_up(P.n_items, WQ);
-  void (*kern)(const WParams) = k_or3<MODE, 8>;
-  if (P.n_terms_max <= 2) kern = k_or3<MODE, 2>;
-  else if (P.n_terms_max <= 3) kern = k_or3<MODE, 3>;
-  else if (P.n_terms_max <= 5) kern = k_or3<MODE, 5>;
+  void (*kern)(const WParams) = k_or3<MODE, 8, MINB>;
+  if (P.n_terms_max <= 2) kern = k_or3<MODE, 2, MINB>;
+  else if (P.n_terms_max <= 3) kern = k_or3<MODE, 3, MINB>;
+  else if (P.n_terms_max <= 5) kern = k_or3<MODE, 5, MINB>;
   SB_LAUNCH(kern, grid, WQ * 32, 0, s, P);
   SB_CHECK_LAUNCH();
+  return SB200_OK;
+}
+template <int MODE>
+static int launch_or3(const WParams& P, cudaStream_t s) {
+  static const int occ = [] { const char* e = getenv("SB200_OR3_OCC"); return e ? atoi(e) : 5; }();
+  if (occ >= 8) return launch_or3_occ<MODE, 8>(P, s);
+  if (occ >= 6) return launch_or3_occ<MODE, 6>(P, s);
+  return launch_or3_occ<MODE, 5>(P, s);
+}
+
+// Result tables to the caller.  An AND batch fills a fraction of its [n_queries][k] table (C4: 72 of 1000 entries per
+// query), and the dense copy of 80 MB was a third of the end-to-end time: when the tables go to host memory and are
+// less than half full, the valid prefixes are packed on the device, cross PCIe as one block and are scattered into the
+// caller's tables by the host.  f32 scores only (path A); dense copy otherwise.
+__global__ void k_pack_tables(const uint32_t* __restrict__ o_n, const uint64_t* __restrict__ off, const uint32_t* __restrict__ o_docs,
+                              const float* __restrict__ o_scores, uint32_t k, uint32_t* p_docs, uint32_t* p_scores) {
+  const uint32_t q = blockIdx.x, n = o_n[q];
+  const uint64_t base = off[q];
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    p_docs[base + i] = o_docs[(size_t)q * k + i];
+    p_scores[base + i] = __float_as_uint(o_scores[(size_t)q * k + i]);
+  }
+}
+static int copy_out_tables(sb200_segment* g, uint32_t nq, uint32_t k, uint32_t* docs, float* scores, double* totals, uint32_t* n_out) {
+  cudaStream_t s = g->stream;
+  const bool sparse_ok = scores && !totals && !is_device_ptr(docs) && !is_device_ptr(scores) && !is_device_ptr(n_out) &&
+                         (size_t)nq * k >= (getenv("SB200_BM25_PACK_MIN") ? (size_t)atol(getenv("SB200_BM25_PACK_MIN")) : ((size_t)1 << 18)) &&
+                         getenv("SB200_BM25_DENSE_OUT") == nullptr;
+  if (sparse_ok) {
+    const size_t head = (size_t)nq + 2 * (size_t)nq;   // counts (u32) + offsets (u64 as two words)
+    if (g->h_pack_words < head) {
+      if (g->h_pack) cudaFreeHost(g->h_pack);
+      g->h_pack = nullptr; g->h_pack_words = 0;
+      SB_CUDA(cudaMallocHost((void**)&g->h_pack, (head + 1024) * 4));
+      g->h_pack_words = head + 1024;
+    }
+    SB_CUDA(cudaMemcpyAsync(g->h_pack, g->o_n.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    uint64_t total = 0;
+    std::vector<uint64_t> off(nq);
+    for (uint32_t q = 0; q < nq; q++) { off[q] = total; total += g->h_pack[q]; }
+    if (total * 2 < (uint64_t)nq * k) {
+      memcpy(n_out, g->h_pack, (size_t)nq * 4);
+      if (total == 0) return SB200_OK;
+      SB_TRY(ensure(g->p_off, nq)); SB_TRY(ensure(g->p_docs, (size_t)total)); SB_TRY(ensure(g->p_scores, (size_t)total));
+      const size_t need = head + 2 * (size_t)total;
+      if (g->h_pack_words < need) {
+        cudaFreeHost(g->h_pack); g->h_pack = nullptr; g->h_pack_words = 0;
+        SB_CUDA(cudaMallocHost((void**)&g->h_pack, (need + (need >> 2)) * 4));
+        g->h_pack_words = need + (need >> 2);
+      }
+      SB_CUDA(cudaMemcpyAsync(g->p_off.p, off.data(), (size_t)nq * 8, cudaMemcpyHostToDevice, s));
+      SB_LAUNCH(k_pack_tables, nq, 128, 0, s, g->o_n.p, g->p_off.p, g->o_docs.p, g->o_scores.p, k, g->p_docs.p, g->p_scores.p);
+      SB_CHECK_LAUNCH();
+      uint32_t* hd = g->h_pack + head; uint32_t* hs = hd + total;
+      SB_CUDA(cudaMemcpyAsync(hd, g->p_docs.p, (size_t)total * 4, cudaMemcpyDeviceToHost, s));
+      SB_CUDA(cudaMemcpyAsync(hs, g->p_scores.p, (size_t)total * 4, cudaMemcpyDeviceToHost, s));
+      SB_CUDA(cudaStreamSynchronize(s));
+      for (uint32_t q = 0; q < nq; q++) {
+        const uint32_t n = n_out[q];
+        if (!n) continue;
+        memcpy(docs + (size_t)q * k, hd + off[q], (size_t)n * 4);
+        memcpy(scores + (size_t)q * k, hs + off[q], (size_t)n * 4);
+      }
+      return SB200_OK;
+    }
+    memcpy(n_out, g->h_pack, (size_t)nq * 4);
+    SB_CUDA(cudaMemcpyAsync(docs, g->o_docs.p, (size_t)nq * k * 4, cudaMemcpyDefault, s));
+    SB_CUDA(cudaMemcpyAsync(scores, g->o_scores.p, (size_t)nq * k * 4, cudaMemcpyDefault, s));
+    return SB200_OK;
+  }
+  SB_CUDA(cudaMemcpyAsync(docs, g->o_docs.p, (size_t)nq * k * 4, cudaMemcpyDefault, s));
+  if (totals) SB_CUDA(cudaMemcpyAsync(totals, g->o_totals.p, (size_t)nq * k * 8, cudaMemcpyDefault, s));
+  else if (scores) SB_CUDA(cudaMemcpyAsync(scores, g->o_scores.p, (size_t)nq * k * 4, cudaMemcpyDefault, s));
+  SB_CUDA(cudaMemcpyAsync(n_out, g->o_n.p, (size_t)nq * 4, cudaMemcpyDefault, s));
   return SB200_OK;
 }
 
@@ -850,7 +928,7 @@ static int run_and3(sb200_segment* g, const Params& P, const std::vector<uint32_
       A.units = (const AUnit*)g->a3_units.p; A.n_units = n_units;
       A.cand_off = g->a3_off.p; A.cand_cnt = g->a3_cnt.p; A.c_key = g->a3_key.p; A.c_doc = g->a3_doc.p;
       A.counters = P.counters;
-      static const int occ = [] { const char* e = getenv("SB200_AND3_OCC"); return e ? atoi(e) : 5; }();
+      static const int occ = [] { const char* e = getenv("SB200_AND3_OCC"); return e ? atoi(e) : 8; }();   // C4: 3.66 / 3.51 / 3.09 ms at 5 / 6 / 8
       if (occ >= 8) SB_LAUNCH(k_and3<8>, div_up(n_units, A3_WARPS), A3_WARPS * 32, 0, s, A);
       else if (occ >= 6) SB_LAUNCH(k_and3<6>, div_up(n_units, A3_WARPS), A3_WARPS * 32, 0, s, A);
       else SB_LAUNCH(k_and3<5>, div_up(n_units, A3_WARPS), A3_WARPS * 32, 0, s, A);
@@ -1032,10 +1110,7 @@ static int run_batch(sb200_segment* g, const sb200_bm25_batch* b, int mode, cons
   }
   }
   SB_CUDA(cudaEventRecord(g->evk1, s));
-  SB_CUDA(cudaMemcpyAsync(docs, g->o_docs.p, (size_t)nq * k * 4, cudaMemcpyDefault, s));
-  if (totals) SB_CUDA(cudaMemcpyAsync(totals, g->o_totals.p, (size_t)nq * k * 8, cudaMemcpyDefault, s));
-  else if (scores) SB_CUDA(cudaMemcpyAsync(scores, g->o_scores.p, (size_t)nq * k * 4, cudaMemcpyDefault, s));
-  SB_CUDA(cudaMemcpyAsync(n_out, g->o_n.p, (size_t)nq * 4, cudaMemcpyDefault, s));
+  SB_TRY(copy_out_tables(g, nq, k, docs, scores, totals, n_out));
   unsigned long long h[4] = {0, 0, 0, 0};
   SB_CUDA(cudaMemcpyAsync(h, g->counters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
   SB_CUDA(cudaEventRecord(g->ev1, s));
@@ -1219,6 +1294,7 @@ void sb200_segment_destroy(sb200_segment* g) {
   if (g->ev1) cudaEventDestroy(g->ev1);
   if (g->evk0) cudaEventDestroy(g->evk0);
   if (g->evk1) cudaEventDestroy(g->evk1);
+  if (g->h_pack) cudaFreeHost(g->h_pack);
   cudaStream_t s = g->stream;
   delete g;
   if (s) cudaStreamDestroy(s);

@@ -163,7 +163,7 @@ __device__ __forceinline__ float a3_term_score(float weight, uint32_t tf, float 
 
 // MINB = resident CTAs per SM the register allocation aims for (5: 96 registers, no spill; 6: 80; 8: 64 with a small spill).
 // ncu on the C4 batch: 27 % warps active at 96 registers with the issue slots 47 % busy -- the kernel lives on latency
-// hiding, so the occupancy variants are kept selectable (SB200_AND3_OCC) until one is measured to win.
+// hiding: measured on the C4 batch 3.66 / 3.51 / 3.09 ms at MINB 5 / 6 / 8, so 8 is the default (SB200_AND3_OCC selects).
 template <int MINB>
 __global__ void __launch_bounds__(A3_WARPS * 32, MINB) k_and3(const A3Params P) {
   __shared__ float cache[256];

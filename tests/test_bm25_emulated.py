@@ -108,3 +108,7 @@ def test_multi_field_signals_against_oracle(emulated):
 
 def test_block_wand_replay_against_oracle(emulated):
     emulated.test_or_wand_replay_matches_block_wand_bit_for_bit()
+
+
+def test_packed_result_copy(emulated, monkeypatch):
+    emulated.test_packed_result_copy_equals_dense(monkeypatch)

@@ -302,3 +302,19 @@ def test_or_wand_replay_matches_block_wand_bit_for_bit():
         od, os_, _ = oseg.topk(np.array(qq, np.uint32), w, caches, 1, 50)
         assert np.array_equal(d[q, :n[q]], od) and np.array_equal(s[q, :n[q]], os_)
     print("queries whose score bits differ between the replay and the query-order union:", flips)
+
+
+def test_packed_result_copy_equals_dense(monkeypatch):
+    """Sparse AND tables leave the device packed (copy_out_tables); same docs / scores / counts as the dense copy."""
+    dfs = [1, 5, 127, 128, 129, 300, 1000, 1280, 5000, 12000]
+    (oseg, seg), rng = random_index(91, 60_000, dfs)
+    terms = np.stack([rng.choice(len(dfs), 2, replace=False) for _ in range(64)]).astype(np.uint32)
+    monkeypatch.setenv("SB200_BM25_DENSE_OUT", "1")
+    d0, s0, n0 = TopDocs.with_limit(500).search_batch(seg, terms, MODE_AND)
+    d0, s0, n0 = d0.copy(), s0.copy(), n0.copy()
+    monkeypatch.delenv("SB200_BM25_DENSE_OUT")
+    monkeypatch.setenv("SB200_BM25_PACK_MIN", "1")
+    d1, s1, n1 = TopDocs.with_limit(500).search_batch(seg, terms, MODE_AND)
+    assert np.array_equal(n0, n1) and int(n1.sum()) * 2 < terms.shape[0] * 500
+    for q in range(terms.shape[0]):
+        assert np.array_equal(d0[q, :n0[q]], d1[q, :n1[q]]) and np.array_equal(s0[q, :n0[q]], s1[q, :n1[q]])
