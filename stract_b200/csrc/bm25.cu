@@ -945,6 +945,7 @@ static int run_and3(sb200_segment* g, const Params& P, const std::vector<uint32_
 
 static int run_batch(sb200_segment* g, const sb200_bm25_batch* b, int mode, const sb200_signal_batch* sb, uint32_t* docs,
                      float* scores, double* totals, uint32_t* n_out, sb200_bm25_stats* stats) {
+  NvtxRange nvtx(sb ? "sb200 signal top-k batch" : "sb200 bm25 top-k batch");
   cudaStream_t s = g->stream;
   if (!b || !b->term_ords || !b->weights || !b->tf_cache256 || !docs || !n_out) SB_FAIL(SB200_EINVAL, "NULL argument");
   const uint32_t nq = b->n_queries, nt = b->n_terms, k = b->k;

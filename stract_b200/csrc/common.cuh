@@ -2,6 +2,7 @@
 #pragma once
 #ifndef SB200_EMU   // tests/emu builds the same sources for a CPU SIMT emulator and force-includes its own shim
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #endif
 #include <stdint.h>
 #include <stdio.h>
@@ -56,6 +57,18 @@ struct Err {
 #endif
 
 #define SB_CHECK_LAUNCH() SB_CUDA(cudaGetLastError())
+
+// NVTX ranges around the host-visible phases (graph staging steps, HyperBall iterations, BM25 batches): they cost a
+// few ns without a tool attached and give nsys / ncu timelines the reference's phase names (the reference
+// wraps the same phases in `tracing` spans).  Header-only NVTX v3, no extra library.
+#ifndef SB200_EMU
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+#else
+struct NvtxRange { explicit NvtxRange(const char*) {} };
+#endif
 
 extern thread_local cudaStream_t t_pool_stream;
 // opt-in slab arena (arena.h / arena.cu, SB200_ARENA=1): replaces cudaMallocAsync inside a PoolScope

@@ -420,10 +420,18 @@ static int exclusive_scan_u32(DevBuf<uint8_t>& tmp, const T* in, uint32_t* out, 
 
 // optional per-phase wall timing of the staging pipeline (SB200_STAGE_TIMING=1 prints to stderr)
 struct PhaseTimer {
-  bool on; cudaStream_t s; double t0; const char* name = nullptr;
+  bool on; cudaStream_t s; double t0; const char* name = nullptr; const char* name_nvtx = nullptr;
+#ifndef SB200_EMU
+  ~PhaseTimer() { if (name_nvtx) nvtxRangePop(); }   // an early error return leaves no range open
+#endif
   explicit PhaseTimer(cudaStream_t st) : s(st) { on = getenv("SB200_STAGE_TIMING") != nullptr; t0 = now(); }
   static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
   void mark(const char* next) {
+#ifndef SB200_EMU
+    if (name_nvtx) nvtxRangePop();
+    name_nvtx = next;
+    if (next) nvtxRangePushA(next);
+#endif
     if (!on) return;
     cudaStreamSynchronize(s);
     const double t = now();

@@ -735,6 +735,7 @@ int hb_barrier(sb200_graph* g) {
 // with_barrier: the changed counts are summed across the ranks on the device (k_barrier_count) and the step finishes
 // with the global count already applied (no sb200_hyperball_exchange_done needed).
 int hb_step_launch(sb200_graph* g, bool with_barrier) {
+  NvtxRange nvtx("sb200 hyperball iteration (launch)");
   cudaStream_t s = g->stream;
   const uint64_t N = g->N, words = (N + 31) / 32;
   if (g->step_in_flight) SB_FAIL(SB200_ESTATE, "the previous step has not been finished");
@@ -773,11 +774,14 @@ int hb_step_launch(sb200_graph* g, bool with_barrier) {
   } else {
     // sharded handles: the same lazy rule for the source-major CSR (of the owned rows); every rank sees the same
     // global changed count, so all ranks switch together (SB200_SHARDED_PUSH=0 keeps them on the pull kernels)
+    // Thresholds from the 2-GPU runs on C2 (profiles/r02_trip3_2gpu.log): the iteration after 16.6 M of 27.8 M nodes changed
+    // costs 5.0 ms as a dense pull and ~3.3 ms frontier-filtered (same 0.75 N rule as a single rank without forward CSR);
+    // the one after 0.49 M changed costs 3.5 ms as a frontier pull over all local edges but < 1 ms as a push.
     static const bool auto_push = env_flag("SB200_SHARDED_PUSH", true);
-    const bool tiny = (double)g->n_changed_prev * 64.0 <= (double)N;
+    const bool tiny = (double)g->n_changed_prev * 16.0 <= (double)N;
     if (!g->has_fwd && ((auto_push && g->reuse > 0 && g->t > 0 && tiny) || force_mode == 2)) SB_TRY(build_fwd_csr(g));
     if (g->has_fwd && tiny) mode = 2;
-    else mode = ((double)g->n_changed_prev >= 0.25 * (double)N) ? 0 : 1;
+    else mode = ((double)g->n_changed_prev >= 0.75 * (double)N) ? 0 : 1;
   }
   if (force_mode >= 0 && (force_mode < 2 || g->has_fwd)) mode = force_mode;
   g->step_mode = mode;
@@ -826,6 +830,7 @@ int hb_step_launch(sb200_graph* g, bool with_barrier) {
 }
 
 int hb_step_finish(sb200_graph* g, sb200_iter_stats* st) {
+  NvtxRange nvtx("sb200 hyperball iteration (wait)");
   cudaStream_t s = g->stream;
   if (!g->step_in_flight) SB_FAIL(SB200_ESTATE, "no step in flight");
   g->step_in_flight = false;
@@ -866,6 +871,7 @@ int hb_step(sb200_graph* g, sb200_iter_stats* st) {
 }
 
 int hb_result(sb200_graph* g, uint64_t* id_lo, uint64_t* id_hi, double* cent, uint64_t cap, uint64_t* len) {
+  NvtxRange nvtx("sb200 hyperball result");
   cudaStream_t s = g->stream;
   const uint64_t N = g->N;
   if (N == 0) { *len = 0; return SB200_OK; }

@@ -31,7 +31,7 @@ if full:
     T.test_long_rows_and_hubs()
     import test_round1_late_gpu as late
     late.test_rank_assignment_matches_store_harmonic_order()
-if os.environ.get("SB200_ARENA"):
+if os.environ.get("SB200_ARENA", "1") != "0":   # the slab arena is the default; "0" = stream-ordered pool
     r, u, p, s = (C.c_uint64(0) for _ in range(4))
     L.sb200_arena_stats.argtypes = [C.c_int] + [C.POINTER(C.c_uint64)] * 4
     L.sb200_arena_stats(0, C.byref(r), C.byref(u), C.byref(p), C.byref(s))
