@@ -558,8 +558,9 @@ def main():
             del r
         barrier()
         per_step, tot, d2h, walls, last_r = [], 0, 0, [], None
+        r = None
         for _ in range(args.e2e_steps):
-            last_r = None   # the caller drops a result before it asks for the next one (its page-locked block is reused)
+            last_r = r = None   # the caller drops a result before it asks for the next one (its page-locked block is reused)
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
             r = HarmonicCentrality.calculate(hgraph, device=local_rank)

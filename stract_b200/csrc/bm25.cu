@@ -805,7 +805,7 @@ static int launch_or3_occ(const WParams& P, cudaStream_t s) {
 }
 template <int MODE>
 static int launch_or3(const WParams& P, cudaStream_t s) {
-  static const int occ = [] { const char* e = getenv("SB200_OR3_OCC"); return e ? atoi(e) : 5; }();
+  static const int occ = [] { const char* e = getenv("SB200_OR3_OCC"); return e ? atoi(e) : 6; }();   // C5: 608 / 588 / 900 ms at 5 / 6 / 8
   if (occ >= 8) return launch_or3_occ<MODE, 8>(P, s);
   if (occ >= 6) return launch_or3_occ<MODE, 6>(P, s);
   return launch_or3_occ<MODE, 5>(P, s);

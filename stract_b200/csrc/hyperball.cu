@@ -232,6 +232,52 @@ __global__ void __launch_bounds__(256, 7) k_pull_quad(uint64_t row_begin, uint64
   publish_row(newr, bm_cur, peers, (uint32_t)row, sub, acc, changed || bm_test(bm_prev, (uint32_t)row), changed);
 }
 
+// Experiment (SB200_QUAD2=1, single-rank handles): two adjacent rows per quad, their index loads and gathers interleaved --
+// twice the loads in flight per lane for the short-row class, which ncu shows waiting on the long scoreboard (69 % of the
+// DRAM peak at 87 % occupancy).  40 registers => 6 CTAs/SM instead of 7.
+template <bool FRONTIER>
+__global__ void __launch_bounds__(256, 4) k_pull_quad2(uint64_t row_begin, uint64_t row_end,
+    const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col,
+    const uint4* __restrict__ oldr, uint4* __restrict__ newr,
+    const uint32_t* __restrict__ bm_prev, uint32_t* __restrict__ bm_cur) {
+  const uint64_t gt = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint32_t sub = threadIdx.x & 3, lane = threadIdx.x & 31;
+  const uint64_t pair = gt >> 2;
+  uint64_t rowA = row_begin + 2 * pair, rowB = rowA + 1;
+  const bool liveA = rowA < row_end, liveB = rowB < row_end;
+  if (!liveA) rowA = row_end - 1;
+  if (!liveB) rowB = row_end - 1;
+  if (__ballot_sync(0xffffffffu, liveA) == 0u) return;
+  const uint32_t a0 = liveA ? row_ptr[rowA] : 0u, a1 = liveA ? row_ptr[rowA + 1] : 0u;
+  const uint32_t b0 = liveB ? row_ptr[rowB] : 0u, b1 = liveB ? row_ptr[rowB + 1] : 0u;
+  uint4 accA = oldr[rowA * 4 + sub], accB = oldr[rowB * 4 + sub];
+  const unsigned qmask = 0xFu << (lane & ~3u);
+  const uint32_t selfA = (uint32_t)rowA, selfB = (uint32_t)rowB;
+  const uint32_t steps = max((a1 - a0 + 3u) >> 2, (b1 - b0 + 3u) >> 2);
+  uint32_t nA = (a0 + sub < a1) ? ld_stream_u32(col + a0 + sub) : selfA;
+  uint32_t nB = (b0 + sub < b1) ? ld_stream_u32(col + b0 + sub) : selfB;
+  for (uint32_t i = 0; i < steps; i++) {
+    uint32_t mA = nA, mB = nB;
+    const uint32_t ea = a0 + 4 * (i + 1) + sub, eb = b0 + 4 * (i + 1) + sub;
+    nA = (ea < a1) ? ld_stream_u32(col + ea) : selfA;
+    nB = (eb < b1) ? ld_stream_u32(col + eb) : selfB;
+    if (FRONTIER) { mA = bm_test(bm_prev, mA) ? mA : selfA; mB = bm_test(bm_prev, mB) ? mB : selfB; }
+    const uint32_t iA0 = __shfl_sync(qmask, mA, 0, 4), iA1 = __shfl_sync(qmask, mA, 1, 4), iA2 = __shfl_sync(qmask, mA, 2, 4), iA3 = __shfl_sync(qmask, mA, 3, 4);
+    const uint32_t iB0 = __shfl_sync(qmask, mB, 0, 4), iB1 = __shfl_sync(qmask, mB, 1, 4), iB2 = __shfl_sync(qmask, mB, 2, 4), iB3 = __shfl_sync(qmask, mB, 3, 4);
+    const uint4 vA0 = oldr[(uint64_t)iA0 * 4 + sub], vA1 = oldr[(uint64_t)iA1 * 4 + sub], vA2 = oldr[(uint64_t)iA2 * 4 + sub], vA3 = oldr[(uint64_t)iA3 * 4 + sub];
+    const uint4 vB0 = oldr[(uint64_t)iB0 * 4 + sub], vB1 = oldr[(uint64_t)iB1 * 4 + sub], vB2 = oldr[(uint64_t)iB2 * 4 + sub], vB3 = oldr[(uint64_t)iB3 * 4 + sub];
+    accA = vmax_u8x16(vmax_u8x16(accA, vA0), vmax_u8x16(vmax_u8x16(vA1, vA2), vA3));
+    accB = vmax_u8x16(vmax_u8x16(accB, vB0), vmax_u8x16(vmax_u8x16(vB1, vB2), vB3));
+  }
+  const uint4 ownA = oldr[rowA * 4 + sub], ownB = oldr[rowB * 4 + sub];   // re-read (L1/L2 hit) instead of holding 8 registers across the loop
+  const unsigned ballA = __ballot_sync(0xffffffffu, ne_u4(accA, ownA)), ballB = __ballot_sync(0xffffffffu, ne_u4(accB, ownB));
+  const bool chA = ((ballA >> (lane & ~3u)) & 0xFu) != 0u, chB = ((ballB >> (lane & ~3u)) & 0xFu) != 0u;
+  if (liveA && (chA || bm_test(bm_prev, selfA))) newr[rowA * 4 + sub] = accA;
+  if (liveA && chA && sub == 0) atomicOr(bm_cur + (selfA >> 5), 1u << (selfA & 31));
+  if (liveB && (chB || bm_test(bm_prev, selfB))) newr[rowB * 4 + sub] = accB;
+  if (liveB && chB && sub == 0) atomicOr(bm_cur + (selfB >> 5), 1u << (selfB & 31));
+}
+
 // ---- pull, long rows: one warp per <=CHUNK_EDGES work item ---------------------------------------------
 template <bool FRONTIER>
 // 8 CTAs/SM (<= 32 registers): at full scale the gathers are DRAM-latency bound and the kernel's speed tracks the
@@ -574,6 +620,11 @@ static int launch_pull(sb200_graph* g, const uint4* oldr, uint4* newr, const uin
   const uint64_t nq = g->quad_row_end - g->quad_row_begin;
   if (nq) {
     PROF_BEGIN(g, FQ);
+    static const bool quad2 = env_flag("SB200_QUAD2", false);
+    if (quad2 && g->world == 1 && g->col_base == 0)
+      SB_LAUNCH(k_pull_quad2<FRONTIER>, div_up(((nq + 1) / 2) * 4, 256), 256, 0, s, g->quad_row_begin, g->quad_row_end, g->row_ptr.p,
+                g->col.p, oldr, newr, bmp, bmc);
+    else
     SB_LAUNCH(k_pull_quad<FRONTIER>, div_up(nq * 4, 256), 256, 0, s, g->quad_row_begin, g->quad_row_end, g->row_ptr.p,
               g->col.p, g->col_base, oldr, newr, bmp, bmc, po);
     SB_CHECK_LAUNCH();
