@@ -134,8 +134,12 @@ SB200_API int sb200_signal_topk_batch(sb200_segment* seg, const sb200_signal_bat
  *   SB200_OP_NUMERIC   column `col` of the signal table
  * chain != 0 marks the members of an n-gram group in the reference's order (largest n first; 1 = first member):
  * score *= 0.4^hits and hits += (score > 0) (NGRAM_DAMPENING, computer/order.rs:95-135).
- * Candidates are the union of all slots' postings; top-k by (total desc, doc asc).  Limits: <= 6 fields, <= 16 slots per
- * query, <= 32 ops.  Optic rule boosts (computer/mod.rs:471-497) are not applied. */
+ * Optic rule boosts (SignalComputer::boosts, computer/mod.rs:471-497): a rule whose docset is one posting list is a slot
+ * with slot_field = field | 0x80 and its boost in slot_boost (negative = downrank); rule slots are probed for the documents
+ * being scored and never produce candidates; total *= (downrank > boost ? 1/(1 + downrank - boost) : boost - downrank + 1)
+ * with the f64 sums taken in slot order.  slot_boost may be NULL when no slot is a rule.
+ * Candidates are the union of the TEXT slots' postings; top-k by (total desc, doc asc).  Limits: <= 6 fields, <= 16 slots
+ * per query, <= 32 ops. */
 #define SB200_OP_BM25 0u
 #define SB200_OP_BM25F 1u
 #define SB200_OP_COVERAGE 2u
@@ -154,6 +158,7 @@ typedef struct {
   const sb200_signal_op* ops;         /* [n_ops], in SignalComputeOrder order */
   const sb200_signals* signals;       /* nullable unless an op is SB200_OP_NUMERIC */
   uint32_t k, _pad;
+  const double* slot_boost;           /* [n_queries*n_slots], read for rule slots only; nullable */
 } sb200_multi_signal_batch;
 SB200_API int sb200_multi_signal_topk_batch(const sb200_multi_signal_batch* batch, uint32_t* docs, double* totals, uint32_t* n_out,
                                             sb200_bm25_stats* stats);

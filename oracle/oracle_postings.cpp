@@ -652,13 +652,16 @@ ORC_API uint32_t orc_signal_topk(void* seg, const uint32_t* terms, const float* 
 // total = f64 sum of coefficient * score in op order.  Candidates = union of all slots' postings, ascending docs.
 ORC_API uint32_t orc_multi_signal_topk(uint32_t n_fields, void* const* segs, const float* const* caches, const float* k1s,
                                        const float* coefs, uint32_t n_slots, const uint8_t* slot_field, const uint32_t* slot_term,
-                                       const float* slot_idf, const float* slot_idf_f, uint32_t n_ops, const uint32_t* op_kind,
+                                       const float* slot_idf, const float* slot_idf_f, const double* slot_boost, uint32_t n_ops,
+                                       const uint32_t* op_kind,
                                        const uint32_t* op_field, const uint32_t* op_chain, const uint32_t* op_col,
                                        const double* op_coeff, const double* const* signals, uint32_t k, uint32_t* docs,
                                        double* totals, uint64_t* scored) {
   if (k == 0) return 0;
   struct Field { const Segment* seg; std::vector<Postings> post; std::vector<float> idf, idf_f; const float* cache; float k1, coef; };
   std::vector<Field> F(n_fields);
+  struct Rule { Postings docset; double boost; };   // RuleBoost (computer/mod.rs:165-172): one posting list per rule here
+  std::vector<Rule> rules;
   std::vector<Postings> cand;
   cand.reserve(n_slots);
   for (uint32_t f = 0; f < n_fields; f++) { F[f].seg = (const Segment*)segs[f]; F[f].cache = caches[f]; F[f].k1 = k1s[f]; F[f].coef = coefs[f]; }
@@ -670,6 +673,10 @@ ORC_API uint32_t orc_multi_signal_topk(uint32_t n_fields, void* const* segs, con
     } else p.open(s, term);
   };
   for (uint32_t x = 0; x < n_slots; x++) {
+    if (slot_field[x] & 0x80) {   // an optic rule's docset: probed per scored doc, never a source of candidates
+      rules.emplace_back(); open(rules.back().docset, F[slot_field[x] & 0x7F].seg, slot_term[x]); rules.back().boost = slot_boost[x];
+      continue;
+    }
     Field& fd = F[slot_field[x]];
     fd.post.emplace_back(); open(fd.post.back(), fd.seg, slot_term[x]);
     fd.idf.push_back(slot_idf[x]); fd.idf_f.push_back(slot_idf_f[x]);
@@ -731,6 +738,16 @@ ORC_API uint32_t orc_multi_signal_topk(uint32_t n_fields, void* const* segs, con
         if (sc > 0.0) hits++;
       }
       total += op_coeff[o] * sc;
+    }
+    if (slot_boost) {   // SignalComputer::boosts, computer/mod.rs:471-497 (always Some once a segment is registered)
+      double downrank = 0.0, boost = 0.0;
+      for (auto& r : rules) {
+        if (r.docset.doc() > d) continue;
+        if (r.docset.doc() == d || r.docset.seek(d) == d) {
+          if (r.boost < 0.0) downrank += std::fabs(r.boost); else boost += r.boost;
+        }
+      }
+      total *= (downrank > boost) ? 1.0 / (1.0 + (downrank - boost)) : boost - downrank + 1.0;
     }
     nscored++;
     top.push(total, d);

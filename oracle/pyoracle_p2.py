@@ -43,7 +43,7 @@ def proto(L, f):
     f("orc_bm25_topk_batch", None, vp, _u32p, _f32p, _f32p, u32, i32, u32, u32, i32, _u32p, _f32p, _u32p, _u64p)
     f("orc_signal_topk_batch", None, vp, _u32p, _f32p, _f32p, f32, u32, f64, vp, _f64p, u32, u32, u32, u32, i32, _u32p,
       _f64p, _u32p, _u64p)
-    f("orc_multi_signal_topk", u32, u32, vp, vp, _f32p, _f32p, u32, _u8p, _u32p, _f32p, _f32p, u32, _u32p, _u32p, _u32p, _u32p, _f64p,
+    f("orc_multi_signal_topk", u32, u32, vp, vp, _f32p, _f32p, u32, _u8p, _u32p, _f32p, _f32p, vp, u32, _u32p, _u32p, _u32p, _u32p, _f64p,
       vp, u32, _u32p, _f64p, C.POINTER(u64))
     f("orc_cursor_open", vp, vp, u32, f32, _f32p)
     f("orc_cursor_free", None, vp)
@@ -202,7 +202,7 @@ class Segment:
             pass
 
 
-def multi_signal_topk(segments, caches, k1s, coefs, slot_field, slot_term, slot_idf, slot_idf_f, ops, signals, k):
+def multi_signal_topk(segments, caches, k1s, coefs, slot_field, slot_term, slot_idf, slot_idf_f, ops, signals, k, slot_boost=None):
     """One query of the multi-field recall stage (orc_multi_signal_topk): `segments` = oracle Segments (one per field),
     `ops` = [(kind, field, chain, col, coeff)], `signals` = list of f64 columns.  Returns (docs, totals)."""
     L = _L()
@@ -215,11 +215,12 @@ def multi_signal_topk(segments, caches, k1s, coefs, slot_field, slot_term, slot_
     sf = np.ascontiguousarray(slot_field, np.uint8); keep = sf != 0xFF
     sf = np.ascontiguousarray(sf[keep]); st = np.ascontiguousarray(np.asarray(slot_term, np.uint32)[keep])
     i1 = np.ascontiguousarray(np.asarray(slot_idf, np.float32)[keep]); i2 = np.ascontiguousarray(np.asarray(slot_idf_f, np.float32)[keep])
+    sb = None if slot_boost is None else np.ascontiguousarray(np.asarray(slot_boost, np.float64)[keep])
     o = np.array([[a, b, c_, d] for a, b, c_, d, _ in ops], np.uint32).reshape(-1, 4)
     oc = np.array([e for *_, e in ops], np.float64)
     docs = np.zeros(k, np.uint32); totals = np.zeros(k, np.float64); sc = C.c_uint64(0)
     n = L.orc_multi_signal_topk(nf, C.cast(segs, C.c_void_p), C.cast(carr, C.c_void_p), np.ascontiguousarray(k1s, np.float32),
-                                np.ascontiguousarray(coefs, np.float32), sf.size, sf, st, i1, i2, len(ops),
+                                np.ascontiguousarray(coefs, np.float32), sf.size, sf, st, i1, i2, None if sb is None else sb.ctypes.data, len(ops),
                                 np.ascontiguousarray(o[:, 0]), np.ascontiguousarray(o[:, 1]), np.ascontiguousarray(o[:, 2]),
                                 np.ascontiguousarray(o[:, 3]), oc, C.cast(sarr, C.c_void_p), k, docs, totals, C.byref(sc))
     return docs[:n], totals[:n]

@@ -37,7 +37,8 @@ class SignalOp(C.Structure):
 class MultiSignalBatch(C.Structure):
     _fields_ = [("n_queries", C.c_uint32), ("n_slots", C.c_uint32), ("slot_field", C.c_void_p), ("slot_term", C.c_void_p),
                 ("slot_idf", C.c_void_p), ("slot_idf_f", C.c_void_p), ("n_fields", C.c_uint32), ("n_ops", C.c_uint32),
-                ("fields", C.c_void_p), ("ops", C.c_void_p), ("signals", C.c_void_p), ("k", C.c_uint32), ("_pad", C.c_uint32)]
+                ("fields", C.c_void_p), ("ops", C.c_void_p), ("signals", C.c_void_p), ("k", C.c_uint32), ("_pad", C.c_uint32),
+                ("slot_boost", C.c_void_p)]
 
 
 def proto(L, f):

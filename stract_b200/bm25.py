@@ -514,18 +514,19 @@ class MultiFieldSignalComputer:
                 c = self.coefficient(name, coef)
         return c
 
-    def top_docs_batch(self, slot_field, slot_term, k, doc_freq_all_body=None, return_stats=False):
+    def top_docs_batch(self, slot_field, slot_term, k, doc_freq_all_body=None, return_stats=False, slot_boost=None):
         """slot_field / slot_term [n_queries, n_slots]: field index into `self.names` (TextFieldEnum order; 0xFF pads) and the term's ordinal in that
         field's reader (NO_TERM = the segment does not hold it).  idf comes from the field's own doc_freq
         (MultiBm25Weight::for_terms), the Bm25F idf from `doc_freq_all_body` [n_queries, n_slots] (WeightCache: the AllBody
-        doc_freq of the token), defaulting to the field's own."""
+        doc_freq of the token), defaulting to the field's own.  Optic rules: a slot with field | 0x80 is the docset of a rule,
+        `slot_boost` [n_queries, n_slots] holds its boost (negative = downrank): SignalComputer::boosts (mod.rs:471-497)."""
         sf = np.ascontiguousarray(slot_field, np.uint8); st = np.ascontiguousarray(slot_term, np.uint32)
         nq, ns = sf.shape
         idf1 = np.zeros((nq, ns), np.float32); idf2 = np.zeros((nq, ns), np.float32)
         for q in range(nq):
             for x in range(ns):
                 f = int(sf[q, x])
-                if f == 0xFF:
+                if f == 0xFF or f & 0x80:
                     continue
                 r = self.readers[f]
                 df = int(r.doc_freq[st[q, x]]) if st[q, x] != NO_TERM and st[q, x] < r.n_terms else 0
@@ -549,6 +550,8 @@ class MultiFieldSignalComputer:
         mb.fields = C.cast(farr, C.c_void_p); mb.ops = C.cast(ops, C.c_void_p)
         mb.signals = self.signals._h if self.signals is not None else None
         mb.k = k
+        sbst = None if slot_boost is None else np.ascontiguousarray(slot_boost, np.float64)
+        mb.slot_boost = _p(sbst)
         stt = B.Bm25Stats()
         check(self._L.sb200_multi_signal_topk_batch(C.byref(mb), _p(docs), _p(totals), _p(n_out), C.byref(stt)))
         self.last_inputs = dict(idf=idf1, idf_f=idf2, caches=caches)

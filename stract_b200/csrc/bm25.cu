@@ -73,6 +73,7 @@ struct sb200_segment {
   // scratch of the multi-field signal path (bm25_multi.cuh); lives in the FIRST field's handle
   sb200::DevBuf<uint8_t> m_fields, m_ops, m_slot_field;
   sb200::DevBuf<float> m_idf_f;
+  sb200::DevBuf<double> m_boost;
   // sparse result tables go to the host packed (copy_out_tables)
   sb200::DevBuf<uint32_t> p_docs, p_scores; sb200::DevBuf<uint64_t> p_off;
   uint32_t* h_pack = nullptr; size_t h_pack_words = 0;   // page-locked staging: [n counts | offsets (u64) | docs | scores]
@@ -694,6 +695,7 @@ static int run_multi(const sb200_multi_signal_batch* b, uint32_t* docs, double* 
   std::vector<uint8_t> sf((size_t)nq * SM, 0);
   std::vector<uint32_t> st((size_t)nq * SM, SB200_NO_TERM), ns(nq, 0), order(nq);
   std::vector<float> w1((size_t)nq * SM, 0.f), w2((size_t)nq * SM, 0.f);
+  std::vector<double> wb(b->slot_boost ? (size_t)nq * SM : 0, 0.0);
   std::vector<uint64_t> work(nq, 0), work_sorted(nq, 0);
   unsigned long long postings = 0;
   for (uint32_t q = 0; q < nq; q++) {
@@ -701,9 +703,10 @@ static int run_multi(const sb200_multi_signal_batch* b, uint32_t* docs, double* 
     for (uint32_t x = 0; x < SM; x++) {
       const uint8_t f = b->slot_field[(size_t)q * SM + x];
       if (f == 0xFF) continue;
-      if (f >= NF) SB_FAIL(SB200_EINVAL, "query %u slot %u: field %u >= %u", q, x, (unsigned)f, NF);
+      if ((f & 0x7F) >= NF) SB_FAIL(SB200_EINVAL, "query %u slot %u: field %u >= %u", q, x, (unsigned)(f & 0x7F), NF);
+      if ((f & 0x80) && !b->slot_boost) SB_FAIL(SB200_EINVAL, "query %u slot %u is a rule slot but slot_boost is NULL", q, x);
       const uint32_t ord = b->slot_term[(size_t)q * SM + x];
-      if (ord != SB200_NO_TERM && ord < b->fields[f].seg->n_terms) work[q] += b->fields[f].seg->h_df[ord];
+      if (ord != SB200_NO_TERM && ord < b->fields[f & 0x7F].seg->n_terms) work[q] += b->fields[f & 0x7F].seg->h_df[ord];
     }
     postings += work[q];
   }
@@ -711,13 +714,15 @@ static int run_multi(const sb200_multi_signal_batch* b, uint32_t* docs, double* 
   for (uint32_t slot = 0; slot < nq; slot++) {
     const uint32_t q = order[slot];
     uint32_t c = 0;
-    for (uint32_t x = 0; x < SM; x++) {
-      const uint8_t f = b->slot_field[(size_t)q * SM + x];
-      if (f == 0xFF) continue;
-      const size_t o = (size_t)slot * SM + c;
-      sf[o] = f; st[o] = b->slot_term[(size_t)q * SM + x]; w1[o] = b->slot_idf[(size_t)q * SM + x]; w2[o] = b->slot_idf_f[(size_t)q * SM + x];
-      c++;
-    }
+    for (int pass = 0; pass < 2; pass++)   // text slots first (query order kept), rule docsets behind them (rule order kept)
+      for (uint32_t x = 0; x < SM; x++) {
+        const uint8_t f = b->slot_field[(size_t)q * SM + x];
+        if (f == 0xFF || ((f & 0x80) != 0) != (pass == 1)) continue;
+        const size_t o = (size_t)slot * SM + c;
+        sf[o] = f; st[o] = b->slot_term[(size_t)q * SM + x]; w1[o] = b->slot_idf[(size_t)q * SM + x]; w2[o] = b->slot_idf_f[(size_t)q * SM + x];
+        if (b->slot_boost) wb[o] = b->slot_boost[(size_t)q * SM + x];
+        c++;
+      }
     ns[slot] = c; work_sorted[slot] = work[q];
   }
   ItemPlan pl;
@@ -749,6 +754,7 @@ static int run_multi(const sb200_multi_signal_batch* b, uint32_t* docs, double* 
   SB_CUDA(cudaMemcpyAsync(g->q_terms.p, st.data(), st.size() * 4, cudaMemcpyHostToDevice, s));
   SB_CUDA(cudaMemcpyAsync(g->q_weights.p, w1.data(), w1.size() * 4, cudaMemcpyHostToDevice, s));
   SB_CUDA(cudaMemcpyAsync(g->m_idf_f.p, w2.data(), w2.size() * 4, cudaMemcpyHostToDevice, s));
+  if (b->slot_boost) { SB_TRY(ensure(g->m_boost, wb.size())); SB_CUDA(cudaMemcpyAsync(g->m_boost.p, wb.data(), wb.size() * 8, cudaMemcpyHostToDevice, s)); }
   SB_CUDA(cudaMemcpyAsync(g->q_nterms.p, ns.data(), ns.size() * 4, cudaMemcpyHostToDevice, s));
   SB_CUDA(cudaMemcpyAsync(g->q_orig.p, order.data(), (size_t)nq * 4, cudaMemcpyHostToDevice, s));
   SB_CUDA(cudaMemcpyAsync(g->q_items.p, pl.q.data(), (size_t)n_items * 4, cudaMemcpyHostToDevice, s));
@@ -762,6 +768,7 @@ static int run_multi(const sb200_multi_signal_batch* b, uint32_t* docs, double* 
   P.fields = (const MField*)g->m_fields.p; P.n_fields = NF; P.max_doc = g->max_doc;
   P.ops = (const MOp*)g->m_ops.p; P.n_ops = NO;
   P.q_slot_field = g->m_slot_field.p; P.q_slot_term = g->q_terms.p; P.q_idf = g->q_weights.p; P.q_idf_f = g->m_idf_f.p; P.q_nslots = g->q_nterms.p;
+  P.q_boost = b->slot_boost ? g->m_boost.p : nullptr;
   P.q_orig = g->q_orig.p; P.n_queries = nq; P.n_slots_max = SM; P.k = k; P.cap = cap;
   P.n_items = n_items; P.item_q = g->q_items.p; P.item_lo = g->q_items.p + n_items; P.item_hi = g->q_items.p + 2 * (size_t)n_items; P.item_out = g->q_items.p + 3 * (size_t)n_items;
   if (n_cols) { P.sig = b->signals->rows.p; P.n_cols = n_cols; }

@@ -16,6 +16,10 @@
 //   chain        n-gram groups (trigram, bigram, monogram of one field): score *= 0.4^hits, hits += score > 0
 // Slots whose term is unknown to the segment stay in the query (SegmentPostings::empty(): they count in
 // num_query_terms and keep their place in the f32 sums) with a zero doc_freq.
+// Optic rule boosts (SignalComputer::boosts, computer/mod.rs:471-497): a rule's docset is a slot too (field | 0x80, its
+// boost beside it), placed behind the text slots by the host.  Rule slots are probed, never enumerated on their own: a
+// document owned by a rule slot is in no text slot and is skipped.  Matching rules add to `boost` or `downrank` in rule
+// order and the total is multiplied by  downrank > boost ? 1/(1 + (downrank - boost)) : boost - downrank + 1.
 #pragma once
 
 namespace sb200 {
@@ -35,6 +39,7 @@ struct MParams {
   const MField* fields; uint32_t n_fields, max_doc;
   const MOp* ops; uint32_t n_ops;
   const uint8_t* q_slot_field; const uint32_t* q_slot_term; const float* q_idf; const float* q_idf_f; const uint32_t* q_nslots;
+  const double* q_boost;   // nullable: [nq][n_slots_max] boost of the rule slots
   const uint32_t* q_orig; uint32_t n_queries, n_slots_max, k, cap;
   uint32_t n_items; const uint32_t* item_q; const uint32_t* item_lo; const uint32_t* item_hi; const uint32_t* item_out;
   const double* sig; uint32_t n_cols;
@@ -59,7 +64,7 @@ __global__ void __launch_bounds__(WQ * 32) k_sig_multi(const MParams P) {
   uint32_t* bloom = tfs + TMAX * 128;                                  // [TMAX][16]
   OTerm* tc = (OTerm*)(bloom + TMAX * 16);                             // [TMAX]
   float* s_wf = (float*)(tc + TMAX);                                   // [TMAX] bm25f idf
-  uint32_t* s_fld = (uint32_t*)(s_wf + TMAX);                          // [TMAX] field of the slot
+  uint32_t* s_fld = (uint32_t*)(s_wf + TMAX);                          // [TMAX] field of the slot (| 0x80: an optic rule's docset)
   uint32_t* s_misc = s_fld + TMAX;                                     // [48]
   uint32_t* s_rstart = s_misc;          // [TMAX + 1]
   uint32_t* s_pos = s_misc + 20;        // [TMAX]
@@ -87,7 +92,8 @@ __global__ void __launch_bounds__(WQ * 32) k_sig_multi(const MParams P) {
   if (lane < T) {
     OTerm c;
     memset(&c, 0, sizeof(c));
-    const uint32_t f = P.q_slot_field[(size_t)q * SM + lane];
+    const uint32_t fr = P.q_slot_field[(size_t)q * SM + lane];
+    const uint32_t f = fr & 0x7Fu;
     const uint32_t ord = P.q_slot_term[(size_t)q * SM + lane];
     const MField& F = P.fields[f];
     if (ord != SB200_NO_TERM && ord < F.n_terms) {
@@ -96,8 +102,8 @@ __global__ void __launch_bounds__(WQ * 32) k_sig_multi(const MParams P) {
       c.tail_off = F.S.t_data_off[ord] + F.S.b_off[c.first + c.nfull];
     }
     c.weight = P.q_idf[(size_t)q * SM + lane];
-    tc[lane] = c; s_wf[lane] = P.q_idf_f[(size_t)q * SM + lane]; s_fld[lane] = f;
-    atomicAdd(s_nf + f, 1u);
+    tc[lane] = c; s_wf[lane] = P.q_idf_f[(size_t)q * SM + lane]; s_fld[lane] = fr;
+    if (!(fr & 0x80u)) atomicAdd(s_nf + f, 1u);   // num_query_terms counts text slots only
     my_done = (c.df == 0);
     budget = 4ull * (c.nfull + 2);
   }
@@ -109,8 +115,8 @@ __global__ void __launch_bounds__(WQ * 32) k_sig_multi(const MParams P) {
     for (uint32_t s = 0; s < T; s++) {
       const OTerm& c = tc[s];
       if (c.nfull == 0) continue;
-      const uint32_t j = o3_dir_search(P.fields[s_fld[s]].S.b_last + c.first, 0, c.nfull, lo_doc, lane);
-      if (lane == s && j > 0) { my_cur = j; my_prev = P.fields[s_fld[s]].S.b_last[c.first + j - 1]; }
+      const uint32_t j = o3_dir_search(P.fields[s_fld[s] & 0x7Fu].S.b_last + c.first, 0, c.nfull, lo_doc, lane);
+      if (lane == s && j > 0) { my_cur = j; my_prev = P.fields[s_fld[s] & 0x7Fu].S.b_last[c.first + j - 1]; }
     }
   }
   bool thr_on = false; uint64_t thr_hi = 0; uint32_t thr_lo = 0;   // warp-uniform
@@ -138,7 +144,7 @@ __global__ void __launch_bounds__(WQ * 32) k_sig_multi(const MParams P) {
           continue;
         }
         uint32_t last;
-        const MField& F = P.fields[s_fld[s]];
+        const MField& F = P.fields[s_fld[s] & 0x7Fu];
         const uint32_t n = o3_decode(F.S, F.a128, c, cur, prev, docs + s * 128, tfs + s * 128, bloom + s * 16, lane, last);
         my_blocks++;
         if (lane == (uint32_t)s) {
@@ -202,6 +208,7 @@ __global__ void __launch_bounds__(WQ * 32) k_sig_multi(const MParams P) {
         }
       }
       if (!owner) continue;
+      if (s_fld[i] & 0x80u) continue;   // only rule docsets hold this doc: not a candidate
       my_docs++;
       uint32_t fid[M_MAX_FIELDS];
 #pragma unroll
@@ -259,6 +266,16 @@ __global__ void __launch_bounds__(WQ * 32) k_sig_multi(const MParams P) {
           if (sc > 0.0) hits++;
         }
         total = __dadd_rn(total, __dmul_rn(op.coeff, sc));
+      }
+      if (P.q_boost) {   // SignalComputer::boosts
+        double down = 0.0, up = 0.0;
+#pragma unroll
+        for (int x = 0; x < TMAX; x++) if ((uint32_t)x < T && (s_fld[x] & 0x80u) && tf[x]) {
+          const double b = P.q_boost[(size_t)q * SM + x];
+          if (b < 0.0) down = __dadd_rn(down, fabs(b)); else up = __dadd_rn(up, b);
+        }
+        const double factor = (down > up) ? __ddiv_rn(1.0, __dadd_rn(1.0, __dsub_rn(down, up))) : __dadd_rn(__dsub_rn(up, down), 1.0);
+        total = __dmul_rn(total, factor);
       }
       const uint64_t kh = ord_f64(total);
       const uint32_t kl = ~d;

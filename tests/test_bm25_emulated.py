@@ -103,6 +103,7 @@ def test_union_kernel_matches_default_kernel(emulated, monkeypatch):
 def test_multi_field_signals_against_oracle(emulated):
     import test_multi_signal_gpu as M
     M.test_multi_field_signals_bit_exact()
+    M.test_optic_rule_boosts_bit_exact()
     M.test_signal_compute_order_mirror()
 
 

@@ -49,8 +49,8 @@ def random_queries(rng, dfs, names, nq, ns):
     return sf, st
 
 
-def check_against_oracle(comp, pairs, cols, sf, st, k, numeric):
-    docs, totals, n_out = comp.top_docs_batch(sf, st, k)
+def check_against_oracle(comp, pairs, cols, sf, st, k, numeric, boost=None):
+    docs, totals, n_out = comp.top_docs_batch(sf, st, k, slot_boost=boost)
     names = comp.names
     osegs = [pairs[n][0] for n in names]
     caches = comp.last_inputs["caches"]
@@ -59,7 +59,7 @@ def check_against_oracle(comp, pairs, cols, sf, st, k, numeric):
            for name, kind, field, chain, col, coef in comp.order.entries]
     for q in range(sf.shape[0]):
         od, ot = oracle.multi_signal_topk(osegs, caches, [1.2] * len(names), coefs, sf[q], st[q], comp.last_inputs["idf"][q],
-                                          comp.last_inputs["idf_f"][q], ops, cols, k)
+                                          comp.last_inputs["idf_f"][q], ops, cols, k, None if boost is None else boost[q])
         n = int(n_out[q])
         assert n == len(od), (q, n, len(od))
         assert np.array_equal(docs[q, :n], od), (q, docs[q, :8], od[:8])
@@ -85,6 +85,38 @@ def test_multi_field_signals_bit_exact():
     for q in range(1, 12):
         sf[q, :2] = [0, 2]; st[q, :2] = [4, 0]
     check_against_oracle(comp, pairs, cols, sf, st, 100, numeric)
+
+
+def test_optic_rule_boosts_bit_exact():
+    """SignalComputer::boosts (computer/mod.rs:471-497): rule docsets as probe-only slots, boosts and downranks, the
+    1/(1+diff) branch, a rule that matches nothing, documents that only a rule holds (never candidates)."""
+    pairs, dfs = make_segment(seed=21)
+    max_doc = 30_000
+    rng = np.random.default_rng(5)
+    cols = [rng.random(max_doc)]
+    comp = MultiFieldSignalComputer({n: pairs[n][1] for n in FIELDS}, ENABLED, SignalTable(cols), [("HostCentrality", 0, 1.0)])
+    names = comp.names
+    nq, ns = 20, 12
+    sf = np.full((nq, ns), 0xFF, np.uint8); st = np.full((nq, ns), NO_TERM, np.uint32); bo = np.zeros((nq, ns), np.float64)
+    for q in range(nq):
+        x = 0
+        for fi, name in enumerate(names[:3]):
+            for _ in range(int(rng.integers(1, 3))):
+                sf[q, x] = fi; st[q, x] = int(rng.integers(0, len(dfs[name]))); x += 1
+        # rules on the Url / CleanBody fields; written BEFORE some text slots on purpose in every other query (the library reorders)
+        rules = [(2, 2, 3.0), (1, 1, -1.5), (2, 1, -4.0), (1, 4, 0.5), (0, NO_TERM, 9.0)][: int(rng.integers(1, 6))]
+        for f, t, b in rules:
+            sf[q, x] = 0x80 | f; st[q, x] = t; bo[q, x] = b; x += 1
+        if q % 2:
+            perm = rng.permutation(x)
+            sf[q, :x], st[q, :x], bo[q, :x] = sf[q, perm], st[q, perm], bo[q, perm]
+            # the f32 sums follow slot order per field, the rule sums rule order: tell the oracle the same (stable) order
+    check_against_oracle(comp, pairs, cols, sf, st, 100, None, boost=bo)
+    # without rules the factor is exactly 1: passing slot_boost must not change a bit
+    sf2 = sf.copy(); sf2[sf2 >= 0x80] = 0xFF; sf2[sf == 0xFF] = 0xFF
+    d0, t0, n0 = comp.top_docs_batch(sf2, st, 100)
+    d1, t1, n1 = comp.top_docs_batch(sf2, st, 100, slot_boost=bo)
+    assert np.array_equal(d0, d1) and np.array_equal(t0, t1) and np.array_equal(n0, n1)
 
 
 def test_signal_compute_order_mirror():
