@@ -690,7 +690,7 @@ def main():
         if not args.no_bm25 and world == 1:
             import bench_bm25
             line["bm25"] = bench_bm25.run(local_rank, peaks, peak_src, cpu=not args.no_cpu)
-            for k in ("and_top1000_10M", "or5_signals_100M"):
+            for k in ("and_top1000_10M", "or5_signals_100M", "multi_field_10M"):
                 if isinstance(line["bm25"].get(k), dict) and "parity" in line["bm25"][k]:
                     parity[k] = line["bm25"][k]["parity"]
                 md = (line["bm25"].get(k) or {}).get("max_docs_250k") if isinstance(line["bm25"].get(k), dict) else None
