@@ -483,7 +483,7 @@ def main():
         ev1.record()
         barrier()
         clocks = sampler.stop()
-        roofline_n = None
+        roofline_n, kernels_n = None, None
         try:   # rank 0's dominant kernel over its owned share of the rows (algorithmic bytes x owned fraction)
             prof = dg.profile()
             dom = max((p for p in prof if "dense" in p["name"] and p["launches"]), key=lambda p: p["ms"], default=None)
@@ -494,6 +494,7 @@ def main():
                               "launches": dom["launches"], "avg_launch_ms": dom["ms"] / dom["launches"],
                               "alg_bytes_per_launch": dom["alg_bytes"] / dom["launches"],
                               "note": "includes the stores of the produced rows into the peers' replicas over NVLink"}
+            kernels_n = [{"kernel": q["name"], "launches": q["launches"], "avg_launch_ms": q["ms"] / q["launches"]} for q in prof if q["launches"]]
         except Exception:  # noqa: BLE001
             roofline_n = None
         dg.set_profiling(False)
@@ -527,7 +528,7 @@ def main():
         else:
             parity["c2"] = {"against": None, "green": None, "fingerprint": got}
         result.update(value=value, ms_per_step=ms_total / args.steps, iters=tot_iters // args.steps, E=E, info=info,
-                      clocks=clocks, roofline=roofline_n, launches=int(nl.item()), kernels=[], per_iter=allr)
+                      clocks=clocks, roofline=roofline_n, launches=int(nl.item()), kernels=kernels_n or [], per_iter=allr)
         dg.close()
         dg = None
         # ---- e2e at N > 1: every rank stages the whole edge stream from ITS OWN page-locked host copy (staging is

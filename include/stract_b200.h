@@ -236,6 +236,19 @@ SB200_API int sb200_approx_harmonic(sb200_graph* g, const uint64_t* src_lo, cons
                                     uint32_t max_dist, uint64_t num_nodes, uint64_t* id_lo, uint64_t* id_hi, double* centrality,
                                     uint64_t cap, uint64_t* len);
 
+/* Inbound similarity (crates/core/src/ranking/inbound_similarity.rs:71-119 over bitvec_similarity.rs:130-185): for every
+ * candidate node, Scorer::score against the liked / disliked nodes:
+ *     s = |disliked| + (sum_liked sim - sum_disliked sim),  s / max(|liked|, 1) if normalized,  max(s, 0)
+ *     sim(a, b) = |in(a) ∩ in(b)| / (sqrt|in(a)| * sqrt|in(b)|), 0 if either set is empty or if the reference's 16 x 64-bit
+ *                 bloom pre-filter over the low 64 id bits says popcount(A & B) / max(ones) < 0.25 (false negatives included);
+ *     a liked / disliked node compared with itself scores self_score (1.0 in the reference until set_self_score).
+ * in(v) = the unique sources of v's links in the handle's edge set, including v itself if it links to itself.  Ids that are
+ * not nodes of the graph have an empty set.  Single-rank handles. */
+SB200_API int sb200_inbound_similarity(sb200_graph* g, const uint64_t* liked_lo, const uint64_t* liked_hi, uint32_t n_liked,
+                                       const uint64_t* disliked_lo, const uint64_t* disliked_hi, uint32_t n_disliked,
+                                       const uint64_t* cand_lo, const uint64_t* cand_hi, uint32_t n_cand, int normalized,
+                                       double self_score, double* scores);
+
 /* Device-memory arena diagnostics.  With SB200_ARENA=1 in the environment, staging temporaries, the CSR and the
  * state of single-rank handles are sub-allocated from large slabs that are kept for the life of the process
  * (deterministic, no driver call per allocation once warm) instead of the driver's stream-ordered pool.

@@ -10,6 +10,8 @@
 // (exact) and, for a fixed sample, on the sums within f32 accumulation error.
 #include "oracle_common.h"
 
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <functional>
 #include <queue>
@@ -72,5 +74,59 @@ ORC_API void orc_approx_harmonic(uint32_t n, const uint32_t* from, const uint32_
       const float term = (1.0f / (float)dist[v]) * norm;
       out32[v] += term; out64[v] += (double)term;
     }
+  }
+}
+
+// ---------------------------------------------------------------- inbound similarity ---------
+// bitvec_similarity.rs:24-185 + inbound_similarity.rs:26-119.  The graph comes as unique links over dense ranks (self-links
+// included) plus the node ids; liked / disliked / candidates are ranks, 0xFFFFFFFF = the one id that is not a node.
+namespace {
+struct BitVecO {
+  std::vector<u128> ranks; uint64_t bloom[16]; size_t ones = 0; double sqrt_len = 0;
+  void build(std::vector<u128> v) {   // BitVec::new
+    std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end());
+    memset(bloom, 0, sizeof(bloom)); ones = 0;
+    for (u128 r : v) {               // VeryJankyBloomFilter::insert_u128 -> insert(item as u64)
+      const uint64_t h = (uint64_t)r * 11400714819323198549ull;
+      const size_t a = (size_t)(h % 16); const uint64_t b = h % 64;
+      if (bloom[a] & (1ull << b)) continue;
+      bloom[a] |= 1ull << b; ones++;
+    }
+    sqrt_len = std::sqrt((double)v.size());
+    ranks.swap(v);
+  }
+  double sim(const BitVecO& o) const {   // BitVec::sim
+    if (sqrt_len == 0.0 || o.sqrt_len == 0.0) return 0.0;
+    const size_t mx = std::max(ones, o.ones);
+    size_t inter = 0;
+    for (int i = 0; i < 16; i++) inter += (size_t)__builtin_popcountll(bloom[i] & o.bloom[i]);
+    if ((double)inter / (double)mx < 0.25) return 0.0;
+    size_t i = 0, j = 0, c = 0;
+    while (i < ranks.size() && j < o.ranks.size()) { if (ranks[i] == o.ranks[j]) { c++; i++; j++; } else if (ranks[i] < o.ranks[j]) i++; else j++; }
+    return (double)c / (sqrt_len * o.sqrt_len);
+  }
+};
+}  // namespace
+ORC_API void orc_inbound_similarity(uint32_t n, const uint64_t* id_lo, const uint64_t* id_hi, const uint32_t* from, const uint32_t* to, uint64_t m,
+                                    const uint32_t* liked, uint32_t n_liked, const uint32_t* disliked, uint32_t n_disliked,
+                                    const uint32_t* cand, uint32_t n_cand, int normalized, double self_score, double* out) {
+  const Csr in = build(n, from, to, m, true);   // ingoing: adjacency of `to`
+  auto inbound = [&](uint32_t r) {
+    BitVecO b; std::vector<u128> v;
+    if (r != 0xFFFFFFFFu) for (uint64_t e = in.ptr[r]; e < in.ptr[r + 1]; e++) v.push_back(orc_make_u128(id_hi[in.adj[e]], id_lo[in.adj[e]]));
+    b.build(std::move(v));
+    return b;
+  };
+  std::vector<BitVecO> L(n_liked), D(n_disliked);
+  for (uint32_t i = 0; i < n_liked; i++) L[i] = inbound(liked[i]);
+  for (uint32_t i = 0; i < n_disliked; i++) D[i] = inbound(disliked[i]);
+  for (uint32_t c = 0; c < n_cand; c++) {
+    const BitVecO cb = inbound(cand[c]);
+    double ls = 0.0, ds = 0.0;   // NodeScorer::sim compares NodeIDs: equal ranks = the same node (0xFFFFFFFF stands for ONE id that is not in the graph)
+    for (uint32_t i = 0; i < n_liked; i++) ls += liked[i] == cand[c] ? self_score : L[i].sim(cb);
+    for (uint32_t i = 0; i < n_disliked; i++) ds += disliked[i] == cand[c] ? self_score : D[i].sim(cb);
+    double s = (double)n_disliked + (ls - ds);
+    if (normalized) s = s / (double)std::max<uint32_t>(n_liked, 1);
+    out[c] = std::max(s, 0.0);
   }
 }

@@ -77,6 +77,8 @@ def _proto(L):
     f("orc_hb_dense_num_self_loops", C.c_uint64, C.c_void_p)
     f("orc_hb_dense_registers_ptr", C.c_void_p, C.c_void_p)
     f("orc_graph_distances", None, C.c_uint32, _u32p, _u32p, C.c_uint64, _u32p, _u32p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, _u8p)
+    f("orc_inbound_similarity", None, C.c_uint32, _u64p, _u64p, _u32p, _u32p, C.c_uint64, _u32p, C.c_uint32, _u32p, C.c_uint32, _u32p, C.c_uint32,
+      C.c_int, C.c_double, _f64p)
     f("orc_approx_harmonic", None, C.c_uint32, _u32p, _u32p, C.c_uint64, _u32p, C.c_uint32, C.c_int, C.c_uint64, _f32p, _f64p)
     f("orc_synth_edges", None, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int,
       _u64p, _u64p, _u64p, _u64p, _u64p, C.c_int)
@@ -283,6 +285,16 @@ def approx_harmonic(n, from_rank, to_rank, sources, max_dist=7, num_nodes=None):
     o32 = np.zeros(n, np.float32); o64 = np.zeros(n, np.float64)
     lib().orc_approx_harmonic(n, fr, tr, fr.size, src, src.size, int(max_dist), int(n if num_nodes is None else num_nodes), o32, o64)
     return o32, o64
+
+
+def inbound_similarity(ids_lo, ids_hi, from_rank, to_rank, liked, disliked, candidates, normalized=False, self_score=1.0):
+    """inbound_similarity::Scorer::score for every candidate (ranks; 0xFFFFFFFF = not a node of the graph)."""
+    lo = np.ascontiguousarray(ids_lo, np.uint64); hi = np.ascontiguousarray(ids_hi, np.uint64)
+    fr = np.ascontiguousarray(from_rank, np.uint32); tr = np.ascontiguousarray(to_rank, np.uint32)
+    li = np.ascontiguousarray(liked, np.uint32); di = np.ascontiguousarray(disliked, np.uint32); ca = np.ascontiguousarray(candidates, np.uint32)
+    out = np.zeros(ca.size, np.float64)
+    lib().orc_inbound_similarity(lo.size, lo, hi, fr, tr, fr.size, li, li.size, di, di.size, ca, ca.size, 1 if normalized else 0, float(self_score), out)
+    return out
 
 
 def harmonic_ranks(ids_lo, ids_hi, values, ties_desc=False):

@@ -117,6 +117,10 @@ void sb200_graph_destroy(sb200_graph* g) {
   if (g->h_counters) cudaFreeHost(g->h_counters);
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
+  if (g->side_stream) { cudaStreamSynchronize(g->side_stream); cudaStreamDestroy(g->side_stream); }
+  if (g->ev_fork) cudaEventDestroy(g->ev_fork);
+  if (g->ev_join) cudaEventDestroy(g->ev_join);
+  for (int k = 0; k < 2; k++) if (g->side_prof[k]) cudaEventDestroy(g->side_prof[k]);
   if (g->ev_run0) cudaEventDestroy(g->ev_run0);
   if (g->ev_run1) cudaEventDestroy(g->ev_run1);
   for (int f = 0; f < sb200_graph::F_COUNT; f++) for (int k = 0; k < 2; k++) if (g->prof_ev[f][k]) cudaEventDestroy(g->prof_ev[f][k]);

@@ -39,6 +39,7 @@ struct sb200_graph {
 
   sb200::DevBuf<uint64_t> id_lo, id_hi;
   sb200::DevBuf<uint32_t> perm, inv;
+  sb200::DevBuf<uint32_t> self_bm;  // [N/32] in RANK order: the node has a kept link to itself (not in the CSR: a no-op for HyperBall)
   sb200::DevBuf<uint32_t> row_ptr, col;
   uint32_t col_base = 0;  // row_ptr values are global; col[] holds [col_base, col_base+E_local)
   sb200::DevBuf<uint32_t> fwd_ptr, fwd_dst;
@@ -95,6 +96,11 @@ struct sb200_graph {
   uint64_t prof_launches[F_COUNT] = {0};
   double prof_ms[F_COUNT] = {0}, prof_bytes[F_COUNT] = {0};
   cudaEvent_t prof_ev[F_COUNT][2] = {{nullptr}};
+  // fused exchange: the short-row kernel runs on a second stream beside the long-row kernel (hyperball.cu, launch_pull)
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, side_prof[2] = {nullptr, nullptr};
+  bool side_prof_used = false;
+  int side_prof_family = 0;
   bool prof_used[F_COUNT] = {false};
   double prof_step_bytes[F_COUNT] = {0};
   uint64_t E_warp = 0, E_quad = 0;   // edges of the warp-class / quad-class rows

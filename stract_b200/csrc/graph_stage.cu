@@ -182,12 +182,14 @@ __global__ void k_map_edges(const uint64_t* __restrict__ flo, const uint64_t* __
 }
 
 __global__ void k_mark_keep(const uint64_t* __restrict__ keys, const uint8_t* __restrict__ skip, uint64_t n,
-                            uint8_t* keep) {
+                            uint8_t* keep, uint32_t* self_bm) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint64_t k = keys[i];
   bool first = (i == 0) || (keys[i - 1] != k);
-  keep[i] = first && !skip[i] && ((uint32_t)k != (uint32_t)(k >> 32));
+  const bool self = (uint32_t)k == (uint32_t)(k >> 32);
+  keep[i] = first && !skip[i] && !self;
+  if (first && !skip[i] && self) atomicOr(self_bm + ((uint32_t)k >> 5), 1u << ((uint32_t)k & 31u));   // kept self-link: remembered, not stored
 }
 
 __global__ void k_degree_hi(const uint64_t* __restrict__ keys, uint64_t n, uint32_t* deg) {
@@ -577,7 +579,9 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
   const int nb = bits_for(N);
   uint64_t *k = keys_a.p, *k_alt = keys_b.p; uint8_t *sk = skip_a.p, *sk_alt = skip_b.p;
   SB_TRY((sort_pairs<uint64_t, uint8_t>(tmp, k, k_alt, sk, sk_alt, n_edges, 0, 32 + nb, false, s)));
-  SB_LAUNCH(k_mark_keep, div_up(n_edges, TPB), TPB, 0, s, k, sk, n_edges, sk_alt);
+  SB_TRY(g->self_bm.alloc((N + 31) / 32 + 1));
+  SB_CUDA(cudaMemsetAsync(g->self_bm.p, 0, ((N + 31) / 32 + 1) * 4, s));
+  SB_LAUNCH(k_mark_keep, div_up(n_edges, TPB), TPB, 0, s, k, sk, n_edges, sk_alt, g->self_bm.p);
   SB_CHECK_LAUNCH();
   {
     size_t need = 0;

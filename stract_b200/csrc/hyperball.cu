@@ -191,18 +191,10 @@ __device__ __forceinline__ bool bm_test(const uint32_t* __restrict__ bm, uint32_
 
 // ---- pull, short rows: 4 lanes per destination row ----------------------------------------------------
 template <bool FRONTIER>
-__global__ void __launch_bounds__(256, 7) k_pull_quad(uint64_t row_begin, uint64_t row_end,
+__device__ __forceinline__ void quad_rows(uint64_t row, bool live, uint32_t sub, uint32_t lane,
     const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col, uint32_t col_base,
     const uint4* __restrict__ oldr, uint4* __restrict__ newr,
-    const uint32_t* __restrict__ bm_prev, uint32_t* __restrict__ bm_cur, const PeerOut peers) {
-  const uint64_t gt = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  const uint32_t sub = threadIdx.x & 3;
-  const uint32_t lane = threadIdx.x & 31;
-  uint64_t row = row_begin + (gt >> 2);
-  bool live = row < row_end;
-  if (!live) row = row_end - 1;  // keep the warp converged; results of dead quads are discarded
-  live = live && owned_row(peers, (uint32_t)row);
-  if (__ballot_sync(0xffffffffu, live) == 0u) return;  // none of this warp's rows belongs to this rank
+    const uint32_t* __restrict__ bm_prev, uint32_t* __restrict__ bm_cur, const PeerOut& peers) {
   const uint32_t e0 = live ? row_ptr[row] - col_base : 0u, e1 = live ? row_ptr[row + 1] - col_base : 0u;
   const uint4 own = oldr[row * 4 + sub];
   uint4 acc = own;
@@ -230,6 +222,43 @@ __global__ void __launch_bounds__(256, 7) k_pull_quad(uint64_t row_begin, uint64
   const bool changed = ((ball >> (lane & ~3u)) & 0xFu) != 0u;
   if (!live) return;
   publish_row(newr, bm_cur, peers, (uint32_t)row, sub, acc, changed || bm_test(bm_prev, (uint32_t)row), changed);
+}
+
+template <bool FRONTIER>
+__global__ void __launch_bounds__(256, 7) k_pull_quad(uint64_t row_begin, uint64_t row_end,
+    const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col, uint32_t col_base,
+    const uint4* __restrict__ oldr, uint4* __restrict__ newr,
+    const uint32_t* __restrict__ bm_prev, uint32_t* __restrict__ bm_cur, const PeerOut peers) {
+  const uint64_t gt = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint32_t sub = threadIdx.x & 3;
+  const uint32_t lane = threadIdx.x & 31;
+  uint64_t row = row_begin + (gt >> 2);
+  bool live = row < row_end;
+  if (!live) row = row_end - 1;  // keep the warp converged; results of dead quads are discarded
+  live = live && owned_row(peers, (uint32_t)row);
+  if (__ballot_sync(0xffffffffu, live) == 0u) return;  // none of this warp's rows belongs to this rank
+  quad_rows<FRONTIER>(row, live, sub, lane, row_ptr, col, col_base, oldr, newr, bm_prev, bm_cur, peers);
+}
+
+// Sharded handles with the fused exchange: the short rows are most of the rows, so this kernel carries most of the
+// stores into the peers' replicas -- it is bound by NVLink, not by HBM, while k_pull_warp is the opposite.  This variant
+// is a small persistent grid (a few CTAs per SM) that walks the OWNED 32-row blocks only (4 warps per block), so that it can
+// sit next to k_pull_warp on a second, higher-priority stream: link traffic of the short rows under the gathers of the long ones.
+template <bool FRONTIER>
+__global__ void __launch_bounds__(256, 4) k_pull_quad_owned(uint64_t row_begin, uint64_t row_end, uint64_t first_block, uint64_t n_tasks,
+    const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col, uint32_t col_base,
+    const uint4* __restrict__ oldr, uint4* __restrict__ newr,
+    const uint32_t* __restrict__ bm_prev, uint32_t* __restrict__ bm_cur, const PeerOut peers) {
+  const uint32_t sub = threadIdx.x & 3, lane = threadIdx.x & 31;
+  const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+  for (uint64_t task = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; task < n_tasks; task += warps) {
+    const uint64_t block = first_block + (task >> 2) * peers.world;
+    uint64_t row = block * 32 + (task & 3) * 8 + (lane >> 2);
+    const bool live = row >= row_begin && row < row_end;
+    if (!live) row = row_begin;
+    if (__ballot_sync(0xffffffffu, live) == 0u) continue;
+    quad_rows<FRONTIER>(row, live, sub, lane, row_ptr, col, col_base, oldr, newr, bm_prev, bm_cur, peers);
+  }
 }
 
 // Experiment (SB200_QUAD2=1, single-rank handles): two adjacent rows per quad, their index loads and gathers interleaved --
@@ -602,6 +631,47 @@ static int launch_pull(sb200_graph* g, const uint4* oldr, uint4* newr, const uin
   const int FW = FRONTIER ? sb200_graph::F_PULL_WARP_FRONT : sb200_graph::F_PULL_WARP_DENSE;
   const int FQ = FRONTIER ? sb200_graph::F_PULL_QUAD_FRONT : sb200_graph::F_PULL_QUAD_DENSE;
   const double per_edge = FRONTIER ? 4.0 : 68.0;  // col index (+ the 64-B gather when every source is read)
+  // fused exchange: short rows on the side stream, next to the long-row kernel (see k_pull_quad_owned)
+  static const int side_ctas = (int)env_f("SB200_QUAD_SIDE_CTAS", 2.0);
+  const bool side_quad = side_ctas > 0 && g->world > 1 && g->p2p && g->n_peers > 0 && g->n_items && g->quad_row_end > g->quad_row_begin;
+  if (side_quad) {
+    if (!g->side_stream) {
+      int lo = 0, hi = 0;
+      SB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      SB_CUDA(cudaStreamCreateWithPriority(&g->side_stream, cudaStreamNonBlocking, hi));
+      SB_CUDA(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
+      SB_CUDA(cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming));
+      SB_CUDA(cudaEventCreate(&g->side_prof[0])); SB_CUDA(cudaEventCreate(&g->side_prof[1]));
+    }
+    int sm_count = 148;
+    SB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, g->device));
+    const uint64_t world = (uint64_t)g->world, b0 = g->quad_row_begin >> 5, b1 = (g->quad_row_end - 1) >> 5;
+    const uint64_t first = b0 + ((uint64_t)g->rank + world - b0 % world) % world;
+    const uint64_t n_tasks = first <= b1 ? ((b1 - first) / world + 1) * 4 : 0;
+    SB_CUDA(cudaEventRecord(g->ev_fork, s));
+    SB_CUDA(cudaStreamWaitEvent(g->side_stream, g->ev_fork, 0));
+    if (g->l2_window_bytes) {
+      cudaStreamAttrValue a;
+      memset(&a, 0, sizeof(a));
+      a.accessPolicyWindow.base_ptr = (void*)oldr; a.accessPolicyWindow.num_bytes = g->l2_window_bytes;
+      a.accessPolicyWindow.hitRatio = 1.0f; a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      SB_CUDA(cudaStreamSetAttribute(g->side_stream, cudaStreamAttributeAccessPolicyWindow, &a));
+    }
+    if (g->profiling) SB_CUDA(cudaEventRecord(g->side_prof[0], g->side_stream));
+    if (getenv("SB200_DEBUG_SIDE")) fprintf(stderr, "[sb200] side quad: rank %d tasks %llu\n", g->rank, (unsigned long long)n_tasks);
+    if (n_tasks) {
+      const unsigned grid = (unsigned)std::min<uint64_t>(div_up(n_tasks, 8), (uint64_t)sm_count * (uint64_t)side_ctas);
+      SB_LAUNCH(k_pull_quad_owned<FRONTIER>, grid, 256, 0, g->side_stream, g->quad_row_begin, g->quad_row_end, first, n_tasks,
+                g->row_ptr.p, g->col.p, g->col_base, oldr, newr, bmp, bmc, po);
+      SB_CHECK_LAUNCH();
+    }
+    if (g->profiling) {
+      SB_CUDA(cudaEventRecord(g->side_prof[1], g->side_stream));
+      g->side_prof_used = true; g->side_prof_family = FQ;
+      g->prof_step_bytes[FQ] = g->own_frac * (per_edge * (double)g->E_quad + 68.0 * (double)(g->quad_row_end - g->quad_row_begin));
+    }
+  }
   if (g->n_items) {
     PROF_BEGIN(g, FW);
     SB_LAUNCH(k_pull_warp<FRONTIER>, div_up(g->n_items * 32, 256), 256, 0, s, g->n_items, g->n_multi_items,
@@ -618,7 +688,8 @@ static int launch_pull(sb200_graph* g, const uint4* oldr, uint4* newr, const uin
     PROF_END(g, sb200_graph::F_PULL_MERGE, 64.0 * (double)g->n_multi_items + 68.0 * (double)g->n_multi_rows);
   }
   const uint64_t nq = g->quad_row_end - g->quad_row_begin;
-  if (nq) {
+  if (side_quad) { SB_CUDA(cudaEventRecord(g->ev_join, g->side_stream)); SB_CUDA(cudaStreamWaitEvent(s, g->ev_join, 0)); }
+  else if (nq) {
     PROF_BEGIN(g, FQ);
     static const bool quad2 = env_flag("SB200_QUAD2", false);
     if (quad2 && g->world == 1 && g->col_base == 0)
@@ -894,6 +965,12 @@ int hb_step_finish(sb200_graph* g, sb200_iter_stats* st) {
       float kms = 0; cudaEventElapsedTime(&kms, g->prof_ev[f][0], g->prof_ev[f][1]);
       g->prof_launches[f]++; g->prof_ms[f] += kms; g->prof_bytes[f] += g->prof_step_bytes[f];
       g->prof_used[f] = false;
+    }
+    if (g->side_prof_used) {
+      const int f = g->side_prof_family;
+      float kms = 0; cudaEventElapsedTime(&kms, g->side_prof[0], g->side_prof[1]);
+      g->prof_launches[f]++; g->prof_ms[f] += kms; g->prof_bytes[f] += g->prof_step_bytes[f];
+      g->side_prof_used = false;
     }
   }
   if (st) {

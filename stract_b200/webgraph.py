@@ -325,6 +325,16 @@ class DeviceGraph:
         k = ln.value
         return olo[:k], ohi[:k], oc[:k]
 
+    def inbound_similarity(self, liked, disliked, candidates, normalized=False, self_score=1.0):
+        """inbound_similarity::Scorer over the resident graph (ranking/inbound_similarity.rs:71-119): one f64 score per candidate."""
+        def split(ids):
+            return (np.array([int(x) & _M64 for x in ids], np.uint64), np.array([int(x) >> 64 for x in ids], np.uint64))
+        ll, lh = split(liked); dl, dh = split(disliked); cl, ch = split(candidates)
+        out = np.zeros(len(cl), np.float64)
+        check(self._L.sb200_inbound_similarity(self._h, ll.ctypes.data, lh.ctypes.data, len(ll), dl.ctypes.data, dh.ctypes.data, len(dl),
+                                               cl.ctypes.data, ch.ctypes.data, len(cl), 1 if normalized else 0, float(self_score), out.ctypes.data))
+        return out
+
     def exchange_done(self, global_n_changed):
         check(self._L.sb200_hyperball_exchange_done(self._h, int(global_n_changed)))
 

@@ -92,6 +92,10 @@ enum cudaAccessProperty { cudaAccessPropertyNormal = 0, cudaAccessPropertyStream
 struct cudaPointerAttributes { cudaMemoryType type; int device; void* devicePointer; void* hostPointer; };
 static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) { a->type = cudaMemoryTypeDevice; a->device = 0; return cudaSuccess; }  // one address space: every pointer is "device" memory
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
+static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 4; return cudaSuccess; }
+static inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = (void*)0x1; return cudaSuccess; }
+static inline cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = -1; return cudaSuccess; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 static inline cudaError_t cudaMallocHost(void** p, size_t n) { *p = aligned_alloc(64, (n + 63) / 64 * 64); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
@@ -193,6 +197,7 @@ static inline double __dadd_rn(double a, double b) { volatile double r = a + b; 
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
 static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
+static inline double __dsqrt_rn(double a) { volatile double r = __builtin_sqrt(a); return r; }
 static inline double __ull2double_rn(unsigned long long v) { return (double)v; }
 static inline unsigned long long __double2ull_rz(double d) { return d <= 0.0 ? 0ull : (d >= 18446744073709551615.0 ? ~0ull : (unsigned long long)d); }
 static inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long)v); }

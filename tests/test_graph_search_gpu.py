@@ -64,3 +64,43 @@ def test_approx_harmonic_fixed_sample():
         assert np.allclose(c, w32[reached].astype(np.float64), rtol=2e-5)    # the reference-shaped f32 accumulation
     finally:
         dg.close()
+
+
+def test_inbound_similarity_matches_scorer():
+    """inbound_similarity::Scorer over the resident CSR: bit-exact f64 scores, incl. the bloom pre-filter's false negatives,
+    self-links as in-neighbours, self_score, ids that are not nodes, empty lists and more than 64 liked nodes (two passes)."""
+    d = synth.rmat_graph(3000, 40000, seed=21)
+    a = [d["from_lo"].copy(), d["from_hi"].copy(), d["to_lo"].copy(), d["to_hi"].copy(), d["rel_flags"].copy()]
+    for k in range(0, 400, 7):                      # plant self-links
+        a[2][k] = a[0][k]; a[3][k] = a[1][k]
+    a = tuple(a)
+    ids_lo, ids_hi, fr, tr = oracle.graph_links(*a, skip_mask=0)
+    n = len(ids_lo)
+    assert (fr == tr).sum() > 20
+    dg = DeviceGraph(Webgraph.from_arrays(*a), skipped_rel=0)
+    try:
+        rng = np.random.default_rng(5)
+        indeg = np.bincount(tr, minlength=n)
+        popular = np.argsort(-indeg)[:300]
+        selfers = np.unique(fr[fr == tr])
+        def ids_of(ranks):
+            return [((int(ids_hi[r]) << 64) | int(ids_lo[r])) if r != 0xFFFFFFFF else (1 << 100) + 12345 for r in ranks]
+        cases = []
+        liked = np.concatenate([rng.choice(popular, 20, replace=False), selfers[:5]]).astype(np.uint32)
+        disliked = np.concatenate([rng.choice(popular, 9, replace=False), selfers[5:8], [0xFFFFFFFF]]).astype(np.uint32)
+        cand = np.concatenate([rng.choice(n, 500, replace=False), liked[:4], disliked[:3], selfers[:10], [0xFFFFFFFF]]).astype(np.uint32)
+        cases.append((liked, disliked, cand, False, 1.0))
+        cases.append((liked, disliked, cand, True, 0.25))
+        cases.append((rng.choice(popular, 150, replace=False).astype(np.uint32), rng.choice(n, 70, replace=False).astype(np.uint32), cand, True, 1.0))
+        cases.append((np.zeros(0, np.uint32), disliked, cand, True, 1.0))
+        cases.append((liked, np.zeros(0, np.uint32), cand[:1], False, 1.0))
+        cases.append((np.zeros(0, np.uint32), np.zeros(0, np.uint32), cand[:40], False, 1.0))
+        nonzero = 0
+        for li, di, ca, norm, ss in cases:
+            want = oracle.inbound_similarity(ids_lo, ids_hi, fr, tr, li, di, ca, norm, ss)
+            got = dg.inbound_similarity(ids_of(li), ids_of(di), ids_of(ca), norm, ss)
+            assert got.tobytes() == want.tobytes(), (len(li), len(di), norm, np.flatnonzero(got != want)[:5])
+            nonzero += int((want != float(len(di))).sum())
+        assert nonzero > 200
+    finally:
+        dg.close()

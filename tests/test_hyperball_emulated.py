@@ -62,5 +62,6 @@ def test_graph_searches_against_oracle():
         import test_graph_search_gpu as T
         T.test_distances_match_dijkstra_multi()
         T.test_approx_harmonic_fixed_sample()
+        T.test_inbound_similarity_matches_scorer()
     finally:
         _lib._LIB = saved
