@@ -51,6 +51,8 @@ struct sb200_graph {
   uint64_t quad_row_begin = 0, quad_row_end = 0;  // rows with 0 < deg <= QUAD_MAX_DEG: quad-per-row
   uint64_t n_items = 0;                           // chunks of the warp rows
   uint64_t n_multi_rows = 0;                      // leading warp rows that span > 1 chunk
+  sb200::DevBuf<uint32_t> owned_items;            // sharded: ascending ids of the items whose row this rank owns
+  uint64_t n_owned_items = 0;
   sb200::DevBuf<uint32_t> item_row, item_start;   // item -> row ; row(-warp_row_begin) -> first item
   sb200::DevBuf<uint4> partial;                   // [n_multi_items][4] chunk partial registers
   uint64_t n_multi_items = 0;
@@ -97,6 +99,7 @@ struct sb200_graph {
   double prof_ms[F_COUNT] = {0}, prof_bytes[F_COUNT] = {0};
   cudaEvent_t prof_ev[F_COUNT][2] = {{nullptr}};
   // fused exchange: the short-row kernel runs on a second stream beside the long-row kernel (hyperball.cu, launch_pull)
+  int sm_count = 0;
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, side_prof[2] = {nullptr, nullptr};
   bool side_prof_used = false;

@@ -308,6 +308,16 @@ __global__ void k_row_chunks(const uint32_t* __restrict__ row_ptr, uint64_t row0
   uint32_t d = row_ptr[row0 + i + 1] - row_ptr[row0 + i];
   nchunks[i] = (d + chunk - 1) / chunk;
 }
+// sharded handles: the work items of the rows this rank owns, ascending (so k_pull_warp launches no warp that would exit)
+__global__ void k_item_owned_flag(uint64_t n_items, const uint32_t* __restrict__ item_row, uint32_t world, uint32_t rank, uint32_t* flag) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i > n_items) return;
+  flag[i] = (i < n_items && ((item_row[i] >> 5) % world) == rank) ? 1u : 0u;
+}
+__global__ void k_item_owned_scatter(uint64_t n_items, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos, uint32_t* list) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n_items && flag[i]) list[pos[i]] = (uint32_t)i;
+}
 __global__ void k_fill_items(const uint32_t* __restrict__ item_start, uint64_t nrows, uint64_t n_items,
                              uint32_t row0, uint32_t* item_row) {
   uint64_t it = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -746,6 +756,22 @@ int stage_graph(sb200_graph* g, const uint64_t* from_lo, const uint64_t* from_hi
       SB_LAUNCH(k_sub_rows, div_up(g->quad_row_end - g->quad_row_begin, TPB), TPB, 0, s, g->quad_row_begin, g->quad_row_end,
                 g->row_ptr.p, g->col.p, (uint32_t)g->world, g->sub_mask.p);
       SB_CHECK_LAUNCH();
+    }
+    g->n_owned_items = 0;
+    if (g->n_items) {
+      DevBuf<uint32_t> flag, pos;
+      SB_TRY(flag.alloc(g->n_items + 1)); SB_TRY(pos.alloc(g->n_items + 1));
+      SB_LAUNCH(k_item_owned_flag, div_up(g->n_items + 1, TPB), TPB, 0, s, g->n_items, g->item_row.p, (uint32_t)g->world, (uint32_t)g->rank, flag.p);
+      SB_CHECK_LAUNCH();
+      SB_TRY(exclusive_scan_u32(tmp, flag.p, pos.p, g->n_items + 1, s));
+      uint32_t n_own = 0;
+      SB_CUDA(cudaMemcpyAsync(&n_own, pos.p + g->n_items, 4, cudaMemcpyDeviceToHost, s));
+      SB_CUDA(cudaStreamSynchronize(s));
+      SB_TRY(g->owned_items.alloc((size_t)n_own + 1));
+      SB_LAUNCH(k_item_owned_scatter, div_up(g->n_items, TPB), TPB, 0, s, g->n_items, flag.p, pos.p, g->owned_items.p);
+      SB_CHECK_LAUNCH();
+      SB_CUDA(cudaStreamSynchronize(s));
+      g->n_owned_items = n_own;
     }
     SB_CUDA(cudaMemsetAsync(ctr.p, 0, sizeof(unsigned long long), s));
     SB_LAUNCH(k_sub_count, div_up(N, TPB), TPB, 0, s, g->sub_mask.p, N, (uint32_t)g->world, (uint32_t)g->rank, ctr.p);

@@ -308,16 +308,17 @@ __global__ void __launch_bounds__(256, 4) k_pull_quad2(uint64_t row_begin, uint6
 }
 
 // ---- pull, long rows: one warp per <=CHUNK_EDGES work item ---------------------------------------------
-template <bool FRONTIER>
+template <bool FRONTIER, bool LISTED>
 // 8 CTAs/SM (<= 32 registers): at full scale the gathers are DRAM-latency bound and the kernel's speed tracks the
 // number of resident warps (36 registers = 7 CTAs measured 11 % slower than 32 registers = 8 CTAs)
 __global__ void __launch_bounds__(256, 8) k_pull_warp(uint64_t n_items, uint64_t first_multi_free_item,
-    const uint32_t* __restrict__ item_row, const uint32_t* __restrict__ item_start, uint32_t warp_row_begin,
+    const uint32_t* __restrict__ item_list, const uint32_t* __restrict__ item_row, const uint32_t* __restrict__ item_start, uint32_t warp_row_begin,
     const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col, uint32_t col_base,
     const uint4* __restrict__ oldr, uint4* __restrict__ newr, uint4* __restrict__ partial,
     const uint32_t* __restrict__ bm_prev, uint32_t* __restrict__ bm_cur, const PeerOut peers) {
-  const uint64_t item = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  uint64_t item = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   if (item >= n_items) return;  // whole warp exits together
+  if (LISTED) item = item_list[item];   // sharded: n_items counts the owned items, listed ascending
   const uint32_t lane = threadIdx.x & 31, sub = lane & 3, q = lane >> 2;
   const uint32_t row = item_row[item];
   if (!owned_row(peers, row)) return;  // sharded: another rank owns this row (warp-uniform)
@@ -470,11 +471,20 @@ __global__ void __launch_bounds__(256) k_finalize(uint64_t row_begin, uint64_t r
   for (int i = threadIdx.x; i < (int)(sizeof(HllTables) / 8); i += blockDim.x) ((double*)&tab)[i] = ((const double*)&c_tab)[i];
   if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
   __syncthreads();
-  const uint64_t v = row_begin + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  // persistent grid: the tables are staged once per CTA, each warp then walks whole 32-row blocks -- only the blocks this
+  // rank owns, and only those with a bit set in either bitmap word (late iterations touch a few thousand rows)
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t world = own_world > 1 ? own_world : 1;
+  const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5), w0 = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint64_t b0 = row_begin >> 5, b1 = (row_end + 31) >> 5;
+  const uint64_t first = b0 + ((uint64_t)own_rank + world - b0 % world) % world;
   unsigned long long my_changed = 0, my_out = 0;
-  if (v < row_end && (own_world <= 1 || ((v >> 5) % own_world) == own_rank)) {
-    const bool bc = bm_test(bm_cur, (uint32_t)v), bp = bm_test(bm_prev, (uint32_t)v);
-    if (bc || bp) {
+  for (uint64_t b = first + w0 * world; b < b1; b += warps * world) {
+    const uint32_t wc = __ldg(bm_cur + b), wp = __ldg(bm_prev + b);
+    if ((wc | wp) == 0u) continue;
+    const uint64_t v = b * 32 + lane;
+    const bool bc = (wc >> lane) & 1u, bp = (wp >> lane) & 1u;
+    if (v >= row_begin && v < row_end && (bc || bp)) {
       double s = ksum[v], e = kerr[v];
       if (bc) {
         uint32_t w[16];
@@ -488,8 +498,8 @@ __global__ void __launch_bounds__(256) k_finalize(uint64_t row_begin, uint64_t r
         const uint64_t d = sn >= so ? sn - so : 0ull;  // checked_sub().unwrap_or_default()
         kahan_add(s, e, __ddiv_rn(__ull2double_rn(d), t_plus_1));
         size_cache[v] = sn;
-        my_changed = 1;
-        if (fwd_ptr) my_out = fwd_ptr[v + 1] - fwd_ptr[v];
+        my_changed += 1;
+        if (fwd_ptr) my_out += fwd_ptr[v + 1] - fwd_ptr[v];
       } else {
         kahan_add(s, e, 0.0);  // the reference adds 0/(t+1) to every unchanged node; once is enough
       }
@@ -643,8 +653,8 @@ static int launch_pull(sb200_graph* g, const uint4* oldr, uint4* newr, const uin
       SB_CUDA(cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming));
       SB_CUDA(cudaEventCreate(&g->side_prof[0])); SB_CUDA(cudaEventCreate(&g->side_prof[1]));
     }
-    int sm_count = 148;
-    SB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, g->device));
+    if (!g->sm_count) SB_CUDA(cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, g->device));
+    const int sm_count = g->sm_count;
     const uint64_t world = (uint64_t)g->world, b0 = g->quad_row_begin >> 5, b1 = (g->quad_row_end - 1) >> 5;
     const uint64_t first = b0 + ((uint64_t)g->rank + world - b0 % world) % world;
     const uint64_t n_tasks = first <= b1 ? ((b1 - first) / world + 1) * 4 : 0;
@@ -674,8 +684,13 @@ static int launch_pull(sb200_graph* g, const uint4* oldr, uint4* newr, const uin
   }
   if (g->n_items) {
     PROF_BEGIN(g, FW);
-    SB_LAUNCH(k_pull_warp<FRONTIER>, div_up(g->n_items * 32, 256), 256, 0, s, g->n_items, g->n_multi_items,
-              g->item_row.p, g->item_start.p, (uint32_t)g->warp_row_begin, g->row_ptr.p, g->col.p, g->col_base, oldr, newr,
+    static const bool owned_list = env_flag("SB200_OWNED_ITEMS", true);
+    const bool listed = owned_list && g->world > 1 && g->owned_items.p;
+    const uint64_t n_launch = listed ? g->n_owned_items : g->n_items;
+    auto kern = listed ? k_pull_warp<FRONTIER, true> : k_pull_warp<FRONTIER, false>;
+    if (n_launch)
+    SB_LAUNCH(kern, div_up(n_launch * 32, 256), 256, 0, s, n_launch, g->n_multi_items,
+              listed ? g->owned_items.p : (const uint32_t*)nullptr, g->item_row.p, g->item_start.p, (uint32_t)g->warp_row_begin, g->row_ptr.p, g->col.p, g->col_base, oldr, newr,
               g->partial.p, bmp, bmc, po);
     SB_CHECK_LAUNCH();
     PROF_END(g, FW, g->own_frac * (per_edge * (double)g->E_warp + 68.0 * (double)(g->warp_row_end - g->warp_row_begin - g->n_multi_rows)));
@@ -931,7 +946,9 @@ int hb_step_launch(sb200_graph* g, bool with_barrier) {
   const uint64_t nrows = g->row_end - g->row_begin;
   if (nrows) {
     PROF_BEGIN(g, sb200_graph::F_FINALIZE);
-    SB_LAUNCH(k_finalize, div_up(nrows, 256), 256, 0, s, g->row_begin, g->row_end, newr, bmp, bmc, g->size_cache.p,
+    if (!g->sm_count) SB_CUDA(cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, g->device));
+    const unsigned fin_grid = (unsigned)std::min<uint64_t>(div_up(div_up(nrows, (uint64_t)std::max(g->world, 1)), 256) + 1, (uint64_t)g->sm_count * 8);
+    SB_LAUNCH(k_finalize, fin_grid, 256, 0, s, g->row_begin, g->row_end, newr, bmp, bmc, g->size_cache.p,
               g->kahan_sum.p, g->kahan_err.p, g->has_fwd ? g->fwd_ptr.p : (const uint32_t*)nullptr, (double)(g->t + 1),
               g->counters.p, (uint32_t)g->world, (uint32_t)g->rank);
     SB_CHECK_LAUNCH();
