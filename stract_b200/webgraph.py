@@ -509,15 +509,89 @@ def run_sharded_loop(engine, world_size, group=None, max_iters=0):
             return t, stats
 
 
+def shard_bounds(n_edges, rank, world_size):
+    """The contiguous slice of an edge stream rank `rank` ingests (equal `ceil(E / world)` slices, the last ones shorter)."""
+    chunk = -(-int(n_edges) // int(world_size)) if n_edges else 0
+    return min(rank * chunk, n_edges), min((rank + 1) * chunk, n_edges)
+
+
+def gather_edge_shards(shard, device, world_size, group=None):
+    """Every rank holds ONE shard of the edge stream on its host -- as the reference's workers each hold one webgraph
+    shard (entrypoint/ampc/harmonic_centrality/worker.rs) -- and needs the whole stream in HBM for the (replicated)
+    staging.  Each rank copies its shard over ITS OWN PCIe link and an all-gather over NVLink/NVSwitch assembles the
+    stream in rank order on every GPU: the stream crosses PCIe once in total instead of once per rank.
+
+    `shard`: Webgraph over host arrays (numpy uint64 / torch int64, ideally page-locked).  `device`: CUDA index, or "cpu"
+    (gloo; the host-logic tests).  Returns a Webgraph over device-resident arrays holding all shards concatenated."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cpu") if device == "cpu" else torch.device("cuda", int(device))
+    cuda = dev.type == "cuda"
+
+    def as_i64(a):
+        if isinstance(a, torch.Tensor):
+            return a.view(torch.int64) if a.dtype != torch.int64 else a
+        return torch.from_numpy(np.ascontiguousarray(a, np.uint64).view(np.int64))
+    cols = [as_i64(a) if shard.n_edges else torch.zeros(0, dtype=torch.int64) for a in (shard.from_lo, shard.from_hi, shard.to_lo, shard.to_hi, shard.rel)]
+    n_local = int(shard.n_edges)
+    counts = torch.tensor([n_local], dtype=torch.int64, device=dev)
+    all_counts = torch.zeros(world_size, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_counts, counts, group=group)
+    all_counts = [int(x) for x in all_counts.tolist()]
+    chunk = max(all_counts) if all_counts else 0
+    total = sum(all_counts)
+    if chunk == 0:
+        z = torch.zeros(0, dtype=torch.int64, device=dev)
+        return Webgraph.from_arrays(z, z, z, z, z)
+    # the gathered layout is already the concatenation iff every shard but the trailing ones is full
+    prefix_ok = all(all_counts[r] == chunk or sum(all_counts[r + 1:]) == 0 for r in range(world_size))
+    copy_s = torch.cuda.Stream(device=dev) if cuda else None
+    pending = []
+    for c in cols:
+        sl = torch.empty(chunk, dtype=torch.int64, device=dev)
+        out = torch.empty(world_size * chunk, dtype=torch.int64, device=dev)
+        if cuda:
+            copy_s.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(copy_s):
+                if n_local:
+                    sl[:n_local].copy_(c, non_blocking=True)
+                if n_local < chunk:
+                    sl[n_local:].zero_()
+            torch.cuda.current_stream(dev).wait_stream(copy_s)   # orders only the work queued so far: later copies overlap the gather
+            sl.record_stream(copy_s)
+        else:
+            sl[:n_local] = c
+            sl[n_local:] = 0
+        pending.append((dist.all_gather_into_tensor(out, sl, group=group, async_op=True), out, sl))
+    full = []
+    for work, out, sl in pending:
+        work.wait()
+        if prefix_ok:
+            full.append(out[:total])
+        else:
+            full.append(torch.cat([out[r * chunk: r * chunk + all_counts[r]] for r in range(world_size)]))
+    del pending
+    if cuda:
+        torch.cuda.current_stream(dev).synchronize()   # the library stages on its own stream: the stream must be complete before it reads
+    return Webgraph.from_arrays(*full)
+
+
 class ShardedHarmonicCentrality:
     """The distributed job (coordinator.rs:122-135): one process per GPU; every rank holds the full counter
     array, owns a destination-row range of the CSR, and runs `run_sharded_loop`."""
 
     @staticmethod
-    def calculate(graph, device, rank, world_size, max_iters=0, group=None, p2p=False, exchange=None):
+    def calculate(graph, device, rank, world_size, max_iters=0, group=None, p2p=False, exchange=None, ingest="replicated"):
         """exchange: None/"nccl" = byte-max all-reduce, "p2p" (or p2p=True) = fused stores over CUDA IPC peer
-        mappings, "symm" / "multicast" = fused stores over torch symmetric memory (unicast / NVSwitch multicast)."""
+        mappings, "symm" / "multicast" = fused stores over torch symmetric memory (unicast / NVSwitch multicast).
+        ingest: "replicated" = `graph` is the whole edge stream on every rank; "shards" = `graph` is THIS rank's shard of it
+        (host arrays) and the ranks assemble the stream in rank order with `gather_edge_shards`."""
+        if ingest == "shards" and world_size > 1:
+            graph = gather_edge_shards(graph, device, world_size, group)
+        elif ingest not in ("replicated", "shards"):
+            raise ValueError(f"ingest must be 'replicated' or 'shards', not {ingest!r}")
         dg = DeviceGraph(graph, device=device, rank=rank, world_size=world_size)
+        graph = None   # the gathered stream is not needed once the CSR is staged
         try:
             if world_size > 1:
                 if exchange in ("symm", "multicast"):

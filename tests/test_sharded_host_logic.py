@@ -100,3 +100,45 @@ def test_two_rank_exchange_protocol_gloo():
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok, _, _ in res), res
+
+
+def _gather_worker(rank, world, port, q, counts):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from stract_b200.webgraph import Webgraph, gather_edge_shards, shard_bounds
+        total = sum(counts)
+        rng = np.random.default_rng(11)
+        cols = [rng.integers(0, 2 ** 63, total, dtype=np.uint64) * np.uint64(2) + np.uint64(1) for _ in range(5)]   # top bit set too
+        lo = sum(counts[:rank]); hi = lo + counts[rank]
+        if rank % 2:   # numpy and torch shards both
+            shard = Webgraph.from_arrays(*[torch.from_numpy(c[lo:hi].view(np.int64).copy()) for c in cols])
+        else:
+            shard = Webgraph.from_arrays(*[c[lo:hi].copy() for c in cols])
+        full = gather_edge_shards(shard, "cpu", world)
+        ok = full.n_edges == total
+        for got, want in zip((full.from_lo, full.from_hi, full.to_lo, full.to_hi, full.rel), cols):
+            ok = ok and np.array_equal(got.numpy().view(np.uint64), want)
+        b = [shard_bounds(total, r, world) for r in range(world)]
+        ok = ok and b[0][0] == 0 and b[-1][1] == total and all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("counts", [[1000, 1000, 1000], [1000, 1000, 37], [334, 334, 332], [500, 0, 200], [0, 0, 0], [7, 0, 0]])
+def test_edge_shards_gathered_in_rank_order_gloo(counts):
+    """`gather_edge_shards`: equal shards (in-place prefix), a short or empty trailing shard, ragged shards (re-packed) and
+    an empty stream all give every rank the concatenation of the shards in rank order."""
+    world = len(counts)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, q, counts)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
