@@ -523,16 +523,17 @@ class MultiFieldSignalComputer:
         sf = np.ascontiguousarray(slot_field, np.uint8); st = np.ascontiguousarray(slot_term, np.uint32)
         nq, ns = sf.shape
         idf1 = np.zeros((nq, ns), np.float32); idf2 = np.zeros((nq, ns), np.float32)
-        for q in range(nq):
-            for x in range(ns):
-                f = int(sf[q, x])
-                if f == 0xFF or f & 0x80:
-                    continue
-                r = self.readers[f]
-                df = int(r.doc_freq[st[q, x]]) if st[q, x] != NO_TERM and st[q, x] < r.n_terms else 0
-                idf1[q, x] = idf(df, r.max_doc)
-                dfa = df if doc_freq_all_body is None else int(doc_freq_all_body[q][x])
-                idf2[q, x] = idf(dfa, r.max_doc)
+        dfa_all = None if doc_freq_all_body is None else np.asarray(doc_freq_all_body, np.int64).reshape(nq, ns)
+        for f, r in enumerate(self.readers):        # one vectorised pass per field (rule slots and pads keep idf 0)
+            m = sf == f
+            if not m.any():
+                continue
+            t = st[m]
+            known = (t != NO_TERM) & (t < r.n_terms)
+            df = np.zeros(t.shape, np.uint32)
+            df[known] = np.asarray(r.doc_freq, np.uint32)[t[known]]
+            idf1[m] = idf_array(df, r.max_doc)
+            idf2[m] = idf1[m] if dfa_all is None else idf_array(dfa_all[m].astype(np.uint32), r.max_doc)
         caches = [np.ascontiguousarray(compute_tf_cache(r.average_fieldnorm, self.k1, self.b)) for r in self.readers]
         farr = (B.SignalField * len(self.readers))()
         for i, (n_, r) in enumerate(zip(self.names, self.readers)):

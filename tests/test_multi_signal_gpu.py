@@ -49,9 +49,21 @@ def random_queries(rng, dfs, names, nq, ns):
     return sf, st
 
 
-def check_against_oracle(comp, pairs, cols, sf, st, k, numeric, boost=None):
-    docs, totals, n_out = comp.top_docs_batch(sf, st, k, slot_boost=boost)
+def check_against_oracle(comp, pairs, cols, sf, st, k, numeric, boost=None, dfa=None):
+    docs, totals, n_out = comp.top_docs_batch(sf, st, k, slot_boost=boost, doc_freq_all_body=dfa)
     names = comp.names
+    # the vectorised idf of the host mirror against the scalar f32 expression (tantivy bm25.rs:52-56), slot by slot
+    from stract_b200.bm25 import idf
+    for q in range(sf.shape[0]):
+        for x in range(sf.shape[1]):
+            f = int(sf[q, x])
+            if f == 0xFF or f & 0x80:
+                assert comp.last_inputs["idf"][q, x] == 0 and comp.last_inputs["idf_f"][q, x] == 0
+                continue
+            r = comp.readers[f]
+            df = int(r.doc_freq[st[q, x]]) if st[q, x] != NO_TERM and st[q, x] < r.n_terms else 0
+            assert comp.last_inputs["idf"][q, x] == idf(df, r.max_doc)
+            assert comp.last_inputs["idf_f"][q, x] == idf(df if dfa is None else int(dfa[q][x]), r.max_doc)
     osegs = [pairs[n][0] for n in names]
     caches = comp.last_inputs["caches"]
     coefs = [np.float32(comp.field_coefficient(n)) for n in names]
@@ -79,6 +91,9 @@ def test_multi_field_signals_bit_exact():
     for ns, nq, k in ((8, 24, 50), (14, 16, 200)):
         sf, st = random_queries(rng, dfs, comp.names, nq, ns)
         check_against_oracle(comp, pairs, cols, sf, st, k, numeric)
+    # WeightCache: the Bm25F idf from the AllBody doc_freq of the token instead of the field's own
+    sf, st = random_queries(rng, dfs, comp.names, 8, 8)
+    check_against_oracle(comp, pairs, cols, sf, st, 50, numeric, dfa=rng.integers(1, 20_000, sf.shape))
     # doc-range work items + merge: a batch dominated by one heavy query
     sf = np.full((12, 6), 0xFF, np.uint8); st = np.full((12, 6), NO_TERM, np.uint32)
     sf[0, :3] = [0, 1, 1]; st[0, :3] = [3, 3, 1]
