@@ -554,7 +554,7 @@ def main():
                 hgraph_n = Webgraph.from_arrays(*hostc)
                 cols = graph = None
                 torch.cuda.empty_cache()   # the timed call needs room for the gathered stream next to the staging temporaries
-                per, d2h_n, its, e2e_chk = [], 0, 0, None
+                per, d2h_n, its, e2e_chk, phases_n = [], 0, 0, None, []
                 n_warm = 2   # device memory pools, NCCL channels and the page-locked result blocks reach steady state
                 for step in range(n_warm + max(2, min(args.e2e_steps, 3))):
                     barrier()
@@ -563,13 +563,13 @@ def main():
                     rr = ShardedHarmonicCentrality.calculate(hgraph_n, local_rank, rank, world, exchange="p2p", ingest="shards")
                     chk = float(rr.values[:1024].sum())  # noqa: F841
                     e1.record(); torch.cuda.synchronize()
-                    torch.cuda.empty_cache()
                     t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
                     dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
                     nb = torch.tensor([len(rr.values) * 24, _i64(result_checksum(rr.ids_lo, rr.ids_hi, rr.values))], device=dev, dtype=torch.int64)
                     dist.all_reduce(nb)
                     if step >= n_warm:
                         per.append(float(t_ms.item())); d2h_n = int(nb[0].item()); its = rr.iterations
+                        phases_n.append(rr.info.get("phase_ms"))
                         e2e_chk = int(nb[1].item()) & ((1 << 64) - 1)
                     del rr
                 if gold:
@@ -578,6 +578,7 @@ def main():
                 result["e2e_n"] = {"value": E * its * len(per) / (sum(per) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": edges * 40,
                                    "d2h_bytes_per_step": d2h_n, "ms_per_step": sum(per) / len(per), "steps": len(per), "pinned_host": True,
                                    "ms_min_median_max": [round(min(per), 1), round(float(np.median(per)), 1), round(max(per), 1)],
+                                   "rank0_phase_ms": phases_n,
                                    "note": f"max over ranks per step; each of the {world} ranks copies its 1/{world} shard of the edge stream from page-locked "
                                            "host memory over its own PCIe link, an NCCL all-gather over NVLink assembles the stream on every GPU, "
                                            "then (replicated) staging + IPC set-up + sharded loop + owned results to the host"}

@@ -419,16 +419,21 @@ __global__ void k_copy_stale(const uint32_t* __restrict__ list, uint64_t n, cons
   newr[v * 4 + (gt & 3)] = oldr[v * 4 + (gt & 3)];
 }
 // fused exchange after a push: every owned row that was refreshed or changed in this iteration goes to the peers
-// (one quad per row, 16-B stores; the frontier is small by construction)
+// (the frontier is small by construction: one quad per OWNED bitmap word, i.e. per 32-row block, walks the set bits)
 __global__ void k_publish_rows(const uint32_t* __restrict__ bm_prev, const uint32_t* __restrict__ bm_cur, uint64_t n_rows,
                                const uint4* __restrict__ newr, const PeerOut peers) {
   const uint64_t gt = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  const uint64_t row = gt >> 2;
-  if (row >= n_rows || !owned_row(peers, (uint32_t)row)) return;
-  if (!(bm_test(bm_prev, (uint32_t)row) || bm_test(bm_cur, (uint32_t)row))) return;
-  const uint4 v = newr[row * 4 + (gt & 3)];
-  const uint32_t want = peers.sub ? __ldg(peers.sub + row) : 0xFFFFFFFFu;
-  for (int p = 0; p < peers.n; p++) if ((want >> peers.prank[p]) & 1u) peers.newr[p][row * 4 + (gt & 3)] = v;
+  const uint64_t w = (gt >> 2) * peers.world + peers.rank;     // this rank's k-th bitmap word
+  if (w * 32 >= n_rows) return;
+  uint32_t m = __ldg(bm_prev + w) | __ldg(bm_cur + w);
+  while (m) {
+    const uint64_t row = w * 32 + (uint64_t)(__ffs(m) - 1);
+    m &= m - 1;
+    if (row >= n_rows) break;
+    const uint4 v = newr[row * 4 + (gt & 3)];
+    const uint32_t want = peers.sub ? __ldg(peers.sub + row) : 0xFFFFFFFFu;
+    for (int p = 0; p < peers.n; p++) if ((want >> peers.prank[p]) & 1u) peers.newr[p][row * 4 + (gt & 3)] = v;
+  }
 }
 __global__ void __launch_bounds__(256) k_push(const uint32_t* __restrict__ list, const uint32_t* __restrict__ off,
     uint32_t n_front, uint64_t n_slots, const uint32_t* __restrict__ fwd_ptr, const uint32_t* __restrict__ fwd_dst,
@@ -755,7 +760,7 @@ static int run_push(sb200_graph* g, const uint4* oldr, uint4* newr, const uint32
   }
   if (g->p2p && g->n_peers > 0) {
     const PeerOut po = make_peer_out(g, true);
-    SB_LAUNCH(k_publish_rows, div_up(N * 4, 256), 256, 0, s, bmp, bmc, N, (const uint4*)newr, po);
+    SB_LAUNCH(k_publish_rows, div_up(div_up(words, (uint64_t)g->world) * 4, 256), 256, 0, s, bmp, bmc, N, (const uint4*)newr, po);
     SB_CHECK_LAUNCH();
   }
   return SB200_OK;

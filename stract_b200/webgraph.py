@@ -586,24 +586,38 @@ class ShardedHarmonicCentrality:
         mappings, "symm" / "multicast" = fused stores over torch symmetric memory (unicast / NVSwitch multicast).
         ingest: "replicated" = `graph` is the whole edge stream on every rank; "shards" = `graph` is THIS rank's shard of it
         (host arrays) and the ranks assemble the stream in rank order with `gather_edge_shards`."""
+        import time
+        phase, t_prev = {}, time.perf_counter()
+
+        def mark(name):   # wall time per phase of this rank (every phase ends in a synchronising call)
+            nonlocal t_prev
+            now = time.perf_counter()
+            phase[name] = round((now - t_prev) * 1e3, 1)
+            t_prev = now
         if ingest == "shards" and world_size > 1:
             graph = gather_edge_shards(graph, device, world_size, group)
+            mark("gather_shards")
         elif ingest not in ("replicated", "shards"):
             raise ValueError(f"ingest must be 'replicated' or 'shards', not {ingest!r}")
         dg = DeviceGraph(graph, device=device, rank=rank, world_size=world_size)
         graph = None   # the gathered stream is not needed once the CSR is staged
+        mark("create")
         try:
             if world_size > 1:
                 if exchange in ("symm", "multicast"):
                     dg.exchange_kind = dg.enable_symmetric(group, multicast=(exchange == "multicast"))
                 elif p2p or exchange == "p2p":
                     dg.enable_p2p(group)
+            mark("exchange_setup")
             if world_size > 1 and getattr(dg, "p2p", False) and exchange not in ("symm", "multicast"):
                 t, stats = dg.run_sharded(max_iters)          # round loop + device-side barrier behind the ABI
             else:
                 t, stats = run_sharded_loop(dg, world_size, group, max_iters)
+            mark("loop")
             lo, hi, c = dg.result()
             info = dg.info()
+            mark("result")
+            info["phase_ms"] = phase
             return HarmonicCentrality(lo, hi, c, info["n_nodes"], t, stats, info)
         finally:
             dg.close()
