@@ -349,6 +349,8 @@ def main():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "symm", "multicast"],
                     help="multi-GPU fused exchange transport: CUDA IPC peer mappings (default), torch symmetric memory "
                          "unicast, or NVSwitch multicast stores")
+    ap.add_argument("--sweep", action="store_true", help="N>1: time the exchange variants (side-stream CTAs, subscriber filter, owned item "
+                    "list, NVSwitch multicast) on one staged graph in one process and print one JSON line; no bench line")
     ap.add_argument("--ref-budget-s", type=float, default=170.0, help="--impl reference: wall budget of the timed loops")
     ap.add_argument("--write-golden", action="store_true", help="N=1, after a green oracle check: rewrite tests/golden/path1_c2.json")
     args = ap.parse_args()
@@ -464,6 +466,67 @@ def main():
         E = info["n_edges_kept"]
 
         behind_abi = exchange_kind == "p2p"   # sb200_hyperball_run_sharded: round loop + device-side barrier, no NCCL
+
+        if args.sweep:
+            # ---- tuning sweep: same staged graph, same process, one variant after the other; each is fingerprinted by the
+            #      per-iteration changed counts summed over the ranks (they must equal the first variant's)
+            def time_variant(handle, label, run, steps=3, warm=2):
+                for _ in range(warm):
+                    handle.reset(); run()
+                handle.set_profiling(True)
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                st = None
+                for _ in range(steps):
+                    handle.reset(); _t, st = run()
+                e1.record()
+                barrier()
+                prof = handle.profile(); handle.set_profiling(False)
+                t_ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+                dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+                fp = torch.tensor([s["n_changed"] for s in st] + [0] * (32 - len(st)), device=dev, dtype=torch.int64)[:32]
+                dist.all_reduce(fp)
+                out = {"variant": label, "ms_per_step": round(float(t_ms.item()), 3), "iterations": len(st),
+                       "iter_ms_rank0": [round(s["ms"], 3) for s in st],
+                       "kernels_rank0": {q["name"]: round(q["ms"] / q["launches"], 3) for q in prof if q["launches"]},
+                       "changed_counts": [int(x) for x in fp.tolist()[:len(st)]]}
+                if rank == 0:
+                    print("[sweep] " + json.dumps(out), file=sys.stderr, flush=True)
+                return out
+            sweep = []
+            variants = [("filter side2", {"publish_all": 0, "quad_side_ctas": 2, "owned_items": 1}),
+                        ("filter side0", {"publish_all": 0, "quad_side_ctas": 0, "owned_items": 1}),
+                        ("all side0", {"publish_all": 1, "quad_side_ctas": 0, "owned_items": 1}),
+                        ("all side2", {"publish_all": 1, "quad_side_ctas": 2, "owned_items": 1}),
+                        ("filter side1", {"publish_all": 0, "quad_side_ctas": 1, "owned_items": 1}),
+                        ("filter side4", {"publish_all": 0, "quad_side_ctas": 4, "owned_items": 1}),
+                        ("filter side8", {"publish_all": 0, "quad_side_ctas": 8, "owned_items": 1})]
+            if exchange_kind == "p2p":
+                for label, opts in variants:
+                    for k_, v_ in opts.items():
+                        dg.set_option(k_, v_)
+                    sweep.append(time_variant(dg, label, dg.run_sharded))
+            dg.close(); dg = None
+            try:   # NVSwitch multicast stores over torch symmetric memory (one store per row, the switch replicates), host-side round loop
+                dg = DeviceGraph(graph, device=local_rank, rank=rank, world_size=world)
+                kind = dg.enable_symmetric(multicast=True)
+                for side in (0, 2):
+                    dg.set_option("quad_side_ctas", side)
+                    sweep.append(time_variant(dg, f"symmetric-memory {kind} side{side}", lambda: run_sharded_loop(dg, world)))
+            except Exception as ex:  # noqa: BLE001
+                sweep.append({"variant": "symmetric-memory multicast", "error": repr(ex)[:300]})
+            finally:
+                if dg is not None:
+                    dg.close(); dg = None
+            if rank == 0:
+                ref = sweep[0].get("changed_counts")
+                for v in sweep:
+                    if "changed_counts" in v:
+                        v["same_counts_as_first"] = v["changed_counts"] == ref
+                print(json.dumps({"sweep": sweep, "n_gpus": world, "workload": f"R-MAT {args.nodes} nodes / {args.edges} edges (C2), {E} kept edges"}))
+            dist.destroy_process_group()
+            return 0
 
         def one_step():
             dg.reset()

@@ -249,6 +249,12 @@ SB200_API int sb200_inbound_similarity(sb200_graph* g, const uint64_t* liked_lo,
                                        const uint64_t* cand_lo, const uint64_t* cand_hi, uint32_t n_cand, int normalized,
                                        double self_score, double* scores);
 
+/* Tuning switches of one handle (the SB200_* environment variables give the defaults): "quad_side_ctas" (CTAs per SM of the
+ * short-row kernel on the side stream of the fused exchange, 0 = one stream), "owned_items" (0 / 1: launch the long-row kernel
+ * over the owned work items only), "publish_all" (0 / 1: store produced rows into every peer, no subscriber filter).  All
+ * ranks of a sharded computation must use the same "publish_all".  Not while an iteration is in flight. */
+SB200_API int sb200_hyperball_set_option(sb200_graph* g, const char* name, double value);
+
 /* Device-memory arena diagnostics.  With SB200_ARENA=1 in the environment, staging temporaries, the CSR and the
  * state of single-rank handles are sub-allocated from large slabs that are kept for the life of the process
  * (deterministic, no driver call per allocation once warm) instead of the driver's stream-ordered pool.

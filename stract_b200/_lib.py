@@ -85,6 +85,7 @@ def declare(L):
     f("sb200_hyperball_group_run", i32, C.POINTER(vp), i32, u32, C.POINTER(u32), C.POINTER(IterStats), u32)
     f("sb200_graph_ownership", i32, vp, vp, vp)
     f("sb200_graph_distances", i32, vp, vp, vp, vp, u32, u32, u32, i32, vp)
+    f("sb200_hyperball_set_option", i32, vp, C.c_char_p, C.c_double)
     f("sb200_inbound_similarity", i32, vp, vp, vp, u32, vp, vp, u32, vp, vp, u32, i32, C.c_double, vp)
     f("sb200_approx_harmonic", i32, vp, vp, vp, u32, u32, u64, vp, vp, vp, u64, C.POINTER(u64))
     f("sb200_hyperball_state_bytes", i32, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))

@@ -145,6 +145,16 @@ int sb200_hyperball_set_policy(sb200_graph* g, double dense_frac, double push_di
   return SB200_OK;
 }
 
+int sb200_hyperball_set_option(sb200_graph* g, const char* name, double value) {
+  if (!g || !name) SB_FAIL(SB200_EINVAL, "NULL graph handle or option name");
+  if (g->step_in_flight) SB_FAIL(SB200_ESTATE, "an iteration is in flight");
+  if (!strcmp(name, "quad_side_ctas")) { if (value < 0 || value > 16) SB_FAIL(SB200_EINVAL, "quad_side_ctas must be 0..16"); g->opt_side_ctas = (int)value; }
+  else if (!strcmp(name, "owned_items")) g->opt_owned_list = value != 0.0 ? 1 : 0;
+  else if (!strcmp(name, "publish_all")) g->publish_all = value != 0.0;
+  else SB_FAIL(SB200_EINVAL, "unknown option '%s'", name);
+  return SB200_OK;
+}
+
 int sb200_hyperball_reset(sb200_graph* g) { SB_ENTER(g); g->reuse++; return hb_reset(g); }
 
 int sb200_hyperball_step(sb200_graph* g, sb200_iter_stats* stats) { SB_ENTER(g); return hb_step(g, stats); }

@@ -100,6 +100,7 @@ struct sb200_graph {
   cudaEvent_t prof_ev[F_COUNT][2] = {{nullptr}};
   // fused exchange: the short-row kernel runs on a second stream beside the long-row kernel (hyperball.cu, launch_pull)
   int sm_count = 0;
+  int opt_side_ctas = -1, opt_owned_list = -1;   // -1: take the environment default at first use (sb200_hyperball_set_option)
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, side_prof[2] = {nullptr, nullptr};
   bool side_prof_used = false;

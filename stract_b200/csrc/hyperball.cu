@@ -647,7 +647,8 @@ static int launch_pull(sb200_graph* g, const uint4* oldr, uint4* newr, const uin
   const int FQ = FRONTIER ? sb200_graph::F_PULL_QUAD_FRONT : sb200_graph::F_PULL_QUAD_DENSE;
   const double per_edge = FRONTIER ? 4.0 : 68.0;  // col index (+ the 64-B gather when every source is read)
   // fused exchange: short rows on the side stream, next to the long-row kernel (see k_pull_quad_owned)
-  static const int side_ctas = (int)env_f("SB200_QUAD_SIDE_CTAS", 2.0);
+  if (g->opt_side_ctas < 0) g->opt_side_ctas = (int)env_f("SB200_QUAD_SIDE_CTAS", 2.0);
+  const int side_ctas = g->opt_side_ctas;
   const bool side_quad = side_ctas > 0 && g->world > 1 && g->p2p && g->n_peers > 0 && g->n_items && g->quad_row_end > g->quad_row_begin;
   if (side_quad) {
     if (!g->side_stream) {
@@ -689,8 +690,8 @@ static int launch_pull(sb200_graph* g, const uint4* oldr, uint4* newr, const uin
   }
   if (g->n_items) {
     PROF_BEGIN(g, FW);
-    static const bool owned_list = env_flag("SB200_OWNED_ITEMS", true);
-    const bool listed = owned_list && g->world > 1 && g->owned_items.p;
+    if (g->opt_owned_list < 0) g->opt_owned_list = env_flag("SB200_OWNED_ITEMS", true) ? 1 : 0;
+    const bool listed = g->opt_owned_list > 0 && g->world > 1 && g->owned_items.p;
     const uint64_t n_launch = listed ? g->n_owned_items : g->n_items;
     auto kern = listed ? k_pull_warp<FRONTIER, true> : k_pull_warp<FRONTIER, false>;
     if (n_launch)

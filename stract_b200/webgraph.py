@@ -135,6 +135,10 @@ class DeviceGraph:
     def reset(self):
         check(self._L.sb200_hyperball_reset(self._h))
 
+    def set_option(self, name, value):
+        """Tuning switch of this handle: "quad_side_ctas", "owned_items", "publish_all" (sb200_hyperball_set_option)."""
+        check(self._L.sb200_hyperball_set_option(self._h, name.encode(), float(value)))
+
     def set_policy(self, dense_frac=-1.0, push_div=-1.0, force_mode=-1):
         check(self._L.sb200_hyperball_set_policy(self._h, dense_frac, push_div, force_mode))
 

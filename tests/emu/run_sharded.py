@@ -86,7 +86,7 @@ def run(world, fused, force_mode, reuse):
     return modes_seen
 
 
-def run_group(world, force_mode):
+def run_group(world, force_mode, options=None):
     """The round loop behind the ABI, single-process form: link + run, then the union of the owned results."""
     from stract_b200.webgraph import DeviceGroup
     d = synth.rmat_graph(3000, 40000, seed=7)
@@ -98,16 +98,21 @@ def run_group(world, force_mode):
     for rep in range(2):
         if rep:
             grp.reset()
+            for h in grp.ranks:                     # the tuning switches may change between computations of one handle
+                for k, v in (options or {}).items():
+                    h.set_option(k, v)
         t, stats = grp.run()
         lo, hi, c = grp.result()
         assert t == f["iters"] and np.array_equal(lo, f["ids_lo"]) and np.array_equal(hi, f["ids_hi"]) and np.array_equal(c, f["centrality"]), (world, force_mode, rep)
     grp.close()
-    print("group world", world, "force_mode", force_mode, "ok", flush=True)
+    print("group world", world, "force_mode", force_mode, "options", options, "ok", flush=True)
 
 
 for world in (2, 4, 8):
     run_group(world, -1)
 run_group(3, 2)
+run_group(4, -1, {"quad_side_ctas": 0, "publish_all": 1, "owned_items": 0})
+run_group(3, -1, {"quad_side_ctas": 4, "publish_all": 0, "owned_items": 1})
 for world in (2, 3):
     for fused in (True, False):
         run(world, fused, -1, False)
