@@ -346,9 +346,11 @@ def main():
     ap.add_argument("--no-bm25", action="store_true")
     ap.add_argument("--no-c1", action="store_true")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL byte-max all-reduce exchange instead of the fused peer-memory stores")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "symm", "multicast"],
-                    help="multi-GPU fused exchange transport: CUDA IPC peer mappings (default), torch symmetric memory "
-                         "unicast, or NVSwitch multicast stores")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "symm", "multicast"],
+                    help="multi-GPU fused exchange transport: CUDA IPC peer mappings, torch symmetric memory unicast, or NVSwitch "
+                         "multicast stores; auto (default) = multicast from 8 GPUs up (measured: 16.9 vs 27.0 ms per step at N = 8, "
+                         "profiles/r02_trip10_8gpu_sweep.log), CUDA IPC peer stores + device-side barrier below, and whenever the "
+                         "multicast binding is not available")
     ap.add_argument("--sweep", action="store_true", help="N>1: time the exchange variants (side-stream CTAs, subscriber filter, owned item "
                     "list, NVSwitch multicast) on one staged graph in one process and print one JSON line; no bench line")
     ap.add_argument("--ref-budget-s", type=float, default=170.0, help="--impl reference: wall budget of the timed loops")
@@ -457,9 +459,29 @@ def main():
         from stract_b200.webgraph import run_sharded_loop
         dg = DeviceGraph(graph, device=local_rank, rank=rank, world_size=world)
         exchange_kind = "nccl"
-        if args.exchange in ("symm", "multicast"):
-            exchange_kind = "symmetric-memory " + dg.enable_symmetric(multicast=(args.exchange == "multicast"))
-        elif not args.no_p2p:
+        want = args.exchange
+        if want == "auto":
+            want = "multicast" if world >= 8 else "p2p"
+        if args.no_p2p:
+            want = "nccl"
+        if want in ("symm", "multicast"):
+            kind, ok = None, 0
+            try:
+                kind = dg.enable_symmetric(multicast=(want == "multicast"))
+                ok = 1 if (want == "symm" or kind == "multicast") else 0
+            except Exception as ex:  # noqa: BLE001
+                print(f"[bench] rank {rank}: symmetric-memory exchange not available: {ex!r}"[:400], file=sys.stderr, flush=True)
+            okt = torch.tensor([ok], device=dev, dtype=torch.int64)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            if int(okt.item()) == 1 or args.exchange != "auto":
+                if kind is None:
+                    raise RuntimeError("--exchange " + args.exchange + ": the symmetric-memory binding failed on this rank")
+                exchange_kind = "symmetric-memory " + kind
+            else:   # auto: no multicast on this box -- peer stores over CUDA IPC on a fresh handle
+                dg.close()
+                dg = DeviceGraph(graph, device=local_rank, rank=rank, world_size=world)
+                want = "p2p"
+        if want == "p2p":
             dg.enable_p2p()
             exchange_kind = "p2p"
         info = dg.info()
@@ -598,7 +620,7 @@ def main():
         #      reference's workers each hold one webgraph shard); the timed call copies it over the rank's own PCIe link,
         #      all-gathers the stream over NVLink, stages (replicated), exchanges the IPC blobs, runs the
         #      sharded loop and reads back its owned share
-        if not args.no_e2e and exchange_kind == "p2p":
+        if not args.no_e2e and exchange_kind != "nccl":
             import psutil
             from stract_b200.webgraph import ShardedHarmonicCentrality, shard_bounds
             need = edges * 40
@@ -608,44 +630,48 @@ def main():
             if int(ok.item()) == 0:
                 result["e2e_n"] = {"skipped": f"host RAM {avail / 2**30:.0f} GiB < 1.3 x {need / 2**30:.0f} GiB (the page-locked shards of the edge stream)"}
             else:
-                s_lo, s_hi = shard_bounds(edges, rank, world)
-                hostc = []
-                for cc in cols:
-                    hh = torch.empty((s_hi - s_lo,), dtype=cc.dtype, pin_memory=True)
-                    hh.copy_(cc[s_lo:s_hi])
-                    hostc.append(hh)
-                hgraph_n = Webgraph.from_arrays(*hostc)
-                cols = graph = None
-                torch.cuda.empty_cache()   # the timed call needs room for the gathered stream next to the staging temporaries
-                per, d2h_n, its, e2e_chk, phases_n = [], 0, 0, None, []
-                n_warm = 2   # device memory pools, NCCL channels and the page-locked result blocks reach steady state
-                for step in range(n_warm + max(2, min(args.e2e_steps, 3))):
-                    barrier()
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                    rr = ShardedHarmonicCentrality.calculate(hgraph_n, local_rank, rank, world, exchange="p2p", ingest="shards")
-                    chk = float(rr.values[:1024].sum())  # noqa: F841
-                    e1.record(); torch.cuda.synchronize()
-                    t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-                    dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-                    nb = torch.tensor([len(rr.values) * 24, _i64(result_checksum(rr.ids_lo, rr.ids_hi, rr.values))], device=dev, dtype=torch.int64)
-                    dist.all_reduce(nb)
-                    if step >= n_warm:
-                        per.append(float(t_ms.item())); d2h_n = int(nb[0].item()); its = rr.iterations
-                        phases_n.append(rr.info.get("phase_ms"))
-                        e2e_chk = int(nb[1].item()) & ((1 << 64) - 1)
-                    del rr
-                if gold:
-                    parity["c2"]["equal"]["e2e_result_checksum"] = e2e_chk == gold["result_checksum"]
-                    parity["c2"]["green"] = all(parity["c2"]["equal"].values())
-                result["e2e_n"] = {"value": E * its * len(per) / (sum(per) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": edges * 40,
-                                   "d2h_bytes_per_step": d2h_n, "ms_per_step": sum(per) / len(per), "steps": len(per), "pinned_host": True,
-                                   "ms_min_median_max": [round(min(per), 1), round(float(np.median(per)), 1), round(max(per), 1)],
-                                   "rank0_phase_ms": phases_n,
-                                   "note": f"max over ranks per step; each of the {world} ranks copies its 1/{world} shard of the edge stream from page-locked "
-                                           "host memory over its own PCIe link, an NCCL all-gather over NVLink assembles the stream on every GPU, "
-                                           "then (replicated) staging + IPC set-up + sharded loop + owned results to the host"}
-                del hostc, hgraph_n
+                try:
+                    s_lo, s_hi = shard_bounds(edges, rank, world)
+                    hostc = []
+                    for cc in cols:
+                        hh = torch.empty((s_hi - s_lo,), dtype=cc.dtype, pin_memory=True)
+                        hh.copy_(cc[s_lo:s_hi])
+                        hostc.append(hh)
+                    hgraph_n = Webgraph.from_arrays(*hostc)
+                    cols = graph = None
+                    torch.cuda.empty_cache()   # the timed call needs room for the gathered stream next to the staging temporaries
+                    per, d2h_n, its, e2e_chk, phases_n = [], 0, 0, None, []
+                    n_warm = 2   # device memory pools, NCCL channels and the page-locked result blocks reach steady state
+                    for step in range(n_warm + max(2, min(args.e2e_steps, 3))):
+                        barrier()
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        rr = ShardedHarmonicCentrality.calculate(hgraph_n, local_rank, rank, world, exchange="p2p", ingest="shards")
+                        chk = float(rr.values[:1024].sum())  # noqa: F841
+                        e1.record(); torch.cuda.synchronize()
+                        t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+                        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+                        nb = torch.tensor([len(rr.values) * 24, _i64(result_checksum(rr.ids_lo, rr.ids_hi, rr.values))], device=dev, dtype=torch.int64)
+                        dist.all_reduce(nb)
+                        if step >= n_warm:
+                            per.append(float(t_ms.item())); d2h_n = int(nb[0].item()); its = rr.iterations
+                            phases_n.append(rr.info.get("phase_ms"))
+                            e2e_chk = int(nb[1].item()) & ((1 << 64) - 1)
+                        del rr
+                    if gold:
+                        parity["c2"]["equal"]["e2e_result_checksum"] = e2e_chk == gold["result_checksum"]
+                        parity["c2"]["green"] = all(parity["c2"]["equal"].values())
+                    result["e2e_n"] = {"value": E * its * len(per) / (sum(per) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": edges * 40,
+                                       "d2h_bytes_per_step": d2h_n, "ms_per_step": sum(per) / len(per), "steps": len(per), "pinned_host": True,
+                                       "ms_min_median_max": [round(min(per), 1), round(float(np.median(per)), 1), round(max(per), 1)],
+                                       "rank0_phase_ms": phases_n,
+                                       "note": f"max over ranks per step; each of the {world} ranks copies its 1/{world} shard of the edge stream from page-locked "
+                                               "host memory over its own PCIe link, an NCCL all-gather over NVLink assembles the stream on every GPU, "
+                                               "then (replicated) staging + CUDA IPC set-up + sharded loop (peer stores + device-side barrier) + owned results to the host",
+                                       "exchange": "p2p (CUDA IPC) -- the end-to-end call always uses this transport; the kernel-loop value above used: " + str(exchange_kind)}
+                    del hostc, hgraph_n
+                except Exception as ex:  # noqa: BLE001  (the kernel-loop line above must survive a failing end-to-end leg)
+                    result["e2e_n"] = {"error": repr(ex)[:400]}
 
     # ---- e2e: the C-ABI call sequence from HOST buffers (N = 1) ----------------------------------
     e2e, host = None, None

@@ -647,7 +647,12 @@ static int launch_pull(sb200_graph* g, const uint4* oldr, uint4* newr, const uin
   const int FQ = FRONTIER ? sb200_graph::F_PULL_QUAD_FRONT : sb200_graph::F_PULL_QUAD_DENSE;
   const double per_edge = FRONTIER ? 4.0 : 68.0;  // col index (+ the 64-B gather when every source is read)
   // fused exchange: short rows on the side stream, next to the long-row kernel (see k_pull_quad_owned)
-  if (g->opt_side_ctas < 0) g->opt_side_ctas = (int)env_f("SB200_QUAD_SIDE_CTAS", 2.0);
+  if (g->opt_side_ctas < 0) {
+    // measured on C2 (profiles/r02_trip9_*gpu.log, r02_trip10_8gpu_sweep.log): unicast peer stores gain from the side stream at
+    // 2 and 4 ranks (35.0 -> 33.1, 22.1 -> 17.5 ms) and lose at 8 (27.0 -> 32.6 ms); one NVSwitch multicast target gains (19.5 -> 16.9)
+    const bool multicast_target = g->n_peers < g->world - 1;
+    g->opt_side_ctas = (int)env_f("SB200_QUAD_SIDE_CTAS", (multicast_target || g->world <= 4) ? 2.0 : 0.0);
+  }
   const int side_ctas = g->opt_side_ctas;
   const bool side_quad = side_ctas > 0 && g->world > 1 && g->p2p && g->n_peers > 0 && g->n_items && g->quad_row_end > g->quad_row_begin;
   if (side_quad) {
