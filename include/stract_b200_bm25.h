@@ -63,6 +63,40 @@ SB200_API int sb200_segment_get_info(const sb200_segment* seg, sb200_segment_inf
  * CoreSignals read per candidate (core/src/ranking/signals/core/non_text.rs).  Column j holds the signal's
  * *score* (the host applies value->score transforms such as score_rank once at open time). */
 SB200_API int sb200_signals_create(const double* const* columns, uint32_t n_cols, uint32_t max_doc, int device, sb200_signals** out);
+/* The same table built from the RAW fast-field columns: the library applies the numeric CoreSignals' value -> score
+ * transforms (core/src/ranking/signals/core/non_text.rs) on the device, one pass per column at open time.
+ *   kind                   reference                                            raw column
+ *   SB200_NUM_IDENTITY     HostCentrality, PageCentrality (:117-155, :203-241)  f64
+ *   SB200_NUM_RANK         score_rank (:50-59): HostCentralityRank, PageCentralityRank   u64  (evaluated on the host: libm ln)
+ *   SB200_NUM_BOOL         IsHomepage (:289-332)                                bool8
+ *   SB200_NUM_BOOL_NOT     HasAds: score = !likely_has_ads (:730-771)           bool8
+ *   SB200_NUM_INVERSE      score_trackers / score_digits / score_slashes (:61-74): TrackerScore, UrlDigits, UrlSlashes   u64
+ *   SB200_NUM_FETCH_TIME   FetchTimeMs over fetch_time_ms_cache (1000 entries, computer/mod.rs:257-259)                  u64
+ *   SB200_NUM_UPDATE_TIME  UpdateTimestamp: score_timestamp (:25-42) over update_time_cache; p0 = current_timestamp      u64
+ *   SB200_NUM_LINK_DENSITY score_link_density (:76-83)                          f64
+ *   SB200_NUM_REGION       score_region (:85-101): lut[region id] = RegionCount::score (count / total, webpage/region.rs:219-227),
+ *                          p1 != 0: a region other than All is selected, p0 = its id (+50); lut NULL = no RegionCount: all 0     u64 */
+#define SB200_NUM_IDENTITY 0u
+#define SB200_NUM_RANK 1u
+#define SB200_NUM_BOOL 2u
+#define SB200_NUM_BOOL_NOT 3u
+#define SB200_NUM_INVERSE 4u
+#define SB200_NUM_FETCH_TIME 5u
+#define SB200_NUM_UPDATE_TIME 6u
+#define SB200_NUM_LINK_DENSITY 7u
+#define SB200_NUM_REGION 8u
+#define SB200_NUM_U64 0u
+#define SB200_NUM_F64 1u
+#define SB200_NUM_BOOL8 2u
+typedef struct {
+  uint32_t kind, dtype;      /* SB200_NUM_* transform, SB200_NUM_U64 / F64 / BOOL8 element type of `raw` */
+  const void* raw;           /* [max_doc], host or device */
+  double p0, p1;
+  const double* lut; uint32_t lut_len, _pad;
+} sb200_numeric_column;
+SB200_API int sb200_signals_create_raw(const sb200_numeric_column* cols, uint32_t n_cols, uint32_t max_doc, int device, sb200_signals** out);
+/* rows [first_doc, first_doc + n_docs) of the table, row-major [n_docs][n_cols] (inspection / tests) */
+SB200_API int sb200_signals_read(const sb200_signals* s, uint32_t first_doc, uint32_t n_docs, double* rows_out);
 SB200_API void sb200_signals_destroy(sb200_signals* s);
 
 #define SB200_MODE_AND 0     /* all clauses Occur::Must  -> Intersection, score = left + right + sum(others) */

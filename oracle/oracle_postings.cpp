@@ -919,3 +919,49 @@ ORC_API uint64_t orc_bitpack(const uint64_t* vals, const uint8_t* bits, uint32_t
   return o.size();
 }
 ORC_API uint64_t orc_extract_bits(const uint8_t* data, uint64_t len, uint64_t addr_bits, uint8_t nb) { return tis::extract_bits(data, (size_t)len, (size_t)addr_bits, nb); }
+
+// ---------------------------------------------------------------- numeric signals -------------
+// core/src/ranking/signals/core/non_text.rs: the value -> score part of every numeric CoreSignal's `compute`, written the way
+// the reference writes it (one function per transform); `which` names the signal.
+namespace numsig {
+static double time_cache_calculation(double hours_since_update) { const double HALF_LIFE = 24.0 * 3.0; return HALF_LIFE / (hours_since_update + HALF_LIFE); }   // :44-47
+static double score_timestamp(uint64_t page_timestamp, bool have_now, uint64_t now) {   // :25-42
+  if (page_timestamp >= (have_now ? now : 0)) return 0.0;
+  uint64_t d = now > page_timestamp ? now - page_timestamp : 0;   // saturating_sub
+  if (d < 1) d = 1;
+  const uint64_t hours = d / 3600;
+  return hours < 3ull * 365 * 24 ? time_cache_calculation((double)hours) : 0.0;   // update_time_cache.get(hours).unwrap_or(0.0)
+}
+static double score_rank(double rank) { const double v = 10.0 - std::log(1.0 + rank) / std::log(8.0); return v > 0.0 ? v : 0.0; }   // :50-59, f64::log(base)
+static double score_inverse(double x) { return 1.0 / (x + 1.0); }   // score_trackers / score_digits / score_slashes :61-74
+static double score_link_density(double x) { return x > 0.5 ? 0.0 : 1.0 - x; }   // :76-83
+}  // namespace numsig
+// which: 0 HostCentrality/PageCentrality, 1 *CentralityRank, 2 IsHomepage, 3 HasAds, 4 TrackerScore/UrlDigits/UrlSlashes, 5 FetchTimeMs,
+//        6 UpdateTimestamp (now < 0: no current timestamp), 7 LinkDensity, 8 Region (counts NULL: no RegionCount; selected < 0: none / All)
+ORC_API void orc_numeric_scores(uint32_t which, const uint64_t* raw_u, const double* raw_f, const uint8_t* raw_b, uint32_t n, int64_t now,
+                                const int64_t* region_counts, uint32_t n_regions, uint64_t region_total, int64_t selected, double* out) {
+  for (uint32_t d = 0; d < n; d++) {
+    double s = 0.0;
+    switch (which) {
+      case 0: s = raw_f[d]; break;
+      case 1: s = numsig::score_rank((double)raw_u[d]); break;
+      case 2: s = raw_b[d] ? 1.0 : 0.0; break;
+      case 3: s = !raw_b[d] ? 1.0 : 0.0; break;
+      case 4: s = numsig::score_inverse((double)raw_u[d]); break;
+      case 5: { const uint64_t x = raw_u[d]; s = x >= 1000 ? 0.0 : 1.0 / ((double)x + 1.0); break; }   // fetch_time_ms_cache, computer/mod.rs:257-259
+      case 6: s = numsig::score_timestamp(raw_u[d], now >= 0, now >= 0 ? (uint64_t)now : 0); break;
+      case 7: s = numsig::score_link_density(raw_f[d]); break;
+      case 8: {   // score_region :85-101 + RegionCount::score (webpage/region.rs:219-227); a negative count = None
+        if (region_counts) {
+          const uint64_t id = raw_u[d];
+          const double boost = (selected >= 0 && (uint64_t)selected == id) ? 50.0 : 0.0;
+          double share = 0.0;
+          if (id < n_regions && region_counts[id] >= 0) share = (double)region_counts[id] / (double)region_total;
+          s = boost + share;
+        }
+        break;
+      }
+    }
+    out[d] = s;
+  }
+}

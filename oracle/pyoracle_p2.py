@@ -287,3 +287,25 @@ def bitpack(vals, bits):
 def extract_bits(data, addr_bits, num_bits):
     d = np.ascontiguousarray(data, np.uint8)
     return int(_L().orc_extract_bits(d, d.size, int(addr_bits), int(num_bits)))
+
+
+def numeric_scores(which, raw, now=None, region_counts=None, region_total=0, selected=None):
+    """orc_numeric_scores: the value -> score transform of one numeric CoreSignal over a raw fast-field column
+    (which: 0 identity f64, 1 score_rank, 2 IsHomepage, 3 HasAds, 4 inverse, 5 FetchTimeMs, 6 UpdateTimestamp, 7 LinkDensity, 8 Region)."""
+    L = _L()
+    fn = L.orc_numeric_scores
+    fn.restype = None
+    fn.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int64, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int64, C.c_void_p]
+    u = f = b = None
+    if which in (0, 7):
+        f = np.ascontiguousarray(raw, np.float64); n = f.size
+    elif which in (2, 3):
+        b = np.ascontiguousarray(raw, np.uint8); n = b.size
+    else:
+        u = np.ascontiguousarray(raw, np.uint64); n = u.size
+    rc = None if region_counts is None else np.array([-1 if c is None else int(c) for c in region_counts], np.int64)
+    out = np.zeros(n, np.float64)
+    fn(which, None if u is None else u.ctypes.data, None if f is None else f.ctypes.data, None if b is None else b.ctypes.data, n,
+       -1 if now is None else int(now), None if rc is None else rc.ctypes.data, 0 if rc is None else rc.size, int(region_total),
+       -1 if selected is None else int(selected), out.ctypes.data)
+    return out

@@ -30,6 +30,11 @@ class SignalField(C.Structure):
     _fields_ = [("seg", C.c_void_p), ("tf_cache256", C.c_void_p), ("k1", C.c_float), ("bm25f_coefficient", C.c_float)]
 
 
+class NumericColumn(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("dtype", C.c_uint32), ("raw", C.c_void_p), ("p0", C.c_double), ("p1", C.c_double),
+                ("lut", C.c_void_p), ("lut_len", C.c_uint32), ("_pad", C.c_uint32)]
+
+
 class SignalOp(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("field", C.c_uint32), ("chain", C.c_uint32), ("col", C.c_uint32), ("coeff", C.c_double)]
 
@@ -47,6 +52,8 @@ def proto(L, f):
     f("sb200_segment_destroy", None, vp)
     f("sb200_segment_get_info", i32, vp, C.POINTER(SegmentInfo))
     f("sb200_signals_create", i32, vp, u32, u32, i32, C.POINTER(vp))
+    f("sb200_signals_create_raw", i32, vp, u32, u32, i32, C.POINTER(vp))
+    f("sb200_signals_read", i32, vp, u32, u32, vp)
     f("sb200_signals_destroy", None, vp)
     f("sb200_bm25_topk_batch", i32, vp, C.POINTER(Bm25Batch), vp, vp, vp, C.POINTER(Bm25Stats))
     f("sb200_bm25_topk", i32, vp, vp, vp, u32, vp, i32, u32, vp, vp, vp)

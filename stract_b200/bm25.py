@@ -233,6 +233,75 @@ class SignalTable:
             pass
 
 
+# The numeric signals of CoreSignalEnum in declaration order (core/src/ranking/signals/mod.rs:206-218) with the transform
+# their `compute` applies to the fast-field value (core/src/ranking/signals/core/non_text.rs), the element type of the column
+# and the default coefficient.
+NUM_IDENTITY, NUM_RANK, NUM_BOOL, NUM_BOOL_NOT, NUM_INVERSE, NUM_FETCH_TIME, NUM_UPDATE_TIME, NUM_LINK_DENSITY, NUM_REGION = range(9)
+NUM_U64, NUM_F64, NUM_BOOL8 = 0, 1, 2
+NUMERIC_SIGNALS = [
+    # name,               transform,        dtype,     default coefficient
+    ("HostCentrality",     NUM_IDENTITY,     NUM_F64,   2.0),
+    ("HostCentralityRank", NUM_RANK,         NUM_U64,   0.02),
+    ("PageCentrality",     NUM_IDENTITY,     NUM_F64,   2.0),
+    ("PageCentralityRank", NUM_RANK,         NUM_U64,   0.02),
+    ("IsHomepage",         NUM_BOOL,         NUM_BOOL8, 0.01),
+    ("FetchTimeMs",        NUM_FETCH_TIME,   NUM_U64,   0.001),
+    ("UpdateTimestamp",    NUM_UPDATE_TIME,  NUM_U64,   0.75),
+    ("TrackerScore",       NUM_INVERSE,      NUM_U64,   0.1),
+    ("Region",             NUM_REGION,       NUM_U64,   0.15),
+    ("UrlDigits",          NUM_INVERSE,      NUM_U64,   0.01),
+    ("UrlSlashes",         NUM_INVERSE,      NUM_U64,   0.1),
+    ("LinkDensity",        NUM_LINK_DENSITY, NUM_F64,   0.0),
+    ("HasAds",             NUM_BOOL_NOT,     NUM_BOOL8, 0.01),
+]
+
+
+class RawSignalTable(SignalTable):
+    """The numeric-signal score table built by the library from the RAW fast-field columns (sb200_signals_create_raw).
+
+    `columns` = {signal name: raw column} (u64 / f64 / bool arrays as in NUMERIC_SIGNALS); the table's column order is
+    CoreSignalEnum order.  `current_timestamp` feeds UpdateTimestamp (SignalComputer::set_current_timestamp), `region_count`
+    = (counts per region id, total) feeds Region (RegionCount::score), `selected_region` the query's region boost.
+    `numeric` is the [(name, column, default coefficient)] list SignalComputeOrder / MultiFieldSignalComputer take."""
+
+    def __init__(self, columns, current_timestamp=None, region_count=None, selected_region=None, device=0):
+        self._L = lib()
+        self._h = C.c_void_p()
+        names = [n for n, _, _, _ in NUMERIC_SIGNALS if n in columns]
+        unknown = set(columns) - set(names)
+        if unknown:
+            raise KeyError(f"not numeric CoreSignals: {sorted(unknown)}")
+        np_dt = {NUM_U64: np.uint64, NUM_F64: np.float64, NUM_BOOL8: np.uint8}
+        arr = (B.NumericColumn * max(len(names), 1))()
+        keep, self.numeric = [], []
+        lut = None
+        if region_count is not None:
+            counts, total = region_count
+            lut = np.array([0.0 if c is None else float(c) / float(total) for c in counts], np.float64)   # count as f64 / total as f64
+        for i, n in enumerate(names):
+            _, kind, dt, coef = next(e for e in NUMERIC_SIGNALS if e[0] == n)
+            raw = np.ascontiguousarray(columns[n], np_dt[dt])
+            keep.append(raw)
+            arr[i].kind, arr[i].dtype, arr[i].raw = kind, dt, raw.ctypes.data
+            if kind == NUM_UPDATE_TIME:
+                arr[i].p0 = float(current_timestamp or 0)
+            if kind == NUM_REGION and lut is not None:
+                arr[i].lut, arr[i].lut_len = lut.ctypes.data, lut.size
+                if selected_region is not None:
+                    arr[i].p0, arr[i].p1 = float(selected_region), 1.0
+            self.numeric.append((n, i, coef))
+        self.n_cols = len(names)
+        self.max_doc = int(keep[0].size) if keep else 0
+        assert all(k.size == self.max_doc for k in keep)
+        check(self._L.sb200_signals_create_raw(arr, self.n_cols, self.max_doc, device, C.byref(self._h)))
+
+    def read(self, first_doc=0, n_docs=None):
+        n = self.max_doc - first_doc if n_docs is None else n_docs
+        out = np.zeros((n, self.n_cols), np.float64)
+        check(self._L.sb200_signals_read(self._h, first_doc, n, out.ctypes.data))
+        return out
+
+
 def score_rank(rank):
     """non_text.rs:50-59: (10 - log_8(1 + rank)).max(0) with f64::log(base) = ln(x)/ln(base)."""
     return max(10.0 - math.log(1.0 + float(rank)) / math.log(8.0), 0.0)

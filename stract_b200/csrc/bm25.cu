@@ -570,6 +570,46 @@ __global__ void k_interleave_signals(const double* const* cols, uint32_t n_cols,
   rows[i] = cols[c][d];
 }
 
+// The numeric CoreSignals' value -> score transforms (core/src/ranking/signals/core/non_text.rs:25-101 and the per-signal
+// `compute`), one thread per document, written straight into column `c` of the row-major table.  Every expression is the
+// reference's f64 expression with explicitly rounded operations; score_rank (a libm `ln`) is not here -- see the host side.
+__global__ void k_numeric_score(uint32_t kind, uint32_t dtype, const void* __restrict__ raw, uint32_t max_doc, double p0, double p1,
+                                const double* __restrict__ lut, uint32_t lut_len, double* __restrict__ rows, uint32_t n_cols, uint32_t c) {
+  const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= max_doc) return;
+  unsigned long long u = 0; double f = 0.0;
+  if (dtype == SB200_NUM_F64) f = ((const double*)raw)[d];
+  else if (dtype == SB200_NUM_U64) { u = ((const unsigned long long*)raw)[d]; f = __ull2double_rn(u); }
+  else { u = ((const uint8_t*)raw)[d] ? 1ull : 0ull; f = (double)u; }
+  double s = 0.0;
+  switch (kind) {
+    case SB200_NUM_IDENTITY: s = f; break;                                                   // HostCentrality, PageCentrality (:117-155, :203-241)
+    case SB200_NUM_BOOL: s = u ? 1.0 : 0.0; break;                                           // IsHomepage (:289-332)
+    case SB200_NUM_BOOL_NOT: s = u ? 0.0 : 1.0; break;                                       // HasAds: score = !has_ads (:730-771)
+    case SB200_NUM_INVERSE: s = __ddiv_rn(1.0, __dadd_rn(f, 1.0)); break;                    // score_trackers / digits / slashes (:61-74)
+    case SB200_NUM_FETCH_TIME: s = u >= 1000ull ? 0.0 : __ddiv_rn(1.0, __dadd_rn(f, 1.0)); break;   // fetch_time_ms_cache (computer/mod.rs:257-259)
+    case SB200_NUM_UPDATE_TIME: {                                                            // score_timestamp (:25-42) over update_time_cache
+      const unsigned long long now = (unsigned long long)p0;                                 //   (computer/mod.rs:261-265), 72 / (hours + 72)
+      if (u < now) {
+        unsigned long long secs = now - u; if (secs < 1ull) secs = 1ull;
+        const unsigned long long hours = secs / 3600ull;
+        if (hours < 3ull * 365ull * 24ull) s = __ddiv_rn(72.0, __dadd_rn(__ull2double_rn(hours), 72.0));
+      }
+      break;
+    }
+    case SB200_NUM_LINK_DENSITY: s = f > 0.5 ? 0.0 : __dsub_rn(1.0, f); break;               // score_link_density (:76-83)
+    case SB200_NUM_REGION: {                                                                 // score_region (:85-101): boost + count / total
+      if (lut) {                                                                             //   lut absent = no RegionCount: the signal is 0
+        const double boost = (p1 != 0.0 && u == (unsigned long long)p0) ? 50.0 : 0.0;         //   p1: a region other than All is selected, p0: its id
+        s = __dadd_rn(boost, u < lut_len ? lut[u] : 0.0);
+      }
+      break;
+    }
+    default: break;
+  }
+  rows[(size_t)d * n_cols + c] = s;
+}
+
 static size_t smem_bytes(uint32_t cap) {
   return (size_t)cap * 12 + sizeof(TermState) * MAXT + MAXT * 128 * 8 + 344 * 4 + 256 * 4 + 256 * 4 + 40 * 4;
 }
@@ -1346,6 +1386,76 @@ int sb200_signals_create(const double* const* columns, uint32_t n_cols, uint32_t
   const int rc = body();
   if (rc != SB200_OK) { delete sg; return rc; }
   *out = sg;
+  return SB200_OK;
+}
+int sb200_signals_create_raw(const sb200_numeric_column* cols, uint32_t n_cols, uint32_t max_doc, int device, sb200_signals** out) {
+  if (!out) SB_FAIL(SB200_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (n_cols && !cols) SB_FAIL(SB200_EINVAL, "cols is NULL");
+  if (n_cols > 64) SB_FAIL(SB200_ERANGE, "at most 64 signal columns");
+  SB_CUDA(cudaSetDevice(device));
+  sb200_signals* sg = new (std::nothrow) sb200_signals();
+  if (!sg) SB_FAIL(SB200_ENOMEM, "host allocation failed");
+  sg->device = device; sg->n_cols = n_cols; sg->max_doc = max_doc;
+  auto body = [&]() -> int {
+    if (!n_cols || !max_doc) return SB200_OK;
+    SB_TRY(sg->rows.alloc((size_t)max_doc * n_cols));
+    for (uint32_t c = 0; c < n_cols; c++) {
+      const sb200_numeric_column& col = cols[c];
+      if (!col.raw) SB_FAIL(SB200_EINVAL, "column %u: raw is NULL", c);
+      if (col.dtype > SB200_NUM_BOOL8) SB_FAIL(SB200_EINVAL, "column %u: unknown dtype %u", c, col.dtype);
+      if (col.kind > SB200_NUM_REGION) SB_FAIL(SB200_EINVAL, "column %u: unknown transform %u", c, col.kind);
+      const size_t esz = col.dtype == SB200_NUM_BOOL8 ? 1 : 8;
+      DevBuf<uint8_t> d_raw; DevBuf<double> d_lut;
+      if (col.kind == SB200_NUM_RANK) {
+        // score_rank = (10 - (1 + rank).log(8)).max(0) (non_text.rs:50-59), f64::log(base) = ln(x) / ln(base).  `ln` is the host
+        // C library's (as for a Rust binary on the same machine); no device `log` is bit-identical to it, so this one transform
+        // is evaluated on the host at open time and only the finished column crosses PCIe.
+        if (col.dtype != SB200_NUM_U64) SB_FAIL(SB200_EINVAL, "column %u: score_rank reads a u64 column", c);
+        std::vector<uint64_t> h_raw;
+        const uint64_t* r = (const uint64_t*)col.raw;
+        if (is_device_ptr(col.raw)) { h_raw.resize(max_doc); SB_CUDA(cudaMemcpy(h_raw.data(), col.raw, (size_t)max_doc * 8, cudaMemcpyDeviceToHost)); r = h_raw.data(); }
+        std::vector<double> sc(max_doc);
+        const double ln8 = log(8.0);
+        for (uint32_t d = 0; d < max_doc; d++) { const double v = 10.0 - log(1.0 + (double)r[d]) / ln8; sc[d] = v > 0.0 ? v : 0.0; }
+        SB_TRY(d_raw.alloc((size_t)max_doc * 8));
+        SB_CUDA(cudaMemcpy(d_raw.p, sc.data(), (size_t)max_doc * 8, cudaMemcpyHostToDevice));
+        SB_LAUNCH(k_numeric_score, div_up(max_doc, 256), 256, 0, 0, (uint32_t)SB200_NUM_IDENTITY, (uint32_t)SB200_NUM_F64, (const void*)d_raw.p, max_doc, 0.0, 0.0,
+                  (const double*)nullptr, 0u, sg->rows.p, n_cols, c);
+        SB_CHECK_LAUNCH();
+        SB_CUDA(cudaDeviceSynchronize());
+        continue;
+      }
+      const void* raw = col.raw;
+      if (!is_device_ptr(col.raw)) {
+        SB_TRY(d_raw.alloc((size_t)max_doc * esz));
+        SB_CUDA(cudaMemcpy(d_raw.p, col.raw, (size_t)max_doc * esz, cudaMemcpyHostToDevice));
+        raw = d_raw.p;
+      }
+      const double* lut = nullptr;
+      if (col.kind == SB200_NUM_REGION && col.lut && col.lut_len) {
+        SB_TRY(d_lut.alloc(col.lut_len));
+        SB_CUDA(cudaMemcpy(d_lut.p, col.lut, (size_t)col.lut_len * 8, cudaMemcpyDefault));
+        lut = d_lut.p;
+      }
+      SB_LAUNCH(k_numeric_score, div_up(max_doc, 256), 256, 0, 0, col.kind, col.dtype, raw, max_doc, col.p0, col.p1, lut, lut ? col.lut_len : 0u,
+                sg->rows.p, n_cols, c);
+      SB_CHECK_LAUNCH();
+      SB_CUDA(cudaDeviceSynchronize());   // the staging copies of this column are released at the end of the iteration
+    }
+    return SB200_OK;
+  };
+  const int rc = body();
+  if (rc != SB200_OK) { delete sg; return rc; }
+  *out = sg;
+  return SB200_OK;
+}
+int sb200_signals_read(const sb200_signals* s, uint32_t first_doc, uint32_t n_docs, double* rows_out) {
+  if (!s || (!rows_out && n_docs)) SB_FAIL(SB200_EINVAL, "NULL argument");
+  if ((uint64_t)first_doc + n_docs > s->max_doc) SB_FAIL(SB200_ERANGE, "docs [%u, +%u) outside the table of %u", first_doc, n_docs, s->max_doc);
+  SB_CUDA(cudaSetDevice(s->device));
+  if (n_docs && s->n_cols)
+    SB_CUDA(cudaMemcpy(rows_out, s->rows.p + (size_t)first_doc * s->n_cols, (size_t)n_docs * s->n_cols * 8, cudaMemcpyDeviceToHost));
   return SB200_OK;
 }
 void sb200_signals_destroy(sb200_signals* s) {

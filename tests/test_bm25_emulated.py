@@ -104,6 +104,7 @@ def test_multi_field_signals_against_oracle(emulated):
     import test_multi_signal_gpu as M
     M.test_multi_field_signals_bit_exact()
     M.test_optic_rule_boosts_bit_exact()
+    M.test_all_numeric_signals_from_raw_columns_in_the_program()
     M.test_signal_compute_order_mirror()
 
 
@@ -113,3 +114,10 @@ def test_block_wand_replay_against_oracle(emulated):
 
 def test_packed_result_copy(emulated, monkeypatch):
     emulated.test_packed_result_copy_equals_dense(monkeypatch)
+
+
+def test_numeric_signal_transforms_against_oracle(emulated):
+    import test_numeric_signals_gpu as N
+    N.test_every_numeric_signal_bit_exact(N.NOW, ([120, None, 30, 0, 77, 1, 5], 233), 2)
+    N.test_every_numeric_signal_bit_exact(None, None, None)
+    N.test_subset_of_signals_in_enum_order()

@@ -102,6 +102,25 @@ def test_multi_field_signals_bit_exact():
     check_against_oracle(comp, pairs, cols, sf, st, 100, numeric)
 
 
+def test_all_numeric_signals_from_raw_columns_in_the_program():
+    """The 13 numeric CoreSignals built from raw fast-field columns (sb200_signals_create_raw) behind the text signals, default
+    coefficients: totals bit-equal to the oracle program over the oracle's own transforms of the same raw columns."""
+    import test_numeric_signals_gpu as N
+    from stract_b200.bm25 import RawSignalTable
+    pairs, dfs = make_segment(seed=33)
+    max_doc = 30_000
+    raw = N.raw_columns(max_doc, seed=4)
+    rc = ([400, 10, None, 3, 90], 503)
+    tab = RawSignalTable(raw, current_timestamp=N.NOW, region_count=rc, selected_region=3)
+    comp = MultiFieldSignalComputer({n: pairs[n][1] for n in FIELDS}, ENABLED, tab, tab.numeric)
+    assert [e[0] for e in comp.order.entries][-13:] == [n for n, _, _ in tab.numeric]
+    cols = [N.want_column(name, raw[name], N.NOW, rc, 3) for name, _, _ in tab.numeric]
+    rng = np.random.default_rng(8)
+    sf, st = random_queries(rng, dfs, comp.names, 16, 8)
+    check_against_oracle(comp, pairs, cols, sf, st, 120, None)
+    tab.close()
+
+
 def test_optic_rule_boosts_bit_exact():
     """SignalComputer::boosts (computer/mod.rs:471-497): rule docsets as probe-only slots, boosts and downranks, the
     1/(1+diff) branch, a rule that matches nothing, documents that only a rule holds (never candidates)."""
