@@ -381,6 +381,10 @@ def main():
     L = lib()
     peaks, peak_src = _peaks()
     full_size = args.nodes == 50_000_000 and args.edges == 1_000_000_000 and args.scale == 26
+    if os.environ.get("SB200_BENCH_FINGERPRINT"):   # flow tests: compare N > 1 runs of another graph with this fingerprint file
+        global GOLDEN_C2
+        GOLDEN_C2 = os.environ["SB200_BENCH_FINGERPRINT"]
+        full_size = True
 
     nodes, edges = args.nodes, args.edges
     tg = time.perf_counter()
@@ -457,13 +461,89 @@ def main():
     else:
         # configs[2]: the same graph, destination rows partitioned over `world` GPUs
         from stract_b200.webgraph import run_sharded_loop
-        dg = DeviceGraph(graph, device=local_rank, rank=rank, world_size=world)
-        exchange_kind = "nccl"
+        # ---- e2e at N > 1: every rank holds ONE contiguous shard of the edge stream in page-locked host memory (as the
+        #      reference's workers each hold one webgraph shard); the timed call copies it over the rank's own PCIe link,
+        #      all-gathers the stream over NVLink, stages (replicated, DESIGN section 8), exchanges the IPC blobs, runs the
+        #      sharded loop and reads back its owned share.  It runs after the kernel-loop measurement, except when that one
+        #      binds torch symmetric memory (8 GPUs): then it runs first, the order (CUDA IPC mappings, then symmetric memory)
+        #      the 8-GPU sweep exercised.
+        e2e_state = {"chk": None}
+
+        def run_e2e_n(free_inputs):
+            nonlocal cols, graph
+            if args.no_e2e or args.no_p2p:
+                return
+            import psutil
+            from stract_b200.webgraph import ShardedHarmonicCentrality, shard_bounds
+            need = edges * 40
+            avail = psutil.virtual_memory().available
+            ok = torch.tensor([1 if avail > need * 1.3 else 0], device=dev, dtype=torch.int64)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                result["e2e_n"] = {"skipped": f"host RAM {avail / 2**30:.0f} GiB < 1.3 x {need / 2**30:.0f} GiB (the page-locked shards of the edge stream)"}
+                return
+            try:
+                s_lo, s_hi = shard_bounds(edges, rank, world)
+                hostc = []
+                for cc in cols:
+                    hh = torch.empty((s_hi - s_lo,), dtype=cc.dtype, pin_memory=True)
+                    hh.copy_(cc[s_lo:s_hi])
+                    hostc.append(hh)
+                hgraph_n = Webgraph.from_arrays(*hostc)
+                if free_inputs:
+                    cols = graph = None
+                torch.cuda.empty_cache()   # the timed call needs room for the gathered stream next to the staging temporaries
+                per, d2h_n, its, kept, phases_n = [], 0, 0, 0, []
+                n_warm = 2   # device memory pools, NCCL channels and the page-locked result blocks reach steady state
+                for step in range(n_warm + max(2, min(args.e2e_steps, 3))):
+                    barrier()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    rr = ShardedHarmonicCentrality.calculate(hgraph_n, local_rank, rank, world, exchange="p2p", ingest="shards")
+                    chk = float(rr.values[:1024].sum())  # noqa: F841
+                    e1.record(); torch.cuda.synchronize()
+                    t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+                    dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+                    nb = torch.tensor([len(rr.values) * 24, _i64(result_checksum(rr.ids_lo, rr.ids_hi, rr.values))], device=dev, dtype=torch.int64)
+                    dist.all_reduce(nb)
+                    if step >= n_warm:
+                        per.append(float(t_ms.item())); d2h_n = int(nb[0].item()); its = rr.iterations
+                        kept = int(rr.info["n_edges_kept"])
+                        phases_n.append(rr.info.get("phase_ms"))
+                        e2e_state["chk"] = int(nb[1].item()) & ((1 << 64) - 1)
+                    del rr
+                result["e2e_n"] = {"value": kept * its * len(per) / (sum(per) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": edges * 40,
+                                   "d2h_bytes_per_step": d2h_n, "ms_per_step": sum(per) / len(per), "steps": len(per), "pinned_host": True,
+                                   "ms_min_median_max": [round(min(per), 1), round(float(np.median(per)), 1), round(max(per), 1)],
+                                   "rank0_phase_ms": phases_n,
+                                   "note": f"max over ranks per step; each of the {world} ranks copies its 1/{world} shard of the edge stream from page-locked "
+                                           "host memory over its own PCIe link, an NCCL all-gather over NVLink assembles the stream on every GPU, "
+                                           "then (replicated) staging + CUDA IPC set-up + sharded loop (peer stores + device-side barrier) + owned results to the host",
+                                   "exchange": "p2p (CUDA IPC): the end-to-end call always uses this transport"}
+                del hostc, hgraph_n
+                torch.cuda.empty_cache()
+            except Exception as ex:  # noqa: BLE001  (the kernel-loop line must survive a failing end-to-end leg)
+                result["e2e_n"] = {"error": repr(ex)[:400]}
+
+        def merge_e2e_parity():
+            c2 = parity.get("c2")
+            if gold and e2e_state["chk"] is not None and isinstance(c2, dict) and isinstance(c2.get("equal"), dict):
+                c2["equal"]["e2e_result_checksum"] = e2e_state["chk"] == gold["result_checksum"]
+                c2["green"] = all(c2["equal"].values())
+
+        gold = None
         want = args.exchange
         if want == "auto":
             want = "multicast" if world >= 8 else "p2p"
         if args.no_p2p:
             want = "nccl"
+        if args.sweep:
+            want = "p2p"   # the sweep walks the CUDA IPC variants on this handle, then binds symmetric memory on a fresh one
+        e2e_first = want in ("symm", "multicast") and not args.sweep
+        if e2e_first:
+            run_e2e_n(False)
+        dg = DeviceGraph(graph, device=local_rank, rank=rank, world_size=world)
+        exchange_kind = "nccl"
         if want in ("symm", "multicast"):
             kind, ok = None, 0
             try:
@@ -616,62 +696,9 @@ def main():
                       clocks=clocks, roofline=roofline_n, launches=int(nl.item()), kernels=kernels_n or [], per_iter=allr)
         dg.close()
         dg = None
-        # ---- e2e at N > 1: every rank holds ONE contiguous shard of the edge stream in page-locked host memory (as the
-        #      reference's workers each hold one webgraph shard); the timed call copies it over the rank's own PCIe link,
-        #      all-gathers the stream over NVLink, stages (replicated, DESIGN section 8), exchanges the IPC blobs, runs the
-        #      sharded loop and reads back its owned share
-        if not args.no_e2e and exchange_kind != "nccl":
-            import psutil
-            from stract_b200.webgraph import ShardedHarmonicCentrality, shard_bounds
-            need = edges * 40
-            avail = psutil.virtual_memory().available
-            ok = torch.tensor([1 if avail > need * 1.3 else 0], device=dev, dtype=torch.int64)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if int(ok.item()) == 0:
-                result["e2e_n"] = {"skipped": f"host RAM {avail / 2**30:.0f} GiB < 1.3 x {need / 2**30:.0f} GiB (the page-locked shards of the edge stream)"}
-            else:
-                try:
-                    s_lo, s_hi = shard_bounds(edges, rank, world)
-                    hostc = []
-                    for cc in cols:
-                        hh = torch.empty((s_hi - s_lo,), dtype=cc.dtype, pin_memory=True)
-                        hh.copy_(cc[s_lo:s_hi])
-                        hostc.append(hh)
-                    hgraph_n = Webgraph.from_arrays(*hostc)
-                    cols = graph = None
-                    torch.cuda.empty_cache()   # the timed call needs room for the gathered stream next to the staging temporaries
-                    per, d2h_n, its, e2e_chk, phases_n = [], 0, 0, None, []
-                    n_warm = 2   # device memory pools, NCCL channels and the page-locked result blocks reach steady state
-                    for step in range(n_warm + max(2, min(args.e2e_steps, 3))):
-                        barrier()
-                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                        e0.record()
-                        rr = ShardedHarmonicCentrality.calculate(hgraph_n, local_rank, rank, world, exchange="p2p", ingest="shards")
-                        chk = float(rr.values[:1024].sum())  # noqa: F841
-                        e1.record(); torch.cuda.synchronize()
-                        t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-                        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-                        nb = torch.tensor([len(rr.values) * 24, _i64(result_checksum(rr.ids_lo, rr.ids_hi, rr.values))], device=dev, dtype=torch.int64)
-                        dist.all_reduce(nb)
-                        if step >= n_warm:
-                            per.append(float(t_ms.item())); d2h_n = int(nb[0].item()); its = rr.iterations
-                            phases_n.append(rr.info.get("phase_ms"))
-                            e2e_chk = int(nb[1].item()) & ((1 << 64) - 1)
-                        del rr
-                    if gold:
-                        parity["c2"]["equal"]["e2e_result_checksum"] = e2e_chk == gold["result_checksum"]
-                        parity["c2"]["green"] = all(parity["c2"]["equal"].values())
-                    result["e2e_n"] = {"value": E * its * len(per) / (sum(per) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": edges * 40,
-                                       "d2h_bytes_per_step": d2h_n, "ms_per_step": sum(per) / len(per), "steps": len(per), "pinned_host": True,
-                                       "ms_min_median_max": [round(min(per), 1), round(float(np.median(per)), 1), round(max(per), 1)],
-                                       "rank0_phase_ms": phases_n,
-                                       "note": f"max over ranks per step; each of the {world} ranks copies its 1/{world} shard of the edge stream from page-locked "
-                                               "host memory over its own PCIe link, an NCCL all-gather over NVLink assembles the stream on every GPU, "
-                                               "then (replicated) staging + CUDA IPC set-up + sharded loop (peer stores + device-side barrier) + owned results to the host",
-                                       "exchange": "p2p (CUDA IPC) -- the end-to-end call always uses this transport; the kernel-loop value above used: " + str(exchange_kind)}
-                    del hostc, hgraph_n
-                except Exception as ex:  # noqa: BLE001  (the kernel-loop line above must survive a failing end-to-end leg)
-                    result["e2e_n"] = {"error": repr(ex)[:400]}
+        if not e2e_first:
+            run_e2e_n(True)
+        merge_e2e_parity()
 
     # ---- e2e: the C-ABI call sequence from HOST buffers (N = 1) ----------------------------------
     e2e, host = None, None
