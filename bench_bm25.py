@@ -93,7 +93,9 @@ def run_and(device, peaks, max_doc=10_000_000, df_scale=2.0e6, n_queries=10_000,
            "kernel_ms_per_batch": kern, "postings_per_batch": postings, "docs_scored": st["docs_scored"],
            "blocks_decoded": st["blocks_decoded"],
            "e2e": {"value": postings / (e2e * 1e-3), "unit": "postings/s", "ms_per_batch": e2e,
-                   "h2d_bytes_per_step": int(terms.size * 8 + 1024), "d2h_bytes_per_step": int(n_queries * k * 8 + n_queries * 4)},
+                   "h2d_bytes_per_step": int(terms.size * 8 + 1024),
+                   # sparse result tables cross PCIe packed (counts, then only the filled entries) when under half of the dense table is filled
+                   "d2h_bytes_per_step": int(n_queries * 4 + (8 * int(n.sum()) if 2 * int(n.sum()) < n_queries * k else n_queries * k * 8))},
            "roofline": {"bound": "hbm", "kernel": "k_and3 + k_and3_select", "achieved": alg / (kern * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                         "unit": "GB/s", "frac": alg / (kern * 1e-3) / 1e9 / peaks["hbm_gbs"], "alg_bytes_per_launch": alg, **_ncu("k_and3", max_doc == 10_000_000)},
            "index_hbm_bytes": seg.info()["hbm_bytes"], "gen_s": round(gen_s, 1), "stage_ms": seg.info()["stage_ms"]}
