@@ -559,19 +559,29 @@ class SignalComputeOrder:
 class MultiFieldSignalComputer:
     """The recall-stage SignalComputer over several text fields of one segment (core/src/ranking/computer/mod.rs:300-389,
     order.rs): `fields` = {TextField name: SegmentReader} in TextFieldEnum order, every reader opened over the same docs.
-    `coefficients` overrides the default coefficient per signal name (SignalComputer::coefficient)."""
+    `coefficients` = the query's SignalCoefficients {signal name: coefficient} (`has_query=False`: a SignalComputer built
+    without a query), `linear_model` = LinearRegression weights {signal name: weight} (set_linear_model) -- see `coefficient`."""
 
-    def __init__(self, fields, enabled, signals=None, numeric=(), coefficients=None, k1=K1, b=B_):
+    def __init__(self, fields, enabled, signals=None, numeric=(), coefficients=None, k1=K1, b=B_, linear_model=None, has_query=True):
         self.names = sorted(fields.keys(), key=TEXT_FIELD_ORDER.index)   # EnumMap<TextFieldEnum, TextFieldData> order
         self.readers = [fields[n] for n in self.names]
         self.signals = signals
         self.order = SignalComputeOrder(set(enabled), numeric)
         self.coefficients = dict(coefficients or {})
+        self.linear_model = None if linear_model is None else dict(linear_model)
+        self.has_query = bool(has_query)
         self.k1, self.b = np.float32(k1), np.float32(b)
         self._L = lib()
 
     def coefficient(self, name, default):
-        return float(self.coefficients.get(name, default))
+        """SignalComputer::coefficient (computer/mod.rs:511-521): with a query, its SignalCoefficients decide -- the entry or
+        the signal's default (signals/mod.rs:430-435) -- and the linear model is never asked (`.map(..)` on a Some never
+        reaches the `or_else`); without a query the linear model's weight for the signal, else the default."""
+        if self.has_query:
+            return float(self.coefficients.get(name, default))
+        if self.linear_model is not None and name in self.linear_model:
+            return float(self.linear_model[name])
+        return float(default)
 
     def field_coefficient(self, field):
         """TextFieldData.signal_coefficient (mod.rs:372): prepare_textfields walks CoreSignalEnum::all() and INSERTS the

@@ -106,6 +106,7 @@ def test_multi_field_signals_against_oracle(emulated):
     M.test_optic_rule_boosts_bit_exact()
     M.test_all_numeric_signals_from_raw_columns_in_the_program()
     M.test_signal_compute_order_mirror()
+    M.test_coefficient_precedence_mirror()
 
 
 def test_block_wand_replay_against_oracle(emulated):

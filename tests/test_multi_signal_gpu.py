@@ -153,6 +153,24 @@ def test_optic_rule_boosts_bit_exact():
     assert np.array_equal(d0, d1) and np.array_equal(t0, t1) and np.array_equal(n0, n1)
 
 
+def test_coefficient_precedence_mirror():
+    """SignalComputer::coefficient: query coefficients (entry or default) shadow the linear model entirely; without a query
+    the model's weight, else the default.  Host logic only (no kernel launch)."""
+    class _R:   # a reader stand-in: the constructor only stores it
+        pass
+    mk = lambda **kw: MultiFieldSignalComputer({"Title": _R()}, {"Bm25Title"}, **kw)
+    lm = {"Bm25Title": 0.5, "TitleCoverage": 0.25}
+    c = mk(coefficients={"Bm25Title": 0.02}, linear_model=lm)
+    assert c.coefficient("Bm25Title", 0.0063) == 0.02 and c.coefficient("TitleCoverage", 0.01) == 0.01     # model ignored
+    c = mk(linear_model=lm, has_query=False)
+    assert c.coefficient("Bm25Title", 0.0063) == 0.5 and c.coefficient("Bm25F", 0.1) == 0.1
+    c = mk(has_query=False)
+    assert c.coefficient("Bm25Title", 0.0063) == 0.0063
+    # TextFieldData.signal_coefficient follows the same rule: Title's last signal is TitleCoverage
+    assert mk(linear_model=lm, has_query=False).field_coefficient("Title") == 0.25
+    assert mk(coefficients={"TitleCoverage": 0.7}, linear_model=lm).field_coefficient("Title") == 0.7
+
+
 def test_signal_compute_order_mirror():
     """SignalComputeOrder::new and the signal_coefficient quirk of prepare_textfields, host side only."""
     o = SignalComputeOrder(ENABLED | {"Bm25CleanBodyBigrams"}, numeric=[("HostCentrality", 0, 1.0)])
