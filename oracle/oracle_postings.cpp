@@ -921,6 +921,7 @@ ORC_API uint64_t orc_bitpack(const uint64_t* vals, const uint8_t* bits, uint32_t
 ORC_API uint64_t orc_extract_bits(const uint8_t* data, uint64_t len, uint64_t addr_bits, uint8_t nb) { return tis::extract_bits(data, (size_t)len, (size_t)addr_bits, nb); }
 
 // ---------------------------------------------------------------- numeric signals -------------
+// PARITY UNPINNED: the reference has no test vectors for these transforms; tests/test_oracle_numeric.py pins hand-derived points.
 // core/src/ranking/signals/core/non_text.rs: the value -> score part of every numeric CoreSignal's `compute`, written the way
 // the reference writes it (one function per transform); `which` names the signal.
 namespace numsig {
