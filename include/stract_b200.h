@@ -243,7 +243,10 @@ SB200_API int sb200_approx_harmonic(sb200_graph* g, const uint64_t* src_lo, cons
  *                 bloom pre-filter over the low 64 id bits says popcount(A & B) / max(ones) < 0.25 (false negatives included);
  *     a liked / disliked node compared with itself scores self_score (1.0 in the reference until set_self_score).
  * in(v) = the unique sources of v's links in the handle's edge set, including v itself if it links to itself.  Ids that are
- * not nodes of the graph have an empty set.  Single-rank handles. */
+ * not nodes of the graph have an empty set.  Single-rank handles.
+ * The reference fills the sets from `HostBacklinksQuery(...).with_limit(512)` and then drops NOFOLLOW edges
+ * (crates/core/src/searcher/api/mod.rs:199-214): stage the handle with skipped_rel_mask = NOFOLLOW for the filter; the 512-edge
+ * limit (the store's own top-docs order) is the caller's to apply to the edge stream -- the handle does not truncate. */
 SB200_API int sb200_inbound_similarity(sb200_graph* g, const uint64_t* liked_lo, const uint64_t* liked_hi, uint32_t n_liked,
                                        const uint64_t* disliked_lo, const uint64_t* disliked_hi, uint32_t n_disliked,
                                        const uint64_t* cand_lo, const uint64_t* cand_hi, uint32_t n_cand, int normalized,

@@ -104,3 +104,61 @@ def test_inbound_similarity_matches_scorer():
         assert nonzero > 200
     finally:
         dg.close()
+
+
+def _ids(n, seed=77):
+    rng = np.random.default_rng(seed)
+    lo = rng.integers(1, 2 ** 63, n, dtype=np.uint64); hi = rng.integers(1, 2 ** 63, n, dtype=np.uint64)
+    return [(int(h) << 64) | int(l) for l, h in zip(lo, hi)]
+
+
+def _graph_from(edges, rel=None):
+    fl = np.array([f & ((1 << 64) - 1) for f, _ in edges], np.uint64); fh = np.array([f >> 64 for f, _ in edges], np.uint64)
+    tl = np.array([t & ((1 << 64) - 1) for _, t in edges], np.uint64); th = np.array([t >> 64 for _, t in edges], np.uint64)
+    r = np.zeros(len(edges), np.uint64) if rel is None else np.array(rel, np.uint64)
+    return fl, fh, tl, th, r
+
+
+def _scores_both(arrays, skip, liked, disliked, cands, normalized=False):
+    """(device scores, oracle scores) for the same handle-shaped input"""
+    ids_lo, ids_hi, fr, tr = oracle.graph_links(*arrays, skip_mask=skip)
+    pos = {(int(h) << 64) | int(l): i for i, (l, h) in enumerate(zip(ids_lo, ids_hi))}
+    rk = lambda xs: np.array([pos.get(x, 0xFFFFFFFF) for x in xs], np.uint32)
+    want = oracle.inbound_similarity(ids_lo, ids_hi, fr, tr, rk(liked), rk(disliked), rk(cands), normalized)
+    dg = DeviceGraph(Webgraph.from_arrays(*arrays), skipped_rel=skip)
+    try:
+        got = dg.inbound_similarity(liked, disliked, cands, normalized)
+    finally:
+        dg.close()
+    assert got.tobytes() == want.tobytes()
+    return got
+
+
+def test_inbound_similarity_reference_scenarios():
+    """The reference's own tests for this path, on the oracle AND the device: `it_favors_liked_hosts`
+    (ranking/inbound_similarity.rs:168-236), the BitVec cases `simple` / `zero_sim` / `empty_sim` / `low_sim`
+    (ranking/bitvec_similarity.rs:222-295, sets given as in-neighbour sets of two nodes) and `test_ignores_no_follow` (:297-330)."""
+    from stract_b200.webgraph import RelFlags
+    a, b, c, d, e, z = _ids(6)
+    edges = [(a, b), (c, d), (a, e), (z, a), (z, b), (z, c), (z, d), (z, d), (z, e)]
+    s = _scores_both(_graph_from(edges), 0, [b], [], [e, d])
+    assert s[0] > s[1]                                             # it_favors_liked_hosts
+    # BitVec cases: node X has in-neighbours = the set a, node Y the set b
+    def bitvec_sim(set_a, set_b, n_nodes):
+        ids = _ids(n_nodes + 2, seed=5)
+        x, y, src = ids[0], ids[1], ids[2:]
+        ed = [(src[i], x) for i in set_a] + [(src[i], y) for i in set_b]
+        ed += [(x, src[0]), (y, src[0])]                             # X and Y are nodes of the graph even with an empty in-neighbour set
+        return _scores_both(_graph_from(ed), 0, [x], [], [y])[0]
+    naive = lambda sa, sb: len(set(sa) & set(sb)) / (np.sqrt(len(sa)) * np.sqrt(len(sb)))
+    sa, sb = list(range(1000, 1010)), list(range(1000, 1008))
+    assert abs(bitvec_sim(sa, sb, 1010) - naive(sa, sb)) < 0.1     # simple
+    assert bitvec_sim([], list(range(300)), 300) == 0.0            # zero_sim (one side empty)
+    assert bitvec_sim([], [], 4) == 0.0                            # empty_sim
+    sa, sb = list(range(3000, 3010)), list(range(0, 3008))
+    assert naive(sa, sb) < 0.05 and abs(bitvec_sim(sa, sb, 3010) - naive(sa, sb)) < 0.1   # low_sim (3 000 instead of 100 000 common in-links)
+    # test_ignores_no_follow: A -nofollow-> B, A -> C: with NOFOLLOW in the handle's skip mask sim(B, C) is 0
+    A, B, C = _ids(3, seed=9)
+    arr = _graph_from([(A, B), (A, C)], rel=[RelFlags.NOFOLLOW, 0])
+    assert _scores_both(arr, RelFlags.NOFOLLOW, [B], [], [C])[0] == 0.0
+    assert _scores_both(arr, 0, [B], [], [C])[0] == 1.0            # and counted when it is not skipped: both have exactly {A}
