@@ -162,3 +162,29 @@ def test_inbound_similarity_reference_scenarios():
     arr = _graph_from([(A, B), (A, C)], rel=[RelFlags.NOFOLLOW, 0])
     assert _scores_both(arr, RelFlags.NOFOLLOW, [B], [], [C])[0] == 0.0
     assert _scores_both(arr, 0, [B], [], [C])[0] == 1.0            # and counted when it is not skipped: both have exactly {A}
+
+
+def test_distances_reference_scenarios():
+    """webgraph/tests.rs:57-137: `distance_calculation`, `nonexisting_node`, `reversed_distance_calculation` on the reference's
+    five-edge test graph (A->B, B->C, A->C, C->A, D->C), oracle and device."""
+    A, B, C, D, E = _ids(5, seed=31)
+    arrays = _graph_from([(A, B), (B, C), (A, C), (C, A), (D, C)])
+    ids_lo, ids_hi, fr, tr = oracle.graph_links(*arrays, skip_mask=0)
+    pos = {(int(h) << 64) | int(l): i for i, (l, h) in enumerate(zip(ids_lo, ids_hi))}
+    dg = DeviceGraph(Webgraph.from_arrays(*arrays), skipped_rel=0)
+    try:
+        def both(src, rev):
+            want = oracle.graph_distances(4, fr, tr, np.array([pos[src]], np.uint32), None, None, rev)[0]
+            got = dg.distances([src], None, 0, rev)[0]
+            assert np.array_equal(got, want)
+            return {k: int(got[pos[k]]) for k in (A, B, C, D)}
+        d = both(D, False)
+        assert (d[C], d[A], d[B]) == (1, 2, 3)                                  # distance_calculation
+        d = both(D, True)
+        assert (d[C], d[A], d[B]) == (255, 255, 255)                            # reversed from D: nothing links to D
+        d = both(A, True)
+        assert (d[C], d[D], d[B]) == (1, 2, 2)                                  # reversed_distance_calculation
+        for rev in (False, True):                                               # nonexisting_node: no distances at all
+            assert (dg.distances([E], None, 0, rev)[0] == 255).all()
+    finally:
+        dg.close()

@@ -64,5 +64,6 @@ def test_graph_searches_against_oracle():
         T.test_approx_harmonic_fixed_sample()
         T.test_inbound_similarity_matches_scorer()
         T.test_inbound_similarity_reference_scenarios()
+        T.test_distances_reference_scenarios()
     finally:
         _lib._LIB = saved
