@@ -294,3 +294,18 @@ def test_term_info_store_reference_kats():
     assert int(store[8:16].view(np.uint64)[0]) == n and meta_len == 47 * ((n + 255) // 256)
     for i in range(n):
         assert term_info_store_get(store, i) == (i, off(i), off(i + 1), off(i) * 3, off(i + 1) * 3), i
+
+
+def test_stract_bm25_idf_scaling_reference_case():
+    """core/src/ranking/bm25.rs:156-177 `test_bm25_idf_scaling`: MultiBm25Weight over ('the': df 98, 'end': df 20) of 100 docs,
+    avg_fieldnorm 1.0; a doc with tf (8, 13) must outscore one with tf (15, 10), fieldnorm id 0 on both."""
+    L = oracle.lib()
+    ws = [stract_bm25_weight(98, 100, 1.0), stract_bm25_weight(20, 100, 1.0)]
+
+    def score(stats):   # MultiBm25Weight::score: f32 sum over the terms in order
+        s = np.float32(0.0)
+        for (idn, tf), (w, cache) in zip(stats, ws):
+            s = np.float32(s + np.float32(L.orc_stract_bm25_score(w, cache, 1.2, idn, tf)))
+        return s
+    high_the, high_end = score([(0, 15), (0, 10)]), score([(0, 8), (0, 13)])
+    assert high_end > high_the
