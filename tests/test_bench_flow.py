@@ -73,3 +73,22 @@ def test_no_e2e_flag(fingerprint_file):
     line = _launch(2, ["--no-e2e"], tmp=fingerprint_file)
     _check(line, 2, "CUDA IPC", e2e_expected=False)
     assert line["e2e"] is None and "e2e_result_checksum" not in line["parity"]["c2"]["equal"]
+
+
+def test_single_gpu_flow_with_full_oracle_parity():
+    """N = 1: kernel loop, the host-buffer e2e leg and the full-graph oracle comparison (`parity.c2`, `cpu_baseline`) -- without
+    the BM25 and C1 legs, which need their own GPU-sized inputs."""
+    subprocess.check_call(["make", "-C", EMU], stdout=subprocess.DEVNULL)
+    env = dict(os.environ, WORLD_SIZE="1", RANK="0", LOCAL_RANK="0", OMP_NUM_THREADS="2")
+    env.pop("SB200_BENCH_FINGERPRINT", None)
+    out = subprocess.run([sys.executable, os.path.join(HERE, "dryrun_bench.py"), "--gpus", "1", "--steps", "1", "--warmup", "0", "--no-bm25", "--no-c1",
+                          "--e2e-steps", "2"], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    c2 = d["parity"]["c2"]
+    assert c2["green"] is True and all(c2["equal"].values()) and c2["equal"]["e2e_result"] is True
+    assert d["n_gpus"] == 1 and d["e2e"]["steps"] == 2 and d["cpu_baseline"]["kind"] == "port" and d["roofline"]["kernel"].startswith("k_pull")
+    for k in ("metric", "value", "unit", "ms_per_step", "higher_is_better", "scaling", "dtype", "data", "config", "clocks", "gpu_launches"):
+        assert k in d
